@@ -1,0 +1,170 @@
+"""TEST INFRASTRUCTURE — ctypes bindings for the oracle libraries.
+
+* ``oracle/_ref/libref_*.so``  — the UNMODIFIED reference compiled as host C++
+  (``oracle/Makefile`` target ``ref``; glue in ``ref_render_tu.cpp`` / ``ref_host_tu.cpp``).
+* ``oracle/librlerc_oracle.so`` — our CPU restatement (``rlerc_oracle.cpp``).
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline /
+``--impl reference`` arm may import this module.  The product package never does.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_DIR = os.path.join(HERE, "_ref")
+
+
+class Vec3f(C.Structure):
+    _fields_ = [("x", C.c_float), ("y", C.c_float), ("z", C.c_float)]
+
+
+class Map4(C.Structure):
+    """R/src/Rle4.h:7-21 on LP64 (32 bytes)."""
+    _fields_ = [("sx", C.c_int), ("sy", C.c_int), ("sz", C.c_int), ("slabs_size", C.c_int),
+                ("map", C.c_void_p), ("slabs", C.c_void_p)]
+
+
+class RayMapGPU(C.Structure):
+    """R/src/RayMap.h:16-54 on LP64 (896 bytes)."""
+    _fields_ = [
+        ("vanishing_point_2d", Vec3f),
+        ("map_line_count", C.c_int),
+        ("map_line_limit", C.c_int),
+        ("rotation", Vec3f),
+        ("position", Vec3f),
+        ("border", C.c_float),
+        ("clip_min", C.c_float),
+        ("clip_max", C.c_float),
+        ("map4_gpu", Map4 * 16),
+        ("nummaps", C.c_int),
+        ("maxres", C.c_int),
+        ("res", C.c_int * 4),
+        ("p4", Vec3f),
+        ("p_2d", Vec3f * 8),
+        ("p_no", Vec3f * 8),
+        ("to3d", C.c_float * 16),
+        ("p_ofs_min", C.c_float * 4),
+        ("p_ofs_max", C.c_float * 4),
+    ]
+
+
+assert C.sizeof(Map4) == 32 and C.sizeof(RayMapGPU) == 896
+
+
+def have_ref():
+    return all(os.path.exists(os.path.join(REF_DIR, n))
+               for n in ("libref_render.so", "libref_render_bench.so", "libref_host.so"))
+
+
+_libs = {}
+
+
+def _load(name):
+    if name not in _libs:
+        path = os.path.join(REF_DIR, name) if name.startswith("libref_") else os.path.join(HERE, name)
+        lib = C.CDLL(path, mode=os.RTLD_LOCAL if hasattr(os, "RTLD_LOCAL") else 0)
+        _libs[name] = lib
+    return _libs[name]
+
+
+def ref_host():
+    lib = _load("libref_host.so")
+    if not getattr(lib, "_typed", False):
+        lib.ref_scene_load.restype = C.c_void_p
+        lib.ref_scene_load.argtypes = [C.c_char_p]
+        lib.ref_scene_save.argtypes = [C.c_void_p, C.c_char_p]
+        lib.ref_scene_free.argtypes = [C.c_void_p]
+        lib.ref_scene_nummaps.argtypes = [C.c_void_p]
+        lib.ref_scene_map4.restype = C.POINTER(Map4)
+        lib.ref_scene_map4.argtypes = [C.c_void_p, C.c_int]
+        lib.ref_tree_new.restype = C.c_void_p
+        lib.ref_tree_new.argtypes = [C.c_int] * 4
+        lib.ref_tree_free.argtypes = [C.c_void_p]
+        lib.ref_tree_set_color.argtypes = [C.c_void_p, C.c_int]
+        lib.ref_tree_sphere.argtypes = [C.c_void_p] + [C.c_float] * 4 + [C.c_int]
+        lib.ref_tree_cube.argtypes = [C.c_void_p] + [C.c_float] * 6
+        for f in (lib.ref_tree_voxel, lib.ref_tree_col1, lib.ref_tree_col2):
+            f.restype = C.c_void_p
+            f.argtypes = [C.c_void_p]
+        lib.ref_compress_all.restype = C.c_void_p
+        lib.ref_compress_all.argtypes = [C.c_void_p]
+        lib.ref_get_ray_map.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float, C.c_int, C.c_void_p]
+        lib._typed = True
+    return lib
+
+
+def ref_render(bench=False):
+    lib = _load("libref_render_bench.so" if bench else "libref_render.so")
+    if not getattr(lib, "_typed", False):
+        lib.ref_render_frame.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                         C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong)]
+        lib._typed = True
+    return lib
+
+
+class RefScene:
+    """A scene held by the reference's RLE4 (Rle4.cpp). Exposes numpy views of map/slabs."""
+
+    def __init__(self, handle):
+        self.h = handle
+        self.lib = ref_host()
+
+    @classmethod
+    def load(cls, path):
+        h = ref_host().ref_scene_load(path.encode())
+        if not h:
+            raise FileNotFoundError(path)
+        return cls(h)
+
+    def save(self, path):
+        self.lib.ref_scene_save(self.h, path.encode())
+
+    @property
+    def nummaps(self):
+        return self.lib.ref_scene_nummaps(self.h)
+
+    def map4(self, m):
+        return self.lib.ref_scene_map4(self.h, m).contents
+
+    def level(self, m, map_words_per_col=2):
+        """(sx, sy, sz, map uint32[sz*sx*w], slabs uint16[slabs_size]) as numpy views."""
+        m4 = self.map4(m)
+        n = m4.sx * m4.sz * map_words_per_col
+        mp = np.ctypeslib.as_array(C.cast(m4.map, C.POINTER(C.c_uint32)), shape=(n,))
+        sl = np.ctypeslib.as_array(C.cast(m4.slabs, C.POINTER(C.c_uint16)), shape=(m4.slabs_size,))
+        return m4.sx, m4.sy, m4.sz, mp, sl
+
+    def fill_raymap(self, rm):
+        """What R/src/main.cpp:277-278 does (for all levels, not just 10)."""
+        for m in range(self.nummaps):
+            src = self.map4(m)
+            C.memmove(C.byref(rm.map4_gpu[m]), C.byref(src), C.sizeof(Map4))
+        rm.nummaps = self.nummaps
+
+    def free(self):
+        if self.h:
+            self.lib.ref_scene_free(self.h)
+            self.h = None
+
+
+def ref_get_ray_map(pos, rot, border, rays_res):
+    rm = RayMapGPU()
+    p = (C.c_float * 3)(*pos)
+    r = (C.c_float * 3)(*rot)
+    ref_host().ref_get_ray_map(p, r, border, rays_res, C.byref(rm))
+    return rm
+
+
+def ref_render_frame(rm, res, mip_distance=None, z_far=80000, rays=None, threads=0, bench=False, fill=0):
+    """Run the reference render_line over all rays; returns (warp uint32[rays,res], perf or None)."""
+    lib = ref_render(bench)
+    nrays = rm.map_line_count if rays is None else rays
+    warp = np.full((max(nrays, 1), res), fill, dtype=np.uint32)
+    perf = (C.c_longlong * 5)()
+    rc = lib.ref_render_frame(C.byref(rm), res, res, mip_distance or res, z_far,
+                              warp.ctypes.data_as(C.c_void_p), 0, nrays, threads, perf)
+    if rc != 0:
+        raise RuntimeError("ref_render_frame rc=%d" % rc)
+    return warp, (list(perf) if bench else None)
