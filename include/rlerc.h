@@ -1,0 +1,211 @@
+/* rlerc — B200-native RLE voxel raycaster frame loop: C ABI.
+ *
+ * Drop-in boundary for the render path of sp4cerat/RLE-based-Voxel-Raycasting
+ * (SURVEY.md §8b).  Every entry point names the reference interface it replaces
+ * ("R/" = RLE-Raycaster/ in the reference checkout).  Plain pointers and sizes
+ * only; no C++/torch types.  All functions return RLERC_OK (0) or a negative
+ * rlerc_status and never hang (the reference spins in while(1) on errors,
+ * R/src/Cuda_Main.cu:146,193).  A context is bound to one CUDA device and is
+ * thread-compatible (one caller thread per context).
+ */
+#ifndef RLERC_H
+#define RLERC_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RLERC_MAX_MAPS 16 /* R/src/RayMap.h:43  Map4 map4_gpu[16] */
+
+typedef enum rlerc_status {
+	RLERC_OK = 0,
+	RLERC_ERR_ARG = -1,      /* null / out-of-range argument */
+	RLERC_ERR_IO = -2,       /* file missing or truncated */
+	RLERC_ERR_FORMAT = -3,   /* malformed .rle4 / non power-of-two grid / >32-bit offsets */
+	RLERC_ERR_CUDA = -4,     /* CUDA runtime error (rlerc_last_error() has the text) */
+	RLERC_ERR_STATE = -5,    /* call order (no scene uploaded, no frame rendered, ...) */
+	RLERC_ERR_NOMEM = -6
+} rlerc_status;
+
+/* ---- POD mirrors of the reference structs (field order kept, LP64) ---------------- */
+
+typedef struct rlerc_vec3f { float x, y, z; } rlerc_vec3f;          /* R/src/VecMath.h:15 / CUDA float3 */
+
+/* R/src/Rle4.h:7-21 `struct Map4` (32 bytes on LP64).
+ * map   : uint32[sx*sz*2], per column {slab_offset (ushort index), n_runs | first_run<<16}
+ *         (layout built by RLE4::load, R/src/Rle4.cpp:297-303)
+ * slabs : uint16[slabs_size], per column [n_runs][n_vox][run * n_runs][attr16 * n_vox],
+ *         columns x-fastest then z.  run = solid(6b)<<10 | skip(10b). */
+typedef struct rlerc_map4 {
+	int32_t   sx, sy, sz, slabs_size;
+	uint32_t* map;
+	uint16_t* slabs;
+} rlerc_map4;
+
+/* R/src/RayMap.h:16-54 `struct RayMap_GPU` (896 bytes on LP64). */
+typedef struct rlerc_raymap {
+	rlerc_vec3f vanishing_point_2d;
+	int32_t     map_line_count;
+	int32_t     map_line_limit;
+	rlerc_vec3f rotation;
+	rlerc_vec3f position;
+	float       border;
+	float       clip_min, clip_max;
+	rlerc_map4  map4_gpu[RLERC_MAX_MAPS];
+	int32_t     nummaps;
+	int32_t     maxres;
+	int32_t     res[4];
+	rlerc_vec3f p4;
+	rlerc_vec3f p_2d[8];
+	rlerc_vec3f p_no[8];
+	float       to3d[4][4];
+	float       p_ofs_min[4];
+	float       p_ofs_max[4];
+} rlerc_raymap;
+
+/* The reference's compile-time configuration (R/src/core.h:3-10) as run-time fields. */
+typedef struct rlerc_frame_config {
+	int32_t width, height;      /* window: SCREEN_SIZE_X, SCREEN_SIZE_Y                  */
+	int32_t render_size;        /* RENDER_SIZE: res_x = res_y of the warped ray buffer   */
+	int32_t rays_casted;        /* RAYS_CASTED: rows of the warped ray buffer            */
+	int32_t rays_casted_res;    /* RAYS_CASTED_RES: angular resolution (maxres*4)        */
+	int32_t z_far;              /* RAYS_DISTANCE                                         */
+	int32_t mip_distance;       /* MIP_DISTANCE                                          */
+	float   border;             /* RayMap::set_border, R/src/main.cpp:774                */
+} rlerc_frame_config;
+
+/* Defaults exactly as R/src/core.h for a W x H window: render_size=W, rays=4W,
+ * z_far=80000, mip_distance=W, border=(1-H/W)/2 (=0.125 for 1024x768, main.cpp:774-776). */
+void rlerc_frame_config_default(int width, int height, rlerc_frame_config* out);
+
+typedef struct rlerc_ctx rlerc_ctx;       /* one CUDA device + streams + device scene replica */
+typedef struct rlerc_scene rlerc_scene;   /* host-side RLE4 (R/src/Rle4.h:25-52)              */
+
+const char* rlerc_last_error(void);
+const char* rlerc_version(void);
+
+/* ---- scene: replaces RLE4::load/save/clear/compress_all (R/src/Rle4.cpp:16-384) ---- */
+
+/* RLE4::load (Rle4.cpp:244-384): reads the file and rebuilds the per-column pointer map. */
+int  rlerc_scene_load(const char* path, rlerc_scene** out);
+/* RLE4::save (Rle4.cpp:220-242). Fails with RLERC_ERR_FORMAT if a level exceeds int32 slabs. */
+int  rlerc_scene_save(const rlerc_scene* s, const char* path);
+/* Deep-copies `nummaps` levels laid out like RLE4::map[] after load(). */
+int  rlerc_scene_from_maps(const rlerc_map4* maps, int nummaps, rlerc_scene** out);
+/* RLE4::clear (Rle4.cpp:210-218). */
+void rlerc_scene_free(rlerc_scene* s);
+int  rlerc_scene_nummaps(const rlerc_scene* s);
+/* Borrowed view of level m (host pointers, valid until rlerc_scene_free). */
+int  rlerc_scene_level(const rlerc_scene* s, int m, rlerc_map4* out, uint64_t* slabs_size64);
+/* RLE4::compress_all (Rle4.cpp:16-50) + Tree::get_mipmap (tree.h:23-85) on a bit volume
+ * (x fastest, then y, then z; bit x&7 of byte (x+y*sx+z*sx*sy)>>3; col1/col2 may be NULL):
+ * byte-identical output, multi-threaded. */
+int  rlerc_scene_compress(const uint8_t* voxel, const uint8_t* col1, const uint8_t* col2,
+                          int sx, int sy, int sz, rlerc_scene** out);
+/* Physical nx x nz tiling of every level in x and z (BASELINE config 3). */
+int  rlerc_scene_tile(const rlerc_scene* s, int nx, int nz, rlerc_scene** out);
+/* Procedural bit volumes for the synthetic benchmark scenes.
+ * kind 0: terrain + boulders + caves ("synth_imrodh"); kind 1: worst-case short-run band. */
+int  rlerc_synth_volume(int kind, int sx, int sy, int sz, uint32_t seed,
+                        uint8_t* voxel, uint8_t* col1, uint8_t* col2);
+
+/* ---- context / device scene: replaces gpu_malloc + RLE4::all_to_gpu ----------------- */
+
+int  rlerc_create(int device, rlerc_ctx** out);
+void rlerc_destroy(rlerc_ctx* c);
+/* RLE4::all_to_gpu / copy_to_gpu (Rle4.cpp:432-448): full replica of every level in HBM. */
+int  rlerc_scene_upload(rlerc_ctx* c, const rlerc_scene* s);
+/* Device-side Map4 table as main.cpp:277-278 copies it into the ray map (all levels). */
+int  rlerc_scene_device_maps(rlerc_ctx* c, rlerc_map4* out16, int* nummaps);
+/* Traversal kernel variant: lanes cooperating on one ray plane (1,2,4,8,16,32; 0 = auto). */
+int  rlerc_set_lanes_per_ray(rlerc_ctx* c, int lanes);
+
+/* ---- frame setup: replaces RayMap::set_border/set_ray_limit/get_ray_map ------------ */
+
+/* RayMap::get_ray_map (R/src/RayMap.h:98-402), host only, byte-exact. Does not touch
+ * out->map4_gpu / out->nummaps. */
+int  rlerc_frame_setup(const float pos[3], const float rot[3], const rlerc_frame_config* cfg,
+                       rlerc_raymap* out);
+
+/* ---- render: replaces cuda_main_render2 (R/src/Cuda_Main.cu:183-271) --------------- */
+
+/* Traversal kernel over ray planes [ray_begin, ray_end) (whole frame: 0, -1) into the
+ * warped ray buffer uint32[rays_casted][render_size] in DEVICE memory (d_warp == NULL:
+ * the context's own buffer).  The ray map's map4_gpu/nummaps are ignored: the uploaded
+ * replica is used.  Asynchronous on the context stream. */
+int  rlerc_render(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_config* cfg,
+                  int ray_begin, int ray_end, uint32_t* d_warp);
+/* Same, additionally writing per-pixel hit identity for parity checks:
+ * d_ids uint32[rays_casted][render_size][2] = {column index vx+vz*sx at the hit level,
+ * mip_level<<16 | voxel index in the column's attribute array}. Debug build of the kernel. */
+int  rlerc_render_ids(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_config* cfg,
+                      int ray_begin, int ray_end, uint32_t* d_warp, uint32_t* d_ids);
+/* Work counters of the last rlerc_render_ids call (DETAIL_BENCH, R/src/Cuda_Render.h:14-22
+ * plus the byte-model terms of SURVEY.md §8d):
+ * [0] elems_total [1] elems_processed [2] voxels_processed [3] elems_rendered [4] pixels
+ * [5] map entries fetched C [6] run-loop iterations E [7] fetched columns with >=1 run C1
+ * [8] cleared pixels K [9] DDA steps */
+int  rlerc_render_counters(rlerc_ctx* c, uint64_t out[10]);
+
+/* ---- unwarp + shade: replaces GLSL pass 1 (R/bin/shader/colorize_buddha_soft.frag,
+ *      uniforms R/src/main.cpp:578-603) ------------------------------------------------ */
+
+/* d_warp (NULL: context buffer) -> RGBA8 uint8[height][width][4] in DEVICE memory, row 0 =
+ * TOP of the window (GL row height-1). rows [row_begin,row_end) only (whole frame: 0,-1). */
+int  rlerc_unwarp(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_config* cfg,
+                  const uint32_t* d_warp, uint8_t* d_rgba, int row_begin, int row_end);
+/* Multi-GPU compositing helper: like rlerc_unwarp, but only pixels whose ray plane lies in
+ * [ray_begin, ray_end) are written; all other pixels are set to 0, so that a sum-reduce of
+ * the per-GPU images equals the single-GPU image (disjoint support). */
+int  rlerc_unwarp_slice(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_config* cfg,
+                        const uint32_t* d_warp, uint8_t* d_rgba, int ray_begin, int ray_end);
+
+/* ---- whole frame with HOST buffers (what render_to_pbo + display_pbo pass 1 do) ----- */
+
+/* get_ray_map -> traversal -> unwarp -> D2H into host_rgba (width*height*4 bytes; pinned
+ * memory recommended).  Synchronous. out_raymap may be NULL. */
+int  rlerc_render_frame(rlerc_ctx* c, const float pos[3], const float rot[3],
+                        const rlerc_frame_config* cfg, uint8_t* host_rgba, rlerc_raymap* out_raymap);
+/* Pipelined variant: up to `depth` frames in flight (device double buffering, D2H of frame n
+ * overlaps traversal of frame n+1). submit returns a ticket; wait blocks until that frame's
+ * pixels are in host_rgba. */
+int  rlerc_frame_submit(rlerc_ctx* c, const float pos[3], const float rot[3],
+                        const rlerc_frame_config* cfg, uint8_t* host_rgba);
+int  rlerc_frame_wait(rlerc_ctx* c, int ticket);
+
+/* ---- plumbing ------------------------------------------------------------------------ */
+int   rlerc_sync(rlerc_ctx* c);
+void* rlerc_stream(rlerc_ctx* c);                    /* cudaStream_t the kernels run on */
+int   rlerc_warp_buffer(rlerc_ctx* c, const rlerc_frame_config* cfg, uint32_t** d_warp);
+int   rlerc_memcpy_d2h(rlerc_ctx* c, void* host, const void* dev, size_t bytes);
+int   rlerc_memcpy_h2d(rlerc_ctx* c, void* dev, const void* host, size_t bytes);
+int   rlerc_host_alloc(void** p, size_t bytes);      /* pinned */
+void  rlerc_host_free(void* p);
+/* Last kernel times in ms from CUDA events on the context stream: [0] traversal [1] unwarp */
+int   rlerc_last_kernel_ms(rlerc_ctx* c, float out[2]);
+/* Enables per-launch CUDA-event timing (adds two event records per kernel). */
+int   rlerc_set_timing(rlerc_ctx* c, int on);
+
+/* ---- legacy surface of the reference, same names and signatures ---------------------- */
+/* R/src/core.h:144-147 */
+void* gpu_malloc(int size);
+void  gpu_memcpy(void* dst, void* src, int count);   /* host -> device */
+void  cpu_memcpy(void* dst, void* src, int count);   /* device -> host */
+extern int cpu_to_gpu_delta;                           /* always 0: no mirrored arena */
+/* R/src/Cuda_Main.cu:124-126.  There is no GL here: a "pbo" is a small integer handle bound to
+ * a device buffer of rays_casted*render_size*4 bytes by rlerc_pbo_bind(); pboRegister/
+ * pboUnregister keep their signatures. raymap is the reference's RayMap_GPU (== rlerc_raymap).
+ * Uses the process-default context created by rlerc_legacy_init(). */
+int   rlerc_legacy_init(int device, const rlerc_scene* scene, const rlerc_frame_config* cfg);
+int   rlerc_pbo_bind(int pbo, void* device_ptr);
+void  pboRegister(int pbo);
+void  pboUnregister(int pbo);
+void  cuda_main_render2(int pbo_out, int width, int height, rlerc_raymap* raymap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RLERC_H */

@@ -1,0 +1,567 @@
+// C ABI of the render path (include/rlerc.h): context, device scene replica, per-frame
+// parameter blocks, kernel launches, host<->device plumbing, and the legacy entry points of
+// the reference (cuda_main_render2 & co, R/src/Cuda_Main.cu:124-148,183-271).
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <cmath>
+#include <map>
+#include <vector>
+#include <cuda_runtime.h>
+#include "kernels.cuh"
+#include "rlerc_internal.h"
+
+using namespace rlerc;
+
+#define CK(call)                                                                        \
+	do {                                                                                \
+		cudaError_t e_ = (call);                                                        \
+		if (e_ != cudaSuccess) {                                                        \
+			set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+			return RLERC_ERR_CUDA;                                                      \
+		}                                                                               \
+	} while (0)
+
+namespace {
+
+struct FrameSlot {            // one in-flight frame of the pipelined path
+	uint32_t* d_warp = nullptr;
+	uint8_t* d_rgba = nullptr;
+	size_t warp_bytes = 0, rgba_bytes = 0;
+	cudaEvent_t done = nullptr;
+	uint8_t* host_dst = nullptr;
+	bool busy = false;
+};
+
+} // namespace
+
+struct rlerc_ctx {
+	int device = 0;
+	cudaStream_t stream = nullptr;      // traversal + unwarp
+	cudaStream_t copy_stream = nullptr; // D2H of finished frames
+	// device scene replica
+	int nummaps = 0;
+	LevelDev level[RLERC_MAX_MAPS];
+	int level_sy[RLERC_MAX_MAPS];
+	uint64_t level_slabs[RLERC_MAX_MAPS];
+	std::vector<void*> scene_allocs;
+	// frame resources
+	uint32_t* d_warp = nullptr;
+	size_t warp_bytes = 0;
+	uint8_t* d_rgba = nullptr;
+	size_t rgba_bytes = 0;
+	uint32_t* d_ids_scratch = nullptr;
+	unsigned long long* d_counters = nullptr;
+	int lanes = 0;                      // 0 = auto
+	bool timing = false;
+	cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
+	bool ev_valid[2] = { false, false };
+	// pipeline
+	static const int kSlots = 3;
+	FrameSlot slot[kSlots];
+	int next_ticket = 0;
+};
+
+namespace {
+
+int set_dev(rlerc_ctx* c)
+{
+	CK(cudaSetDevice(c->device));
+	return RLERC_OK;
+}
+
+void free_scene(rlerc_ctx* c)
+{
+	for (void* p : c->scene_allocs) cudaFree(p);
+	c->scene_allocs.clear();
+	c->nummaps = 0;
+}
+
+int ensure(void** p, size_t* have, size_t need)
+{
+	if (*have >= need && *p) return RLERC_OK;
+	if (*p) cudaFree(*p);
+	*p = nullptr; *have = 0;
+	CK(cudaMalloc(p, need));
+	CK(cudaMemset(*p, 0, need));
+	*have = need;
+	return RLERC_OK;
+}
+
+int check_cfg(const rlerc_frame_config* cfg)
+{
+	if (!cfg) { set_error("null frame config"); return RLERC_ERR_ARG; }
+	if (cfg->width < 4 || cfg->height < 1 || cfg->render_size < 32 || cfg->render_size > 16384 ||
+	    cfg->rays_casted < 4 || cfg->rays_casted_res < 4 || cfg->z_far < 1 || cfg->mip_distance < 1)
+	{
+		set_error("frame config out of range");
+		return RLERC_ERR_ARG;
+	}
+	return RLERC_OK;
+}
+
+// Host half of the traversal set-up: everything that depends only on the camera.
+int fill_traverse(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_config* cfg,
+                  int ray_begin, int ray_end, uint32_t* d_warp, TraverseParams& P)
+{
+	if (c->nummaps < 1) { set_error("no scene uploaded"); return RLERC_ERR_STATE; }
+	memset(&P, 0, sizeof(P));
+	for (int m = 0; m < c->nummaps; m++) P.level[m] = c->level[m];
+	P.nummaps = c->nummaps;
+	int count = rm->map_line_count;
+	if (count > cfg->rays_casted) count = cfg->rays_casted;      // Cuda_Main.cu:196
+	if (count < 0) count = 0;
+	for (int i = 0; i < 4; i++) P.res[i] = rm->res[i];
+	P.vp[0] = rm->p_2d[5].x; P.vp[1] = rm->p_2d[5].y; P.vp[2] = rm->p_2d[5].z;
+	for (int i = 0; i < 8; i++) { P.p_no[i][0] = rm->p_no[i].x; P.p_no[i][1] = rm->p_no[i].y; P.p_no[i][2] = rm->p_no[i].z; }
+	P.clip_min = rm->clip_min; P.clip_max = rm->clip_max;
+	memcpy(P.to3d, rm->to3d, sizeof(P.to3d));
+	P.p4[0] = rm->p4.x; P.p4[1] = rm->p4.y; P.p4[2] = rm->p4.z;
+	P.viewpos[0] = rm->position.x; P.viewpos[1] = rm->position.y; P.viewpos[2] = rm->position.z;
+	const float rx = rm->rotation.x, ry = rm->rotation.y;
+	// same overloads the host-compiled reference resolves to: sin(float) -> sinf etc.
+	P.sin_x = std::sin(rx); P.cos_x = std::cos(rx);
+	P.sin_y = std::sin(ry); P.cos_y = std::cos(ry);
+	P.sin_my = std::sin(-ry); P.cos_my = std::cos(-ry);
+	P.res_x = cfg->render_size; P.res_y = cfg->render_size;
+	// Cuda_Render.h:182,335: int mapswitch = MIP_DISTANCE; mapswitch = mapswitch * (0.25*(4-abs(viewrot.x)));
+	{
+		int mapswitch = cfg->mip_distance;
+		mapswitch = mapswitch * (0.25 * (4 - std::abs(rx)));
+		P.mapswitch0 = mapswitch;
+	}
+	P.z_far = cfg->z_far;
+	if (ray_end < 0 || ray_end > count) ray_end = count;
+	if (ray_begin < 0) ray_begin = 0;
+	P.ray_begin = ray_begin; P.ray_end = ray_end;
+	P.mask_words = (cfg->render_size + 31) / 32 + 1;
+	P.warp = d_warp;
+	return RLERC_OK;
+}
+
+// Uniforms of the colorize pass exactly as main.cpp:578-603 computes them.
+int fill_unwarp(const rlerc_raymap* rm, const rlerc_frame_config* cfg, const uint32_t* d_warp, uint8_t* d_rgba, UnwarpParams& U)
+{
+	memset(&U, 0, sizeof(U));
+	U.warp = d_warp; U.rgba = d_rgba;
+	U.W = cfg->width; U.H = cfg->height;
+	U.RS = cfg->render_size; U.RC = cfg->rays_casted;
+	const float border = rm->border;
+	U.vanish_x = 1 - rm->vanishing_point_2d.x;
+	U.vanish_y = (1 - rm->vanishing_point_2d.y - border) * float(cfg->width) / float(cfg->height);
+	const float ofs1 = 4 * float(rm->res[0]) / float(cfg->rays_casted_res);
+	const float ofs2 = 4 * float(rm->res[1]) / float(cfg->rays_casted_res) + ofs1;
+	const float ofs3 = 4 * float(rm->res[2]) / float(cfg->rays_casted_res) + ofs2;
+	U.ofs_add[0] = -rm->p_ofs_min[0];
+	U.ofs_add[1] = -rm->p_ofs_min[1] + ofs1;
+	U.ofs_add[2] = -rm->p_ofs_min[2] + ofs2;
+	U.ofs_add[3] = -rm->p_ofs_min[3] + ofs3;
+	U.ratio = float(cfg->rays_casted_res) / float(cfg->rays_casted);
+	U.rot_x_gt0 = (rm->rotation.x > 0) ? 1 : 0;
+	U.row_begin = 0; U.row_end = cfg->height;
+	U.ray_begin = 0; U.ray_end = -1;
+	return RLERC_OK;
+}
+
+int pick_lanes(const rlerc_ctx* c, int rays)
+{
+	if (c->lanes > 0) return c->lanes;
+	(void)rays;
+	return 32;
+}
+
+} // namespace
+
+extern "C" {
+
+int rlerc_create(int device, rlerc_ctx** out)
+{
+	if (!out) { set_error("rlerc_create: null out"); return RLERC_ERR_ARG; }
+	*out = nullptr;
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess || n < 1) { set_error("no CUDA device: %s", cudaGetErrorString(e)); return RLERC_ERR_CUDA; }
+	if (device < 0 || device >= n) { set_error("device %d out of range (%d devices)", device, n); return RLERC_ERR_ARG; }
+	rlerc_ctx* c = new rlerc_ctx();
+	c->device = device;
+	CK(cudaSetDevice(device));
+	CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+	for (int i = 0; i < 4; i++) CK(cudaEventCreate(&c->ev[i]));
+	for (int i = 0; i < rlerc_ctx::kSlots; i++) CK(cudaEventCreateWithFlags(&c->slot[i].done, cudaEventDisableTiming));
+	CK(cudaMalloc((void**)&c->d_counters, 16 * sizeof(unsigned long long)));
+	*out = c;
+	return RLERC_OK;
+}
+
+void rlerc_destroy(rlerc_ctx* c)
+{
+	if (!c) return;
+	cudaSetDevice(c->device);
+	cudaDeviceSynchronize();
+	free_scene(c);
+	if (c->d_warp) cudaFree(c->d_warp);
+	if (c->d_rgba) cudaFree(c->d_rgba);
+	if (c->d_counters) cudaFree(c->d_counters);
+	for (int i = 0; i < rlerc_ctx::kSlots; i++)
+	{
+		if (c->slot[i].d_warp) cudaFree(c->slot[i].d_warp);
+		if (c->slot[i].d_rgba) cudaFree(c->slot[i].d_rgba);
+		if (c->slot[i].done) cudaEventDestroy(c->slot[i].done);
+	}
+	for (int i = 0; i < 4; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+	if (c->stream) cudaStreamDestroy(c->stream);
+	if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+	delete c;
+}
+
+int rlerc_scene_upload(rlerc_ctx* c, const rlerc_scene* s)
+{
+	if (!c || !s || s->levels.empty()) { set_error("rlerc_scene_upload: bad argument"); return RLERC_ERR_ARG; }
+	int rc = set_dev(c);
+	if (rc) return rc;
+	// the traversal wraps coordinates with & (grid-1) and halves the grid per level
+	// (Cuda_Render.h:351-352,441-442): validate instead of rendering garbage
+	const int n = (int)s->levels.size();
+	for (int m = 0; m < n; m++)
+	{
+		const Level& lv = s->levels[m];
+		if (lv.sx < 1 || lv.sz < 1 || (lv.sx & (lv.sx - 1)) || (lv.sz & (lv.sz - 1)))
+		{
+			set_error("level %d: grid %d x %d is not a power of two", m, lv.sx, lv.sz);
+			return RLERC_ERR_FORMAT;
+		}
+		if (m > 0 && (lv.sx != (s->levels[0].sx >> m) || lv.sz != (s->levels[0].sz >> m)))
+		{
+			set_error("level %d: grid %d x %d is not level 0 halved %d times", m, lv.sx, lv.sz, m);
+			return RLERC_ERR_FORMAT;
+		}
+		if (lv.sy > 65535) { set_error("level %d: sy %d exceeds 65535", m, lv.sy); return RLERC_ERR_FORMAT; }
+		if (lv.slabs.size() > 0xffffffffull) { set_error("level %d: slab stream exceeds 32-bit offsets", m); return RLERC_ERR_FORMAT; }
+		if (lv.map.size() != (size_t)lv.sx * lv.sz * 2) { set_error("level %d: pointer map size mismatch", m); return RLERC_ERR_FORMAT; }
+	}
+	free_scene(c);
+	for (int m = 0; m < n; m++)
+	{
+		const Level& lv = s->levels[m];
+		void *dm = nullptr, *ds = nullptr;
+		// +64 bytes of zero padding behind the slabs: a column's "first run" style look-ahead
+		// and vector loads may read a few words past the last column
+		const size_t mbytes = lv.map.size() * 4, sbytes = lv.slabs.size() * 2;
+		CK(cudaMalloc(&dm, mbytes));
+		c->scene_allocs.push_back(dm);
+		CK(cudaMalloc(&ds, sbytes + 64));
+		c->scene_allocs.push_back(ds);
+		CK(cudaMemcpy(dm, lv.map.data(), mbytes, cudaMemcpyHostToDevice));
+		CK(cudaMemcpy(ds, lv.slabs.data(), sbytes, cudaMemcpyHostToDevice));
+		CK(cudaMemset((char*)ds + sbytes, 0, 64));
+		c->level[m].map = (const uint2*)dm;
+		c->level[m].slabs = (const uint16_t*)ds;
+		c->level[m].sx = lv.sx;
+		c->level[m].sz = lv.sz;
+		c->level_sy[m] = lv.sy;
+		c->level_slabs[m] = lv.slabs.size();
+	}
+	c->nummaps = n;
+	return RLERC_OK;
+}
+
+int rlerc_scene_device_maps(rlerc_ctx* c, rlerc_map4* out16, int* nummaps)
+{
+	if (!c || !out16) { set_error("rlerc_scene_device_maps: bad argument"); return RLERC_ERR_ARG; }
+	memset(out16, 0, sizeof(rlerc_map4) * RLERC_MAX_MAPS);
+	for (int m = 0; m < c->nummaps; m++)
+	{
+		out16[m].sx = c->level[m].sx; out16[m].sy = c->level_sy[m]; out16[m].sz = c->level[m].sz;
+		out16[m].slabs_size = (int32_t)(uint32_t)c->level_slabs[m];
+		out16[m].map = (uint32_t*)c->level[m].map;
+		out16[m].slabs = (uint16_t*)c->level[m].slabs;
+	}
+	if (nummaps) *nummaps = c->nummaps;
+	return RLERC_OK;
+}
+
+int rlerc_set_lanes_per_ray(rlerc_ctx* c, int lanes)
+{
+	if (!c || !(lanes == 0 || lanes == 1 || lanes == 2 || lanes == 4 || lanes == 8 || lanes == 16 || lanes == 32))
+	{
+		set_error("lanes per ray must be 0,1,2,4,8,16 or 32");
+		return RLERC_ERR_ARG;
+	}
+	c->lanes = lanes;
+	return RLERC_OK;
+}
+
+int rlerc_set_timing(rlerc_ctx* c, int on)
+{
+	if (!c) return RLERC_ERR_ARG;
+	c->timing = on != 0;
+	return RLERC_OK;
+}
+
+int rlerc_warp_buffer(rlerc_ctx* c, const rlerc_frame_config* cfg, uint32_t** d_warp)
+{
+	int rc = check_cfg(cfg);
+	if (rc) return rc;
+	if (!c || !d_warp) { set_error("rlerc_warp_buffer: null argument"); return RLERC_ERR_ARG; }
+	if ((rc = set_dev(c))) return rc;
+	rc = ensure((void**)&c->d_warp, &c->warp_bytes, (size_t)cfg->rays_casted * cfg->render_size * 4);
+	if (rc) return rc;
+	*d_warp = c->d_warp;
+	return RLERC_OK;
+}
+
+static int render_impl(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_config* cfg,
+                       int ray_begin, int ray_end, uint32_t* d_warp, uint32_t* d_ids, bool ids)
+{
+	if (!c || !rm) { set_error("rlerc_render: null argument"); return RLERC_ERR_ARG; }
+	int rc = check_cfg(cfg);
+	if (rc) return rc;
+	if ((rc = set_dev(c))) return rc;
+	if (!d_warp)
+	{
+		rc = ensure((void**)&c->d_warp, &c->warp_bytes, (size_t)cfg->rays_casted * cfg->render_size * 4);
+		if (rc) return rc;
+		d_warp = c->d_warp;
+	}
+	TraverseParams P;
+	if ((rc = fill_traverse(c, rm, cfg, ray_begin, ray_end, d_warp, P))) return rc;
+	if (ids)
+	{
+		if (!d_ids) { set_error("rlerc_render_ids: null ids buffer"); return RLERC_ERR_ARG; }
+		P.ids = d_ids;
+		P.counters = c->d_counters;
+		CK(cudaMemsetAsync(c->d_counters, 0, 16 * sizeof(unsigned long long), c->stream));
+	}
+	if (c->timing) CK(cudaEventRecord(c->ev[0], c->stream));
+	launch_traverse(P, pick_lanes(c, P.ray_end - P.ray_begin), ids, c->stream);
+	if (c->timing) { CK(cudaEventRecord(c->ev[1], c->stream)); c->ev_valid[0] = true; }
+	CK(cudaGetLastError());
+	return RLERC_OK;
+}
+
+int rlerc_render(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_config* cfg, int ray_begin, int ray_end, uint32_t* d_warp)
+{
+	return render_impl(c, rm, cfg, ray_begin, ray_end, d_warp, nullptr, false);
+}
+
+int rlerc_render_ids(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_config* cfg, int ray_begin, int ray_end, uint32_t* d_warp, uint32_t* d_ids)
+{
+	return render_impl(c, rm, cfg, ray_begin, ray_end, d_warp, d_ids, true);
+}
+
+int rlerc_render_counters(rlerc_ctx* c, uint64_t out[10])
+{
+	if (!c || !out) return RLERC_ERR_ARG;
+	int rc = set_dev(c);
+	if (rc) return rc;
+	CK(cudaStreamSynchronize(c->stream));
+	unsigned long long h[10];
+	CK(cudaMemcpy(h, c->d_counters, sizeof(h), cudaMemcpyDeviceToHost));
+	for (int i = 0; i < 10; i++) out[i] = h[i];
+	return RLERC_OK;
+}
+
+static int unwarp_impl(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_config* cfg, const uint32_t* d_warp,
+                       uint8_t* d_rgba, int row_begin, int row_end, int ray_begin, int ray_end)
+{
+	if (!c || !rm) { set_error("rlerc_unwarp: null argument"); return RLERC_ERR_ARG; }
+	int rc = check_cfg(cfg);
+	if (rc) return rc;
+	if ((rc = set_dev(c))) return rc;
+	if (!d_warp)
+	{
+		if (!c->d_warp) { set_error("rlerc_unwarp: nothing rendered yet"); return RLERC_ERR_STATE; }
+		d_warp = c->d_warp;
+	}
+	if (!d_rgba)
+	{
+		rc = ensure((void**)&c->d_rgba, &c->rgba_bytes, (size_t)cfg->width * cfg->height * 4);
+		if (rc) return rc;
+		d_rgba = c->d_rgba;
+	}
+	UnwarpParams U;
+	fill_unwarp(rm, cfg, d_warp, d_rgba, U);
+	if (row_end < 0 || row_end > cfg->height) row_end = cfg->height;
+	if (row_begin < 0) row_begin = 0;
+	U.row_begin = row_begin; U.row_end = row_end;
+	U.ray_begin = ray_begin; U.ray_end = ray_end;
+	if (c->timing) CK(cudaEventRecord(c->ev[2], c->stream));
+	launch_unwarp(U, c->stream);
+	if (c->timing) { CK(cudaEventRecord(c->ev[3], c->stream)); c->ev_valid[1] = true; }
+	CK(cudaGetLastError());
+	return RLERC_OK;
+}
+
+int rlerc_unwarp(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_config* cfg, const uint32_t* d_warp, uint8_t* d_rgba, int row_begin, int row_end)
+{
+	return unwarp_impl(c, rm, cfg, d_warp, d_rgba, row_begin, row_end, 0, -1);
+}
+
+int rlerc_unwarp_slice(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_config* cfg, const uint32_t* d_warp, uint8_t* d_rgba, int ray_begin, int ray_end)
+{
+	if (ray_begin < 0 || ray_end < ray_begin) { set_error("rlerc_unwarp_slice: bad ray range"); return RLERC_ERR_ARG; }
+	return unwarp_impl(c, rm, cfg, d_warp, d_rgba, 0, -1, ray_begin, ray_end);
+}
+
+int rlerc_render_frame(rlerc_ctx* c, const float pos[3], const float rot[3], const rlerc_frame_config* cfg, uint8_t* host_rgba, rlerc_raymap* out_raymap)
+{
+	if (!c || !pos || !rot || !host_rgba) { set_error("rlerc_render_frame: null argument"); return RLERC_ERR_ARG; }
+	int rc = check_cfg(cfg);
+	if (rc) return rc;
+	rlerc_raymap rm;
+	memset(&rm, 0, sizeof(rm));
+	if ((rc = rlerc_frame_setup(pos, rot, cfg, &rm))) return rc;
+	if ((rc = render_impl(c, &rm, cfg, 0, -1, nullptr, nullptr, false))) return rc;
+	if ((rc = unwarp_impl(c, &rm, cfg, nullptr, nullptr, 0, -1, 0, -1))) return rc;
+	CK(cudaMemcpyAsync(host_rgba, c->d_rgba, (size_t)cfg->width * cfg->height * 4, cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	if (out_raymap) *out_raymap = rm;
+	return RLERC_OK;
+}
+
+int rlerc_frame_submit(rlerc_ctx* c, const float pos[3], const float rot[3], const rlerc_frame_config* cfg, uint8_t* host_rgba)
+{
+	if (!c || !pos || !rot || !host_rgba) { set_error("rlerc_frame_submit: null argument"); return RLERC_ERR_ARG; }
+	int rc = check_cfg(cfg);
+	if (rc) return rc;
+	if ((rc = set_dev(c))) return rc;
+	const int ticket = c->next_ticket;
+	FrameSlot& s = c->slot[ticket % rlerc_ctx::kSlots];
+	if (s.busy) { CK(cudaEventSynchronize(s.done)); s.busy = false; }
+	if ((rc = ensure((void**)&s.d_warp, &s.warp_bytes, (size_t)cfg->rays_casted * cfg->render_size * 4))) return rc;
+	if ((rc = ensure((void**)&s.d_rgba, &s.rgba_bytes, (size_t)cfg->width * cfg->height * 4))) return rc;
+	rlerc_raymap rm;
+	memset(&rm, 0, sizeof(rm));
+	if ((rc = rlerc_frame_setup(pos, rot, cfg, &rm))) return rc;
+	if ((rc = render_impl(c, &rm, cfg, 0, -1, s.d_warp, nullptr, false))) return rc;
+	if ((rc = unwarp_impl(c, &rm, cfg, s.d_warp, s.d_rgba, 0, -1, 0, -1))) return rc;
+	// hand the finished frame to the copy stream so the next frame's traversal overlaps the D2H
+	CK(cudaEventRecord(s.done, c->stream));
+	CK(cudaStreamWaitEvent(c->copy_stream, s.done, 0));
+	CK(cudaMemcpyAsync(host_rgba, s.d_rgba, (size_t)cfg->width * cfg->height * 4, cudaMemcpyDeviceToHost, c->copy_stream));
+	CK(cudaEventRecord(s.done, c->copy_stream));
+	s.busy = true;
+	s.host_dst = host_rgba;
+	c->next_ticket++;
+	return ticket;
+}
+
+int rlerc_frame_wait(rlerc_ctx* c, int ticket)
+{
+	if (!c || ticket < 0 || ticket >= c->next_ticket) { set_error("rlerc_frame_wait: bad ticket"); return RLERC_ERR_ARG; }
+	// a later submit that recycled this ticket's slot has already waited for it
+	if (ticket < c->next_ticket - rlerc_ctx::kSlots) return RLERC_OK;
+	FrameSlot& s = c->slot[ticket % rlerc_ctx::kSlots];
+	int rc = set_dev(c);
+	if (rc) return rc;
+	if (s.busy) { CK(cudaEventSynchronize(s.done)); s.busy = false; }
+	return RLERC_OK;
+}
+
+int rlerc_sync(rlerc_ctx* c)
+{
+	if (!c) return RLERC_ERR_ARG;
+	int rc = set_dev(c);
+	if (rc) return rc;
+	CK(cudaStreamSynchronize(c->stream));
+	CK(cudaStreamSynchronize(c->copy_stream));
+	return RLERC_OK;
+}
+
+void* rlerc_stream(rlerc_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+int rlerc_memcpy_d2h(rlerc_ctx* c, void* host, const void* dev, size_t bytes)
+{
+	if (!c || !host || !dev) return RLERC_ERR_ARG;
+	int rc = set_dev(c);
+	if (rc) return rc;
+	CK(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	return RLERC_OK;
+}
+
+int rlerc_memcpy_h2d(rlerc_ctx* c, void* dev, const void* host, size_t bytes)
+{
+	if (!c || !host || !dev) return RLERC_ERR_ARG;
+	int rc = set_dev(c);
+	if (rc) return rc;
+	CK(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	return RLERC_OK;
+}
+
+int rlerc_host_alloc(void** p, size_t bytes)
+{
+	if (!p) return RLERC_ERR_ARG;
+	CK(cudaMallocHost(p, bytes));
+	return RLERC_OK;
+}
+
+void rlerc_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int rlerc_last_kernel_ms(rlerc_ctx* c, float out[2])
+{
+	if (!c || !out) return RLERC_ERR_ARG;
+	int rc = set_dev(c);
+	if (rc) return rc;
+	out[0] = out[1] = -1.0f;
+	if (c->ev_valid[0]) { CK(cudaEventSynchronize(c->ev[1])); CK(cudaEventElapsedTime(&out[0], c->ev[0], c->ev[1])); }
+	if (c->ev_valid[1]) { CK(cudaEventSynchronize(c->ev[3])); CK(cudaEventElapsedTime(&out[1], c->ev[2], c->ev[3])); }
+	return RLERC_OK;
+}
+
+// ---- legacy surface (R/src/core.h:144-147, R/src/Cuda_Main.cu:124-148,183-271) ----------
+
+int cpu_to_gpu_delta = 0;
+
+static rlerc_ctx* g_legacy = nullptr;
+static rlerc_frame_config g_legacy_cfg;
+static std::map<int, void*>* g_pbo = nullptr;
+
+void* gpu_malloc(int size)
+{
+	void* p = nullptr;
+	if (cudaMalloc(&p, (size_t)size) != cudaSuccess) { set_error("gpu_malloc(%d) failed", size); return nullptr; }
+	return p;
+}
+void gpu_memcpy(void* dst, void* src, int count) { cudaMemcpy(dst, src, (size_t)count, cudaMemcpyHostToDevice); }
+void cpu_memcpy(void* dst, void* src, int count) { cudaMemcpy(dst, src, (size_t)count, cudaMemcpyDeviceToHost); }
+
+int rlerc_legacy_init(int device, const rlerc_scene* scene, const rlerc_frame_config* cfg)
+{
+	int rc = check_cfg(cfg);
+	if (rc) return rc;
+	if (g_legacy) { rlerc_destroy(g_legacy); g_legacy = nullptr; }
+	if ((rc = rlerc_create(device, &g_legacy))) return rc;
+	if ((rc = rlerc_scene_upload(g_legacy, scene))) return rc;
+	g_legacy_cfg = *cfg;
+	if (!g_pbo) g_pbo = new std::map<int, void*>();
+	return RLERC_OK;
+}
+
+int rlerc_pbo_bind(int pbo, void* device_ptr)
+{
+	if (!g_pbo) g_pbo = new std::map<int, void*>();
+	(*g_pbo)[pbo] = device_ptr;
+	return RLERC_OK;
+}
+void pboRegister(int pbo) { if (!g_pbo) g_pbo = new std::map<int, void*>(); if (!g_pbo->count(pbo)) (*g_pbo)[pbo] = nullptr; }
+void pboUnregister(int pbo) { if (g_pbo) g_pbo->erase(pbo); }
+
+// Same contract as the reference: renders map_line_count ray planes of `raymap` into the
+// buffer behind `pbo_out` and returns once the kernel has finished (Cuda_Main.cu:241).
+void cuda_main_render2(int pbo_out, int width, int height, rlerc_raymap* raymap)
+{
+	if (pbo_out == 0 || !g_legacy || !g_pbo || !raymap) return;         // Cuda_Main.cu:187
+	auto it = g_pbo->find(pbo_out);
+	if (it == g_pbo->end() || !it->second) { set_error("cuda_main_render2: pbo %d has no device buffer", pbo_out); return; }
+	rlerc_frame_config cfg = g_legacy_cfg;
+	cfg.render_size = width;
+	(void)height;                                                        // res_x == res_y == RENDER_SIZE
+	if (rlerc_render(g_legacy, raymap, &cfg, 0, -1, (uint32_t*)it->second) != RLERC_OK) return;
+	cudaStreamSynchronize(g_legacy->stream);
+}
+
+} // extern "C"

@@ -1,0 +1,58 @@
+// Device-side parameter blocks shared between the launcher (capi.cu) and kernels.cu.
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+
+namespace rlerc {
+
+struct LevelDev {
+	const uint2*    map;    // [sz][sx] {slab offset (ushort index), n_runs | first_run<<16}
+	const uint16_t* slabs;
+	int sx, sz;
+};
+
+// Everything the traversal kernel needs for one frame (~700 B), passed as a
+// __grid_constant__ kernel parameter: replaces the 82,832-byte `Render` block the reference
+// copies host->device every frame (R/src/Cuda_Main.cu:218).
+struct TraverseParams {
+	LevelDev level[16];
+	int nummaps;
+	int res[4];              // rays per quadrant           (RayMap_GPU::res)
+	float vp[3];             // p_2d[5], vanishing point    (Cuda_Render.h:149)
+	float p_no[8][3];        // quadrant border points      (Cuda_Render.h:150)
+	float clip_min, clip_max;
+	float to3d[4][4];
+	float p4[3];
+	float viewpos[3];
+	// trig of the camera angles, evaluated once on the host with the libm the oracle uses
+	float sin_x, cos_x, sin_y, cos_y;   // sin/cos(rotation.x), sin/cos(rotation.y)  (Cuda_Render.h:188-191)
+	float sin_my, cos_my;               // sin/cos(-rotation.y)                      (Cuda_Render.h:77-78)
+	int res_x, res_y;
+	int mapswitch0;          // int(MIP_DISTANCE * (0.25*(4-abs(rot.x)))), double math (Cuda_Render.h:335)
+	int z_far;
+	int ray_begin, ray_end;  // slice of the ray index range rendered by this launch
+	int mask_words;          // per-ray occlusion bitmask size in 32-bit words
+	uint32_t* warp;          // [rays_casted][res_y]
+	uint32_t* ids;           // optional [rays_casted][res_y][2]
+	unsigned long long* counters; // optional [10]
+};
+
+struct UnwarpParams {
+	const uint32_t* warp;
+	uint8_t* rgba;           // [H][W][4], row 0 = top
+	int W, H;                // window
+	int RS, RC;              // warped buffer: RS texels wide (along a ray), RC rows (rays)
+	float vanish_x, vanish_y;
+	float ofs_add[4];
+	float ratio;             // RAYS_CASTED_RES / RAYS_CASTED
+	int rot_x_gt0;
+	int row_begin, row_end;
+	int ray_begin, ray_end;  // slice mode (ray_end < 0: off)
+	int rays_prefix_dummy;
+};
+
+void launch_traverse(const TraverseParams& p, int lanes_per_ray, bool ids, cudaStream_t st);
+void launch_unwarp(const UnwarpParams& p, cudaStream_t st);
+void launch_fill_u32(uint32_t* p, uint32_t v, size_t n, cudaStream_t st);
+
+} // namespace rlerc
