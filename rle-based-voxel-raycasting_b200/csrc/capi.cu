@@ -166,9 +166,8 @@ int fill_unwarp(const rlerc_raymap* rm, const rlerc_frame_config* cfg, const uin
 
 int pick_lanes(const rlerc_ctx* c, int rays)
 {
-	if (c->lanes > 0) return c->lanes;
 	(void)rays;
-	return 32;
+	return c->lanes;   // 0 = warp-per-ray, lane<->column kernel (k_traverse_w)
 }
 
 } // namespace

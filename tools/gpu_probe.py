@@ -50,7 +50,7 @@ def main():
         tref = time.time() - t0
         ref = ref[:cfg.rays_casted]
         line = "cam %s rays %d ref %.0f ms |" % (rot[:2], rm.map_line_count, tref * 1e3)
-        for G in (1, 4, 8, 16, 32):
+        for G in (8, 32, 0):
             r.set_lanes_per_ray(G)
             wp = r.warp_buffer(cfg)
             r.upload(wp, np.zeros((cfg.rays_casted, cfg.render_size), np.uint32))
@@ -68,7 +68,7 @@ def main():
             line += " G%d bad=%d %.3f ms |" % (G, bad, min(ts))
         print(line, flush=True)
     # unwarp timing
-    r.set_lanes_per_ray(32)
+    r.set_lanes_per_ray(0)
     r.render(rm, cfg)
     r.unwarp(rm, cfg)
     r.sync()
