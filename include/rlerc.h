@@ -163,6 +163,14 @@ int  rlerc_unwarp(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_config
 int  rlerc_unwarp_slice(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_config* cfg,
                         const uint32_t* d_warp, uint8_t* d_rgba, int ray_begin, int ray_end);
 
+/* Interleaved multi-GPU slices: ray plane r belongs to `rank` iff
+ * (r / block) % nranks == rank.  render: traverses only the owned ray planes; unwarp: writes
+ * only pixels whose ray plane is owned, 0 elsewhere (sum over ranks == single-GPU image). */
+int  rlerc_render_interleaved(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_config* cfg,
+                              int block, int nranks, int rank, uint32_t* d_warp);
+int  rlerc_unwarp_interleaved(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_config* cfg,
+                              int block, int nranks, int rank, const uint32_t* d_warp, uint8_t* d_rgba);
+
 /* ---- whole frame with HOST buffers (what render_to_pbo + display_pbo pass 1 do) ----- */
 
 /* get_ray_map -> traversal -> unwarp -> D2H into host_rgba (width*height*4 bytes; pinned
@@ -179,6 +187,8 @@ int  rlerc_frame_wait(rlerc_ctx* c, int ticket);
 /* ---- plumbing ------------------------------------------------------------------------ */
 int   rlerc_sync(rlerc_ctx* c);
 void* rlerc_stream(rlerc_ctx* c);                    /* cudaStream_t the kernels run on */
+/* Run the kernels on a caller-owned cudaStream_t (e.g. the stream NCCL collectives are enqueued on). */
+int   rlerc_set_stream(rlerc_ctx* c, void* cuda_stream);
 int   rlerc_warp_buffer(rlerc_ctx* c, const rlerc_frame_config* cfg, uint32_t** d_warp);
 int   rlerc_memcpy_d2h(rlerc_ctx* c, void* host, const void* dev, size_t bytes);
 int   rlerc_memcpy_h2d(rlerc_ctx* c, void* dev, const void* host, size_t bytes);

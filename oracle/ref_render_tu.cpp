@@ -99,7 +99,8 @@ int ref_render_frame(const void* raymap_gpu, int res_x, int res_y, int mip_dista
 	if (count > RAYS_CASTED) return -2;
 	memset(g_render.perf, 0, sizeof(g_render.perf));
 #endif
-	const int mask_words = (res_y + 31) / 32 + 2;
+	/* render_line itself clears words 0..30 (Cuda_Render.h:263), whatever res_y is */
+	const int mask_words = ((res_y + 31) / 32 > 31 ? (res_y + 31) / 32 : 31) + 2;
 	vec3f pos = g_render.ray_map.position;
 	vec3f rot = g_render.ray_map.rotation;
 #ifdef _OPENMP

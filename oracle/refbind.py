@@ -168,3 +168,72 @@ def ref_render_frame(rm, res, mip_distance=None, z_far=80000, rays=None, threads
     if rc != 0:
         raise RuntimeError("ref_render_frame rc=%d" % rc)
     return warp, (list(perf) if bench else None)
+
+
+# ---- our CPU restatement (oracle/rlerc_oracle.cpp) ------------------------------------------
+
+def port():
+    lib = _load("librlerc_oracle.so")
+    if not getattr(lib, "_typed", False):
+        lib.orc_build_map.argtypes = [C.c_void_p, C.c_ulonglong, C.c_int, C.c_int, C.c_void_p]
+        lib.orc_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                   C.POINTER(C.c_longlong), C.c_int, C.c_int, C.c_int]
+        lib.orc_unwarp.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                   C.c_int, C.c_int]
+        lib.orc_get_ray_map.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float, C.c_int, C.c_void_p]
+        lib._typed = True
+    return lib
+
+
+def have_port():
+    return os.path.exists(os.path.join(HERE, "librlerc_oracle.so"))
+
+
+COUNTER_NAMES = ["elems_total", "elems_processed", "voxels_processed", "elems_rendered", "pixels",
+                 "cols_fetched", "run_iters", "cols_nonempty", "cleared", "dda_steps"]
+
+
+def orc_get_ray_map(pos, rot, border, rays_res):
+    rm = RayMapGPU()
+    port().orc_get_ray_map((C.c_float * 3)(*pos), (C.c_float * 3)(*rot), border, rays_res, C.byref(rm))
+    return rm
+
+
+def orc_build_map(slabs, sx, sz):
+    slabs = np.ascontiguousarray(slabs, dtype=np.uint16)
+    mp = np.zeros(sx * sz * 2, np.uint32)
+    rc = port().orc_build_map(slabs.ctypes.data, slabs.size, sx, sz, mp.ctypes.data)
+    if rc:
+        raise RuntimeError("orc_build_map rc=%d" % rc)
+    return mp
+
+
+def orc_render(rm, res, rays_casted, mip_distance=None, z_far=80000, want_ids=False, threads=0, ray_begin=0, ray_end=-1):
+    """Returns (warp uint32[rays_casted,res], ids uint32[rays_casted,res,2] or None, counters dict)."""
+    warp = np.zeros((rays_casted, res), np.uint32)
+    ids = np.full((rays_casted, res, 2), 0xffffffff, np.uint32) if want_ids else None
+    cnt = (C.c_longlong * 10)()
+    rc = port().orc_render(C.byref(rm), res, mip_distance or res, z_far, warp.ctypes.data,
+                           ids.ctypes.data if want_ids else None, cnt, ray_begin, ray_end, threads)
+    if rc:
+        raise RuntimeError("orc_render rc=%d" % rc)
+    return warp, ids, dict(zip(COUNTER_NAMES, list(cnt)))
+
+
+def orc_unwarp(rm, W, H, RS, RC, rays_res, warp, ray_begin=0, ray_end=-1):
+    warp = np.ascontiguousarray(warp, dtype=np.uint32)
+    rgba = np.zeros((H, W, 4), np.uint8)
+    port().orc_unwarp(C.byref(rm), W, H, RS, RC, rays_res, warp.ctypes.data, rgba.ctypes.data, ray_begin, ray_end)
+    return rgba
+
+
+def attach_host_scene(rm, levels):
+    """Point rm.map4_gpu at host arrays: levels = [(sx, sy, sz, map uint32[], slabs uint16[]), ...].
+    What R/src/main.cpp:277-278 does with device pointers."""
+    for m, (sx, sy, sz, mp, sl) in enumerate(levels):
+        e = rm.map4_gpu[m]
+        e.sx, e.sy, e.sz = sx, sy, sz
+        e.slabs_size = min(len(sl), 0x7fffffff)
+        e.map, e.slabs = mp.ctypes.data, sl.ctypes.data
+    rm.nummaps = len(levels)
+    return rm

@@ -97,6 +97,9 @@ _SIGS = {
     "rlerc_render_counters": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "rlerc_unwarp": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int]),
     "rlerc_unwarp_slice": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int]),
+    "rlerc_render_interleaved": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
+    "rlerc_unwarp_interleaved": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "rlerc_set_stream": (C.c_int, [_P, _P]),
     "rlerc_render_frame": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), _P, _P, _P]),
     "rlerc_frame_submit": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), _P, _P]),
     "rlerc_frame_wait": (C.c_int, [_P, C.c_int]),
@@ -324,6 +327,16 @@ class Renderer:
 
     def unwarp_slice(self, raymap_gpu, cfg, ray_begin, ray_end, d_warp=None, d_rgba=None):
         _check(lib().rlerc_unwarp_slice(self._c, C.byref(raymap_gpu), C.byref(cfg), d_warp, d_rgba, ray_begin, ray_end))
+
+    def render_interleaved(self, raymap_gpu, cfg, block, nranks, rank, d_warp=None):
+        _check(lib().rlerc_render_interleaved(self._c, C.byref(raymap_gpu), C.byref(cfg), block, nranks, rank, d_warp))
+
+    def unwarp_interleaved(self, raymap_gpu, cfg, block, nranks, rank, d_warp=None, d_rgba=None):
+        _check(lib().rlerc_unwarp_interleaved(self._c, C.byref(raymap_gpu), C.byref(cfg), block, nranks, rank, d_warp, d_rgba))
+
+    def set_stream(self, cuda_stream):
+        """Launch on a caller-owned stream (int handle, e.g. torch.cuda.current_stream().cuda_stream)."""
+        _check(lib().rlerc_set_stream(self._c, cuda_stream))
 
     def render_frame(self, pos, rot, cfg, host_rgba):
         """get_ray_map -> traversal -> unwarp -> D2H (synchronous). Returns the ray map used."""

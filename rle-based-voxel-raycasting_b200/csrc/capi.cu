@@ -55,6 +55,7 @@ struct rlerc_ctx {
 	unsigned long long* d_counters = nullptr;
 	int lanes = 0;                      // 0 = auto
 	bool timing = false;
+	bool own_stream = true;
 	cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
 	bool ev_valid[2] = { false, false };
 	// pipeline
@@ -137,6 +138,7 @@ int fill_traverse(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_config
 	P.ray_begin = ray_begin; P.ray_end = ray_end;
 	P.mask_words = (cfg->render_size + 31) / 32 + 1;
 	P.warp = d_warp;
+	P.slice_block = 1; P.slice_n = 1; P.slice_rank = 0;
 	return RLERC_OK;
 }
 
@@ -161,6 +163,7 @@ int fill_unwarp(const rlerc_raymap* rm, const rlerc_frame_config* cfg, const uin
 	U.rot_x_gt0 = (rm->rotation.x > 0) ? 1 : 0;
 	U.row_begin = 0; U.row_end = cfg->height;
 	U.ray_begin = 0; U.ray_end = -1;
+	U.slice_block = 1; U.slice_n = 1; U.slice_rank = 0;
 	return RLERC_OK;
 }
 
@@ -210,7 +213,7 @@ void rlerc_destroy(rlerc_ctx* c)
 		if (c->slot[i].done) cudaEventDestroy(c->slot[i].done);
 	}
 	for (int i = 0; i < 4; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
-	if (c->stream) cudaStreamDestroy(c->stream);
+	if (c->stream && c->own_stream) cudaStreamDestroy(c->stream);
 	if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
 	delete c;
 }
@@ -312,7 +315,8 @@ int rlerc_warp_buffer(rlerc_ctx* c, const rlerc_frame_config* cfg, uint32_t** d_
 }
 
 static int render_impl(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_config* cfg,
-                       int ray_begin, int ray_end, uint32_t* d_warp, uint32_t* d_ids, bool ids)
+                       int ray_begin, int ray_end, uint32_t* d_warp, uint32_t* d_ids, bool ids,
+                       int slice_block = 1, int slice_n = 1, int slice_rank = 0)
 {
 	if (!c || !rm) { set_error("rlerc_render: null argument"); return RLERC_ERR_ARG; }
 	int rc = check_cfg(cfg);
@@ -326,6 +330,7 @@ static int render_impl(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_c
 	}
 	TraverseParams P;
 	if ((rc = fill_traverse(c, rm, cfg, ray_begin, ray_end, d_warp, P))) return rc;
+	if (slice_n > 1) { P.slice_block = slice_block; P.slice_n = slice_n; P.slice_rank = slice_rank; P.ray_begin = 0; }
 	if (ids)
 	{
 		if (!d_ids) { set_error("rlerc_render_ids: null ids buffer"); return RLERC_ERR_ARG; }
@@ -363,7 +368,8 @@ int rlerc_render_counters(rlerc_ctx* c, uint64_t out[10])
 }
 
 static int unwarp_impl(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_config* cfg, const uint32_t* d_warp,
-                       uint8_t* d_rgba, int row_begin, int row_end, int ray_begin, int ray_end)
+                       uint8_t* d_rgba, int row_begin, int row_end, int ray_begin, int ray_end,
+                       int slice_block = 1, int slice_n = 1, int slice_rank = 0)
 {
 	if (!c || !rm) { set_error("rlerc_unwarp: null argument"); return RLERC_ERR_ARG; }
 	int rc = check_cfg(cfg);
@@ -386,6 +392,7 @@ static int unwarp_impl(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_c
 	if (row_begin < 0) row_begin = 0;
 	U.row_begin = row_begin; U.row_end = row_end;
 	U.ray_begin = ray_begin; U.ray_end = ray_end;
+	if (slice_n > 1) { U.slice_block = slice_block; U.slice_n = slice_n; U.slice_rank = slice_rank; }
 	if (c->timing) CK(cudaEventRecord(c->ev[2], c->stream));
 	launch_unwarp(U, c->stream);
 	if (c->timing) { CK(cudaEventRecord(c->ev[3], c->stream)); c->ev_valid[1] = true; }
@@ -402,6 +409,37 @@ int rlerc_unwarp_slice(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_c
 {
 	if (ray_begin < 0 || ray_end < ray_begin) { set_error("rlerc_unwarp_slice: bad ray range"); return RLERC_ERR_ARG; }
 	return unwarp_impl(c, rm, cfg, d_warp, d_rgba, 0, -1, ray_begin, ray_end);
+}
+
+static int check_slice(int block, int nranks, int rank)
+{
+	if (block < 1 || nranks < 1 || rank < 0 || rank >= nranks) { set_error("bad interleaved slice (block %d, nranks %d, rank %d)", block, nranks, rank); return RLERC_ERR_ARG; }
+	return RLERC_OK;
+}
+
+int rlerc_render_interleaved(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_config* cfg, int block, int nranks, int rank, uint32_t* d_warp)
+{
+	int rc = check_slice(block, nranks, rank);
+	if (rc) return rc;
+	return render_impl(c, rm, cfg, 0, -1, d_warp, nullptr, false, block, nranks, rank);
+}
+
+int rlerc_unwarp_interleaved(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_config* cfg, int block, int nranks, int rank, const uint32_t* d_warp, uint8_t* d_rgba)
+{
+	int rc = check_slice(block, nranks, rank);
+	if (rc) return rc;
+	return unwarp_impl(c, rm, cfg, d_warp, d_rgba, 0, -1, 0, -1, block, nranks, rank);
+}
+
+int rlerc_set_stream(rlerc_ctx* c, void* cuda_stream)
+{
+	if (!c) return RLERC_ERR_ARG;
+	int rc = set_dev(c);
+	if (rc) return rc;
+	CK(cudaStreamSynchronize(c->stream));
+	if (c->own_stream) { cudaStreamDestroy(c->stream); c->own_stream = false; }
+	c->stream = (cudaStream_t)cuda_stream;
+	return RLERC_OK;
 }
 
 int rlerc_render_frame(rlerc_ctx* c, const float pos[3], const float rot[3], const rlerc_frame_config* cfg, uint8_t* host_rgba, rlerc_raymap* out_raymap)

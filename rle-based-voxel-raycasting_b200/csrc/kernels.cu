@@ -69,6 +69,27 @@ __device__ __forceinline__ float line_scale(float ix, float iy, float cx, float 
 	return (sx < sy) ? sx : sy;
 }
 
+// i-th ray plane of this launch: contiguous from ray_begin, or, for interleaved multi-GPU
+// slices, the i-th ray r >= ray_begin... with (r / slice_block) % slice_n == slice_rank.
+__device__ __forceinline__ int owned_ray(const TraverseParams& P, int i)
+{
+	if (P.slice_n <= 1) return P.ray_begin + i;
+	const int blk = i / P.slice_block, off = i - blk * P.slice_block;
+	return (blk * P.slice_n + P.slice_rank) * P.slice_block + off;
+}
+
+// host: how many rays of [0, count) an interleaved slice owns
+int owned_count(int count, int block, int n, int rank)
+{
+	if (n <= 1) return count;
+	const int cyc = block * n;
+	int owned = (count / cyc) * block;
+	int rem = count % cyc - rank * block;
+	if (rem > block) rem = block;
+	if (rem > 0) owned += rem;
+	return owned;
+}
+
 template <int G, bool IDS>
 __global__ void __launch_bounds__(RLERC_BLOCK)
 k_traverse(const __grid_constant__ TraverseParams P)
@@ -83,7 +104,7 @@ k_traverse(const __grid_constant__ TraverseParams P)
 	const unsigned gbits = (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
 	const unsigned gmask = gbits << gshift;
 
-	const int x = P.ray_begin + blockIdx.x * GPB + grp;
+	const int x = owned_ray(P, blockIdx.x * GPB + grp);
 	if (x >= P.ray_end) return;
 
 	// shared: [GPB][G] crossing records (2 x float4), then [GPB][mask_words] occlusion bits
@@ -547,7 +568,7 @@ k_traverse_w(const __grid_constant__ TraverseParams P)
 	const int wid = threadIdx.x >> 5;
 	const unsigned FULL = 0xffffffffu;
 
-	const int x = P.ray_begin + blockIdx.x * WPB + wid;
+	const int x = owned_ray(P, blockIdx.x * WPB + wid);
 	if (x >= P.ray_end) return;
 
 	// shared per warp: 33 crossing records (float4) | DrawJob (16 words) | occlusion bits
@@ -1241,7 +1262,7 @@ template <bool IDS>
 static void launch_traverse_w(const TraverseParams& p, cudaStream_t st)
 {
 	const int wpb = RLERC_BLOCK / 32;
-	const int rays = p.ray_end - p.ray_begin;
+	const int rays = (p.slice_n > 1) ? owned_count(p.ray_end, p.slice_block, p.slice_n, p.slice_rank) : p.ray_end - p.ray_begin;
 	if (rays <= 0) return;
 	const int blocks = (rays + wpb - 1) / wpb;
 	const size_t smem = (size_t)wpb * ((33 * 4 + 16 + p.mask_words + 3) & ~3) * sizeof(uint32_t);
@@ -1258,7 +1279,7 @@ template <int G, bool IDS>
 static void launch_traverse_t(const TraverseParams& p, cudaStream_t st)
 {
 	const int gpb = RLERC_BLOCK / G;
-	const int rays = p.ray_end - p.ray_begin;
+	const int rays = (p.slice_n > 1) ? owned_count(p.ray_end, p.slice_block, p.slice_n, p.slice_rank) : p.ray_end - p.ray_begin;
 	if (rays <= 0) return;
 	const int blocks = (rays + gpb - 1) / gpb;
 	const size_t smem = ((size_t)gpb * G * 8 + (size_t)gpb * p.mask_words) * sizeof(uint32_t);
@@ -1343,6 +1364,7 @@ __device__ __forceinline__ uint32_t unwarp_pixel(const UnwarpParams& P, int px, 
 	ix = ix < 0 ? 0 : (ix >= P.RS ? P.RS - 1 : ix);
 	iy = iy < 0 ? 0 : (iy >= P.RC ? P.RC - 1 : iy);
 	if (P.ray_end >= 0 && (iy < P.ray_begin || iy >= P.ray_end)) return 0u;   // slice mode
+	if (P.slice_n > 1 && (iy / P.slice_block) % P.slice_n != P.slice_rank) return 0u;
 	const uint32_t t = __ldg(P.warp + (size_t)iy * P.RS + ix);
 	const float cr = (float)(t & 255u) / 255.0f, cg = (float)((t >> 8) & 255u) / 255.0f;
 	const float cb = (float)((t >> 16) & 255u) / 255.0f, ca = (float)(t >> 24) / 255.0f;

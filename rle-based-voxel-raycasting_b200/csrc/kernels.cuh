@@ -31,6 +31,8 @@ struct TraverseParams {
 	int mapswitch0;          // int(MIP_DISTANCE * (0.25*(4-abs(rot.x)))), double math (Cuda_Render.h:335)
 	int z_far;
 	int ray_begin, ray_end;  // slice of the ray index range rendered by this launch
+	// interleaved multi-GPU slices: ray r belongs to this launch iff (r / slice_block) % slice_n == slice_rank
+	int slice_block, slice_n, slice_rank;
 	int mask_words;          // per-ray occlusion bitmask size in 32-bit words
 	uint32_t* warp;          // [rays_casted][res_y]
 	uint32_t* ids;           // optional [rays_casted][res_y][2]
@@ -48,7 +50,7 @@ struct UnwarpParams {
 	int rot_x_gt0;
 	int row_begin, row_end;
 	int ray_begin, ray_end;  // slice mode (ray_end < 0: off)
-	int rays_prefix_dummy;
+	int slice_block, slice_n, slice_rank;   // interleaved slice mode (slice_n <= 1: off)
 };
 
 void launch_traverse(const TraverseParams& p, int lanes_per_ray, bool ids, cudaStream_t st);

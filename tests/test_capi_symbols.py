@@ -1,0 +1,63 @@
+"""The C-ABI library loads and exports every symbol include/rlerc.h declares (no compute calls)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "rlerc.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    funcs = set(re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\([^;{}]*\)\s*;", src))
+    funcs -= {"defined"}
+    data = set(re.findall(r"extern\s+int\s+([A-Za-z_][A-Za-z0-9_]*)\s*;", src))
+    return funcs, data
+
+
+def test_header_declares_the_reference_surface():
+    funcs, data = declared_symbols()
+    # R/src/Cuda_Main.cu:124-126, R/src/core.h:144-147
+    for name in ("cuda_main_render2", "pboRegister", "pboUnregister", "gpu_malloc", "gpu_memcpy", "cpu_memcpy"):
+        assert name in funcs
+    assert "cpu_to_gpu_delta" in data
+    assert len(funcs) > 35
+
+
+def test_library_exports_every_declared_symbol(R):
+    lib = C.CDLL(R.LIB_PATH)
+    funcs, data = declared_symbols()
+    missing = [n for n in sorted(funcs | data) if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_python_mirror_binds_every_declared_function(R):
+    funcs, _ = declared_symbols()
+    assert funcs == set(R._SIGS), (funcs ^ set(R._SIGS))
+
+
+def test_struct_layouts_match_the_reference_abi(R):
+    assert C.sizeof(R.Map4) == 32          # R/src/Rle4.h:7-21 on LP64
+    assert C.sizeof(R.RayMapGPU) == 896    # R/src/RayMap.h:16-54 on LP64
+    assert R.RayMapGPU.map4_gpu.offset == 56 and R.RayMapGPU.to3d.offset == 796
+    cfg = R.FrameConfig.default(1024, 768)
+    # R/src/core.h:3-10, R/src/main.cpp:774
+    assert (cfg.render_size, cfg.rays_casted, cfg.rays_casted_res, cfg.z_far, cfg.mip_distance) == (1024, 4096, 4096, 80000, 1024)
+    assert cfg.border == 0.125
+
+
+def test_compute_fails_loudly_without_a_gpu(R):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(R.RlercError):
+        R.Renderer(0)
+
+
+def test_version_and_error_strings(R):
+    assert b"rlerc" in R.lib().rlerc_version()
+    p = C.c_void_p()
+    assert R.lib().rlerc_scene_load(b"/nonexistent/file.rle4", C.byref(p)) == -2
+    assert b"cannot open" in R.lib().rlerc_last_error()

@@ -1,0 +1,114 @@
+"""Pins the oracle port (oracle/rlerc_oracle.cpp) to the reference itself, compiled as host C++
+from /root/reference (oracle/_ref).  Runs wherever oracle/_ref has been built."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from util import camera_grid, few_cameras, levels_of, oracle_raymap
+
+
+@pytest.fixture(scope="module")
+def need_ref(have_ref):
+    if not have_ref:
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+
+
+def _both(R, rb, scene, cfg, pos, rot):
+    rm = R.RayMap(cfg).get_ray_map(pos, rot)
+    orm = oracle_raymap(rb, rm, scene)
+    ref, _ = rb.ref_render_frame(orm, cfg.render_size, mip_distance=cfg.mip_distance, z_far=cfg.z_far, rays=cfg.rays_casted)
+    port, ids, cnt = rb.orc_render(orm, cfg.render_size, cfg.rays_casted, cfg.mip_distance, cfg.z_far, want_ids=True)
+    return ref, port, ids, cnt
+
+
+def test_render_line_port_equals_reference_on_camera_grid(R, rb, need_ref, scene_mid):
+    cfg = R.FrameConfig.default(640, 480)
+    for pos, rot in camera_grid(-100.0):
+        ref, port, ids, cnt = _both(R, rb, scene_mid, cfg, pos, rot)
+        assert np.array_equal(ref, port), rot
+        # every written pixel has an identity, and nothing else does
+        has_id = ids[..., 0] != 0xffffffff
+        assert int(has_id.sum()) == cnt["pixels"]
+        assert not np.any(port[has_id] == 0xff8844)               # a hit never looks like sky (depth is even)
+        assert np.all(has_id[(port != 0) & (port != 0xff8844)])
+
+
+def test_render_line_port_equals_reference_other_scenes(R, rb, need_ref, scene_small, scene_runs):
+    for scene, h in ((scene_small, -40.0), (scene_runs, -90.0)):
+        cfg = R.FrameConfig.default(512, 384)
+        for pos, rot in few_cameras(h):
+            ref, port, ids, cnt = _both(R, rb, scene, cfg, pos, rot)
+            assert np.array_equal(ref, port), (h, rot)
+
+
+def test_render_line_port_non_default_config(R, rb, need_ref, scene_small):
+    """z_far, mip_distance and a non power-of-two render size are run-time here."""
+    cfg = R.FrameConfig.default(600, 400)
+    cfg.z_far = 5000
+    cfg.mip_distance = 300
+    for pos, rot in few_cameras(-40.0)[:3]:
+        ref, port, ids, cnt = _both(R, rb, scene_small, cfg, pos, rot)
+        assert np.array_equal(ref, port), rot
+
+
+def test_detail_bench_counters(R, rb, need_ref, scene_mid):
+    """The reference's own DETAIL_BENCH counters (Cuda_Render.h:14-22).  That build changes the control
+    flow (Cuda_Render.h:369-372,505-508: no early return, and columns are skipped once
+    y_clip_min>>1 >= y_clip_max>>1), so it stops a ray up to one pixel early and keeps counting
+    elems_total to z_far: its counters bound ours, they do not equal them."""
+    cfg = R.FrameConfig.default(640, 480)
+    pos, rot = few_cameras(-100.0)[0]
+    rm = R.RayMap(cfg).get_ray_map(pos, rot)
+    orm = oracle_raymap(rb, rm, scene_mid)
+    _, perf = rb.ref_render_frame(orm, cfg.render_size, mip_distance=cfg.mip_distance, z_far=cfg.z_far, bench=True)
+    _, _, cnt = rb.orc_render(orm, cfg.render_size, cfg.rays_casted, cfg.mip_distance, cfg.z_far)
+    assert 0.995 * cnt["pixels"] <= perf[4] <= cnt["pixels"]
+    assert 0.99 * cnt["elems_rendered"] <= perf[3] <= cnt["elems_rendered"]
+    assert perf[0] >= cnt["elems_total"] > 0
+
+
+def test_compressor_equals_reference(R, rb, need_ref):
+    """rlerc_scene_compress vs RLE4::compress_all on a CSG volume built with the reference's Tree."""
+    lib = rb.ref_host()
+    N = 64
+    for color in (1, 0):
+        t = lib.ref_tree_new(N, N, N, color)
+        lib.ref_tree_cube(t, 0, 40, 0, N, 50, N)
+        lib.ref_tree_sphere(t, 30, 25, 30, 12, 0)
+        lib.ref_tree_set_color(t, 3)
+        lib.ref_tree_sphere(t, 10, 38, 12, 6, 0)
+        lib.ref_tree_set_color(t, 0)
+        lib.ref_tree_sphere(t, 50, 38, 40, 7, 0)
+        lib.ref_tree_sphere(t, 20, 45, 50, 9, 1)      # carve
+        nb = N * N * N // 8
+        grab = lambda p: np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(nb,)).copy()
+        vox = grab(lib.ref_tree_voxel(t))
+        c1 = grab(lib.ref_tree_col1(t)) if color else None
+        c2 = grab(lib.ref_tree_col2(t)) if color else None
+        ref = rb.RefScene(lib.ref_compress_all(t))
+        mine = R.RLE4.compress_all(vox, N, N, N, c1, c2)
+        assert ref.nummaps == mine.nummaps == 6
+        for m in range(ref.nummaps):
+            a, b = ref.level(m, 1), mine.level(m)
+            assert a[:3] == b[:3]
+            if a[0] < 8:
+                # levels narrower than 8 voxels: the reference's Tree::init allocates (sx/8)*sy*sz = 0
+                # bytes and writes past it (tree.h:132-137) — undefined contents, not compared
+                continue
+            assert np.array_equal(a[4], b[4]), m
+            assert np.array_equal(a[3], b[3][0::2]), m     # compress() emits offsets only (Rle4.cpp:78)
+
+
+def test_loader_equals_reference(R, rb, need_ref, scene_mid, tmp_path):
+    f = str(tmp_path / "s.rle4")
+    scene_mid.save(f)
+    ref = rb.RefScene.load(f)
+    assert ref.nummaps == scene_mid.nummaps
+    for m in range(ref.nummaps):
+        a, b = ref.level(m), scene_mid.level(m)
+        assert a[:3] == b[:3] and np.array_equal(a[3], b[3]) and np.array_equal(a[4], b[4])
+    # and the reference's writer produces the bytes ours does
+    g = str(tmp_path / "r.rle4")
+    ref.save(g)
+    assert open(f, "rb").read() == open(g, "rb").read()
