@@ -425,6 +425,9 @@ int orc_render(const void* raymap, int res, int mip_distance, int z_far, uint32_
  * from the warped buffer seen as an RGBA8 texture RS wide x RC tall; fragment centres at +0.5,
  * GL origin bottom-left.  Output RGBA8 [H][W][4] with row 0 = TOP of the window, the 8-bit
  * quantisation of the GL_RGBA8 FBO it renders into (R/src/GL_Main.h:151): round(clamp(c)*255). */
+static int32_t* g_texel_out = 0;   /* optional int32[H][W][2] = {ray row iy, texel ix} chosen per pixel */
+void orc_unwarp_set_texel_output(int32_t* p) { g_texel_out = p; }
+
 int orc_unwarp(const void* raymap, int W, int H, int RS, int RC, int rays_casted_res, const uint32_t* warp, uint8_t* rgba,
                int ray_begin, int ray_end)
 {
@@ -471,6 +474,7 @@ int orc_unwarp(const void* raymap, int W, int H, int RS, int RC, int rays_casted
 			ix = ix < 0 ? 0 : (ix >= RS ? RS - 1 : ix);
 			iy = iy < 0 ? 0 : (iy >= RC ? RC - 1 : iy);
 			uint8_t* o = rgba + ((size_t)row * W + px) * 4;
+			if (g_texel_out) { g_texel_out[((size_t)row * W + px) * 2] = iy; g_texel_out[((size_t)row * W + px) * 2 + 1] = ix; }
 			if (ray_end >= 0 && (iy < ray_begin || iy >= ray_end)) { o[0] = o[1] = o[2] = o[3] = 0; continue; }
 			const uint32_t t = warp[(size_t)iy * RS + ix];
 			const float cr = (float)(t & 255u) / 255.0f, cg = (float)((t >> 8) & 255u) / 255.0f;

@@ -182,13 +182,20 @@ k_traverse(const __grid_constant__ TraverseParams P)
 		if (q1y < 0) q1y = 0; if (q1y >= res_y) q1y = res_y - 1;
 		if (q2x < 0) q2x = 0; if (q2x >= res_x) q2x = res_x - 1;
 		if (q2y < 0) q2y = 0; if (q2y >= res_y) q2y = res_y - 1;
-		if (q1y == q2y) return;                         // Cuda_Render.h:226
+		bool skip_ray = (q1y == q2y);                   // Cuda_Render.h:226
 		ycmin = res_x - 1 - q1x;
 		ycmax = res_x - 1 - q2x;
 		if (vertical) { ycmin = res_y - 1 - q1y; ycmax = res_y - 1 - q2y; }
 		if (reverse) { ycmin = res_y - 1 - ycmin; ycmax = res_y - 1 - ycmax; }
 		if (ycmin > ycmax) { const int t = ycmin; ycmin = ycmax; ycmax = t; }
-		if (ycmin >= ycmax) return;
+		if (ycmin >= ycmax) skip_ray = true;            // Cuda_Render.h:250
+		// Texels outside the clip range are never written by the reference (stale from the previous
+		// frame) yet the unwarp samples a few of them; they are defined as 0 here so
+		// that a frame does not depend on history.
+		if (skip_ray) { ycmin = res_y; ycmax = res_y - 1; }
+		for (int y = gl; y < ycmin; y += G) row[y] = 0;
+		for (int y = ycmax + 1 + gl; y < res_y; y += G) row[y] = 0;
+		if (skip_ray) return;
 	}
 	const int ymin0 = ycmin, ymax0 = ycmax;
 
@@ -646,13 +653,18 @@ k_traverse_w(const __grid_constant__ TraverseParams P)
 		if (q1y < 0) q1y = 0; if (q1y >= res_y) q1y = res_y - 1;
 		if (q2x < 0) q2x = 0; if (q2x >= res_x) q2x = res_x - 1;
 		if (q2y < 0) q2y = 0; if (q2y >= res_y) q2y = res_y - 1;
-		if (q1y == q2y) return;
+		bool skip_ray = (q1y == q2y);                   // Cuda_Render.h:226
 		ycmin = res_x - 1 - q1x;
 		ycmax = res_x - 1 - q2x;
 		if (vertical) { ycmin = res_y - 1 - q1y; ycmax = res_y - 1 - q2y; }
 		if (reverse) { ycmin = res_y - 1 - ycmin; ycmax = res_y - 1 - ycmax; }
 		if (ycmin > ycmax) { const int t = ycmin; ycmin = ycmax; ycmax = t; }
-		if (ycmin >= ycmax) return;
+		if (ycmin >= ycmax) skip_ray = true;            // Cuda_Render.h:250
+		// texels outside the clip range: defined as 0 (see k_traverse / DESIGN.md §4)
+		if (skip_ray) { ycmin = res_y; ycmax = res_y - 1; }
+		for (int y = gl; y < ycmin; y += G) row[y] = 0;
+		for (int y = ycmax + 1 + gl; y < res_y; y += G) row[y] = 0;
+		if (skip_ray) return;
 	}
 	const int ymin0 = ycmin, ymax0 = ycmax;
 

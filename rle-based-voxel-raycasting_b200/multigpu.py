@@ -30,7 +30,7 @@ def owned_count(count, block, nranks, rank):
 def composite(image, dist, dst=0):
     """Sum-reduce the per-rank images (uint8 tensors with disjoint support) onto rank `dst`.
     NCCL over NVLink on GPUs; gloo in the CPU tests.  Returns `image` (complete on rank dst)."""
-    if dist.get_world_size() > 1:
+    if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
         dist.reduce(image, dst=dst, op=dist.ReduceOp.SUM)
     return image
 
@@ -38,9 +38,9 @@ def composite(image, dist, dst=0):
 class SlicedFrame:
     """Per-rank driver of a sliced frame: traverse own ray planes -> unwarp own pixels -> composite."""
 
-    def __init__(self, renderer, cfg, dist, torch, block=DEFAULT_BLOCK):
+    def __init__(self, renderer, cfg, torch, rank=0, world=1, dist=None, block=DEFAULT_BLOCK):
         self.r, self.cfg, self.dist, self.torch, self.block = renderer, cfg, dist, torch, block
-        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.rank, self.world = rank, world
         dev = torch.device("cuda", renderer.device)
         self.rgba = torch.zeros((cfg.height, cfg.width, 4), dtype=torch.uint8, device=dev)
         # kernels and the collective share torch's current stream: ordering without host syncs

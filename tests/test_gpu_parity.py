@@ -215,6 +215,26 @@ def test_ray_slices_compose_to_the_full_frame(R, gpu, scene_mid):
         assert torch.equal(acc.to(torch.uint8), full_img), (block, world)
 
 
+def test_frame_does_not_depend_on_history(R, rb, gpu, scene_mid):
+    """Texels the reference leaves stale (outside a ray's clip range) are defined as 0 here: a frame
+    rendered over garbage equals the frame rendered over zeros; rows of unused ray planes stay untouched."""
+    gpu.all_to_gpu(scene_mid)
+    cfg = R.FrameConfig.default(640, 480)
+    for lanes in (0, 32):
+        gpu.set_lanes_per_ray(lanes)
+        for pos, rot in few_cameras(-100.0)[:3]:
+            rm = R.RayMap(cfg).get_ray_map(pos, rot)
+            _, want, _, _ = _oracle(rb, rm, scene_mid, cfg)
+            wp = gpu.warp_buffer(cfg)
+            gpu.upload(wp, np.full((cfg.rays_casted, cfg.render_size), 0xdeadbeef, np.uint32))
+            gpu.render(rm, cfg)
+            got = gpu.read_warp(cfg)
+            n = rm.map_line_count
+            assert np.array_equal(got[:n], want[:n])
+            assert np.all(got[n:] == 0xdeadbeef)
+    gpu.set_lanes_per_ray(0)
+
+
 def test_physical_tiling_equals_coordinate_wrap(R, gpu, scene_small):
     """Size-independent property: the traversal wraps coordinates with & (grid-1) (Cuda_Render.h:441-442),
     so a physically 4x4-tiled scene must render the identical frame."""
