@@ -1,0 +1,763 @@
+// k_traverse_w — the production traversal kernel: one WARP per ray plane, lane <-> COLUMN,
+// software-pipelined over batches of 32 cell crossings.  Replaces cudaRender +
+// Render::render_line (R/src/Cuda_Main.cu:150-181, R/src/Cuda_Render.h:96-737) and gives the
+// same warped ray buffer bit for bit (arithmetic contract: see kernels.cu / DESIGN.md §3).
+//
+// The serial algorithm pays one dependent memory round trip chain per visited column
+// (pointer-map entry -> run words -> attribute word) and one ray plane is inherently
+// sequential in its occlusion state.  What is NOT sequential is everything that does not read
+// that state, so the work of a ray plane is split into a state-free front end, which runs
+// 32 columns wide and two batches ahead, and a state-carrying back end, which only spends
+// time on the columns that actually draw:
+//
+//   A   DDA for the next 32 cell crossings (uniform serial float recurrence, integer-budgeted
+//       so the inner loop has no LOD / z_far tests); every lane keeps one crossing, turns it
+//       into a column address + projected cell, applies a conservative top-clip test and
+//       issues its 8-byte pointer-map gather.                                  [batch b+2]
+//   C1  the entry has arrived: issue the loads of the column's next run words (the first
+//       run rides in the entry).                                                [batch b+1]
+//   C2  the run words have arrived: project up to RW runs to screen rows (2 divides each)
+//       into shared memory; a run that already breaks under the current horizon ends the
+//       column for good (the horizon only rises).                               [batch b]
+//   B   consume batch b in front-to-back order: each lane checks whether ITS column would
+//       draw under the current floating-horizon bounds; a ballot finds the first such
+//       column; all columns before it are provable no-ops and cost nothing.  The owner lane
+//       advances the state through its column in the serial statement order; short pixel
+//       spans are shaded by the owner (attribute gathers left in flight, stores flushed at the
+//       end of the batch), long spans by the whole warp with coalesced stores.  Columns with
+//       more than RW undecided runs use the lane <-> run scheme (as k_traverse<32>).
+//
+// Loads issued in A and C1 have a whole consume phase to land before they are used.
+#include <stdint.h>
+#include <limits.h>
+#include "kernels.cuh"
+#include "device_common.cuh"
+
+namespace rlerc {
+
+#define RLERC_RW 8          // runs pre-projected per column (first 8 run words)
+#define RLERC_COOP_MIN 12   // pixel spans at least this long are shaded by the whole warp
+
+struct DrawJob {            // owner lane -> warp hand-off for a long pixel span (shared memory)
+	float cpz, cpy;
+	int y, s2, rtop, rbot, rtex, rtexn;
+	int m, colid;
+	unsigned e0, slen;
+};
+
+// One batch of 32 columns in flight: what a lane knows about its column.
+struct Stage {
+	float pz, py, czz, cyy;  // pos3d_z, pos3d_y (scaled), corr_zz, corr_yy (Cuda_Render.h:459-464,483-486)
+	int cmip, cidx;          // mip level and column index vx + vz*gridx
+	unsigned e0, e1;         // pointer-map entry
+	unsigned rw[4];          // run words 0..7, two per register
+	int nvalid;              // crossings in this batch (uniform); 0 = empty stage
+	bool have;               // this lane's column may be visited
+};
+
+// run word r (0..7) of a stage
+__device__ __forceinline__ unsigned run_word(const unsigned (&rw)[4], int r)
+{
+	return (rw[r >> 1] >> ((r & 1) * 16)) & 0xffffu;
+}
+
+template <bool IDS>
+__global__ void __launch_bounds__(RLERC_BLOCK, 3)
+k_traverse_w(const __grid_constant__ TraverseParams P)
+{
+	extern __shared__ __align__(16) uint32_t smem[];
+	constexpr int G = 32;
+	constexpr int WPB = RLERC_BLOCK / 32;
+	const int gl = threadIdx.x & 31;
+	const int wid = threadIdx.x >> 5;
+	const unsigned FULL = 0xffffffffu;
+
+	const int x = owned_ray(P, blockIdx.x * WPB + wid);
+	if (x >= P.ray_end) return;
+
+	// shared per warp: 33 crossing records (float4) | DrawJob (16 words) | RW x 32 projected runs (int2) |
+	//                  RW x 32 deferred short spans | occlusion bits
+	const int per_warp = ((G + 1) * 4 + 16 + RLERC_RW * 96 + P.mask_words + 3) & ~3;
+	uint32_t* wbase = smem + (size_t)wid * per_warp;
+	float4* rec = reinterpret_cast<float4*>(wbase);
+	DrawJob* job = reinterpret_cast<DrawJob*>(wbase + (G + 1) * 4);
+	int2* proj = reinterpret_cast<int2*>(wbase + (G + 1) * 4 + 16);     // [r][lane] = {scr_y1, scr_y2}
+	uint32_t* shade = wbase + (G + 1) * 4 + 16 + RLERC_RW * 64;         // [r][lane] deferred short spans
+	uint32_t* ymask = wbase + (G + 1) * 4 + 16 + RLERC_RW * 96;
+
+	const int res_y = P.res_y;
+	const float res_y2 = (float)(res_y / 2);             // Cuda_Render.h:108 (integer division)
+	uint32_t* row = P.warp + (size_t)x * res_y;
+
+	RayInit ri;
+	ray_init(P, x, ri);
+	clear_outside<G>(row, res_y, ri, gl);
+	if (ri.skip) return;
+	const float ray_x = ri.ray_x, ray_z = ri.ray_z, rx2mr = ri.rx2mr;
+	const bool vertical = ri.vertical;
+	const float sin_x = P.sin_x, cos_x = P.cos_x;
+	int ycmin = ri.ycmin, ycmax = ri.ycmax;
+	const int ymin0 = ycmin, ymax0 = ycmax;
+
+	// occlusion mask clear; the sky sentinel is written at the end to the pixels that stayed
+	// open (same final row as clear-then-overwrite, Cuda_Render.h:255-264)
+	for (int w = gl; w < P.mask_words; w += G) ymask[w] = 0;
+	__syncwarp();
+
+	const float vpx = P.viewpos[0], mountain = P.viewpos[1], vpz = P.viewpos[2];
+	Dda dd;
+	dda_init(P, ray_x, ray_z, dd);
+	const int fixx = dd.fixx, fixz = dd.fixz;
+	float g0x = dd.g0x, g0y = dd.g0y, g1x = dd.g1x, g1y = dd.g1y, i0x = dd.i0x, i0y = dd.i0y, i1x = dd.i1x, i1y = dd.i1y;
+	float gd0 = dd.gd0, gd1 = dd.gd1, d0 = dd.d0, d1 = dd.d1;
+	float posx = 0, posy = 0, dist_now = 0;
+	int index = 0;
+	int mip = 0;
+	const float pz_add = sin_x;                                  // pos3d_z_add (Cuda_Render.h:313)
+	const float py_add = (vertical ? cos_x : 0.0f) * rx2mr;      // pos3d_y_add (Cuda_Render.h:314-315)
+	int zi = 0, dzi = 1;                                         // z and dz (Cuda_Render.h:181,325), integer valued
+	int mapswitch = P.mapswitch0;
+	const int zfar_i = P.z_far;
+	const int last_map = P.nummaps - 1;
+	// The y_map_switch half of the LOD loop condition (Cuda_Render.h:343) can only be true on
+	// the first crossing (it halves until <= 512 and never grows), where z = 0 < mapswitch.
+	for (float yms = mountain; yms > 512.0f; yms = yms * 0.5f)
+	{
+		if (mip < last_map) mip++;
+		g0x *= 2; g0y *= 2; g1x *= 2; g1y *= 2;
+		gd0 *= 2; gd1 *= 2;
+		mapswitch *= 2;
+		dzi *= 2;
+	}
+
+	// per-lane statistics (IDS build only)
+	unsigned long long c_total = 0, c_proc = 0, c_vox = 0, c_rend = 0, c_pix = 0, c_cols = 0, c_iter = 0, c_cols1 = 0, c_steps = 0;
+
+	Stage s0, s1, s2;
+	s0.nvalid = s1.nvalid = s2.nvalid = 0;
+	s0.have = s1.have = s2.have = false;
+	s0.pz = s0.py = s0.czz = s0.cyy = 0; s0.cmip = s0.cidx = 0; s0.e0 = s0.e1 = 0;
+	s1 = s0; s2 = s0;
+	#pragma unroll
+	for (int k = 0; k < 4; k++) { s0.rw[k] = 0; s1.rw[k] = 0; s2.rw[k] = 0; }
+	bool dda_done = false;
+
+	while (true)
+	{
+		if (ycmin >= ycmax) break;                               // Cuda_Render.h:370
+		s0 = s1; s1 = s2;
+		s2.nvalid = 0; s2.have = false;
+
+		// ---- C2. project the runs of batch s0 (their words were requested one iteration ago) ----
+		int slen = 0, nr = 0;
+		bool longcol = false;
+		unsigned flags = 0;               // bit r: run r can be seen (z1 > 0); bit 8+r: its bottom too (z2 > 0)
+		if (s0.have)
+		{
+			slen = (int)(s0.e1 & 0xffffu);
+			nr = slen < RLERC_RW ? slen : RLERC_RW;
+			longcol = slen > RLERC_RW;
+			int blen = 0;
+			bool stop = false;
+			#pragma unroll
+			for (int r = 0; r < RLERC_RW; r++)
+			{
+				const unsigned rw = run_word(s0.rw, r);
+				const int skip = (int)(rw & 1023u), solid = (int)(rw >> 10);
+				const int top = (blen + skip) << s0.cmip;                // sti_general_sti_skip
+				const int bot = top + (solid << s0.cmip);                // sti_general
+				blen += skip + solid;
+				if (r < nr && !stop && solid > 0)
+				{
+					const float ft = (float)top, fb = (float)bot;       // Cuda_Render.h:529-560
+					float zz1 = s0.pz, yy1 = s0.py;
+					if (mountain + ft >= 0) { zz1 += s0.czz; yy1 += s0.cyy; }
+					const float z1 = zz1 + pz_add * ft;
+					if (!(z1 <= 0))
+					{
+						flags |= 1u << r;
+						const float y1 = yy1 + py_add * ft;
+						const int sy2 = f2i(res_y2 + y1 / z1);
+						int sy1 = 0;
+						if (sy2 <= ycmin)
+						{
+							// breaks now, hence under every later (higher) horizon: later runs are dead
+							stop = true; nr = r + 1; longcol = false;
+						}
+						else
+						{
+							float zz2 = s0.pz, yy2 = s0.py;
+							if (mountain + fb < 0) { zz2 += s0.czz; yy2 += s0.cyy; }
+							const float z2 = zz2 + pz_add * fb;
+							if (!(z2 <= 0))
+							{
+								flags |= 1u << (8 + r);
+								const float y2 = yy2 + py_add * fb;
+								sy1 = f2i(res_y2 + y2 / z2 - 1);
+							}
+						}
+						proj[r * 32 + gl] = make_int2(sy1, sy2);
+					}
+				}
+			}
+		}
+
+		// ---- A. next batch of crossings: DDA, column address, conservative top clip, map gather ---
+		if (!dda_done)
+		{
+			// z, dz, mapswitch and z_far are integer valued (z counts steps of 2^k), so the number of
+			// crossings before the next LOD switch / before z_far is known up front and the inner
+			// loop runs without per-step tests.  Slot s+1 receives the state after crossing s; slot
+			// 0 carries the state before the batch.  All lanes store the same words (uniform address).
+			int nvalid = G;
+			rec[0] = make_float4(dist_now, posx, posy, __int_as_float(index));
+			for (int s = 0; s < G;)
+			{
+				while (zi > mapswitch)                               // Cuda_Render.h:343-365
+				{
+					if (mip < last_map) mip++;
+					g0x *= 2; g0y *= 2; g1x *= 2; g1y *= 2;
+					gd0 *= 2; gd1 *= 2;
+					mapswitch *= 2;
+					dzi *= 2;
+				}
+				const int lod_free = (mapswitch - zi) / dzi + 1;     // crossings before z > mapswitch
+				const int far_free = (zfar_i - zi) / dzi;            // crossings with z + dz <= z_far (Cuda_Render.h:366-367)
+				if (far_free <= 0) { nvalid = s; break; }
+				int n = G - s;
+				n = n < lod_free ? n : lod_free;
+				n = n < far_free ? n : far_free;
+				const int mipbits = mip << 1;
+				float4* out = rec + s + 1;
+				#define RLERC_DDA_STEP(K)                                                         \
+					{                                                                             \
+						const bool t1 = d1 < d0;                      /* Cuda_Render.h:398-414 */ \
+						dist_now = t1 ? d1 : d0;                                                  \
+						posx = t1 ? i1x : i0x;                                                    \
+						posy = t1 ? i1y : i0y;                                                    \
+						if (t1) { d1 += gd1; i1x += g1x; i1y += g1y; }                            \
+						else    { d0 += gd0; i0x += g0x; i0y += g0y; }                            \
+						out[K] = make_float4(dist_now, posx, posy, __int_as_float(mipbits | (t1 ? 1 : 0))); \
+					}
+				int j = 0;
+				for (; j + 4 <= n; j += 4)
+				{
+					RLERC_DDA_STEP(j) RLERC_DDA_STEP(j + 1) RLERC_DDA_STEP(j + 2) RLERC_DDA_STEP(j + 3)
+				}
+				for (; j < n; j++) RLERC_DDA_STEP(j)
+				#undef RLERC_DDA_STEP
+				index = __float_as_int(out[n - 1].w) & 1;
+				zi += n * dzi;
+				s += n;
+			}
+			if (nvalid < G) dda_done = true;
+			if (IDS && gl == 0) c_steps += nvalid;
+			s2.nvalid = nvalid;
+			if (gl < nvalid)
+			{
+				const float4 ra = rec[gl], rb = rec[gl + 1];        // state before / after crossing gl
+				const float db = ra.x, dn = rb.x;
+				const int ib = __float_as_int(ra.w) & 1;
+				s2.cmip = __float_as_int(rb.w) >> 1;
+				const int fix_x = (1 - ib) * fixx, fix_z = ib * fixz;    // Cuda_Render.h:418-419
+				const float ddelta = dn - db;
+				const float vsx = ray_x * db, vsz = ray_z * db;
+				const int voxel_x = f2i(vpx + ra.y) + fix_x;             // Cuda_Render.h:429-430
+				const int voxel_z = f2i(vpz + ra.z) + fix_z;
+				const int gx = P.level[s2.cmip].sx, gz = P.level[s2.cmip].sz;
+				const int vx = (voxel_x >> s2.cmip) & (gx - 1);          // Cuda_Render.h:441-442
+				const int vz = (voxel_z >> s2.cmip) & (gz - 1);
+				s2.cidx = vx + vz * gx;
+				const float corx = ray_x * ddelta, corz = ray_z * ddelta;
+				s2.pz = cos_x * vsz + sin_x * mountain;                  // Cuda_Render.h:459-464
+				s2.py = vertical ? (cos_x * mountain - sin_x * vsz) : vsx;
+				s2.py *= rx2mr;
+				s2.czz = cos_x * corz;                                   // Cuda_Render.h:483-486
+				s2.cyy = vertical ? (-sin_x * corz) : corx;
+				s2.cyy *= rx2mr;
+				// The horizon only rises until this batch is consumed.  For pz > 0 a column culled
+				// now stays culled; for pz <= 0 (or NaN) the test can flip, so keep those.
+				s2.have = !(s2.pz * res_y2 + s2.py <= s2.pz * (float)ycmin) || !(s2.pz > 0);
+				if (s2.have)
+				{
+					const uint2 ent = __ldg(P.level[s2.cmip].map + s2.cidx);     // Cuda_Render.h:474-478
+					s2.e0 = ent.x; s2.e1 = ent.y;
+				}
+			}
+		}
+
+		// ---- C1. run words of batch s1 (its entries were requested one iteration ago) ------------
+		if (s1.have)
+		{
+			const int sl = (int)(s1.e1 & 0xffffu);
+			// element i0 of the slab stream is run 0; runs 0..7 are fetched as aligned 32-bit words
+			const unsigned i0 = 2u + s1.e0;
+			const uint32_t* w32 = reinterpret_cast<const uint32_t*>(P.level[s1.cmip].slabs);
+			const unsigned first = s1.e1 >> 16;
+			if (!(i0 & 1u))
+			{
+				const uint32_t* p = w32 + (i0 >> 1);
+				s1.rw[0] = first | ((sl > 1) ? (__ldg(p) & 0xffff0000u) : 0u);
+				s1.rw[1] = (sl > 2) ? __ldg(p + 1) : 0u;
+				s1.rw[2] = (sl > 4) ? __ldg(p + 2) : 0u;
+				s1.rw[3] = (sl > 6) ? __ldg(p + 3) : 0u;
+			}
+			else
+			{
+				const uint32_t* p = w32 + ((i0 + 1) >> 1);              // words hold runs (1,2) (3,4) (5,6) (7,8)
+				const unsigned a = (sl > 1) ? __ldg(p) : 0u;
+				const unsigned b = (sl > 3) ? __ldg(p + 1) : 0u;
+				const unsigned c = (sl > 5) ? __ldg(p + 2) : 0u;
+				const unsigned d = (sl > 7) ? __ldg(p + 3) : 0u;
+				s1.rw[0] = first | (a << 16);
+				s1.rw[1] = __funnelshift_r(a, b, 16);
+				s1.rw[2] = __funnelshift_r(b, c, 16);
+				s1.rw[3] = __funnelshift_r(c, d, 16);
+			}
+		}
+
+		// ---- B. consume batch s0: only columns that draw under the current bounds change anything ---
+		unsigned todo = (s0.nvalid >= 32) ? FULL : ((1u << s0.nvalid) - 1u);
+		bool finished = false;
+		unsigned shade_runs = 0;          // runs of my column with a deferred short span
+		while (todo)
+		{
+			if (ycmin >= ycmax) { finished = true; break; }
+			const bool mine = (todo >> gl) & 1u;
+			const bool pass = mine && s0.have && !(s0.pz * res_y2 + s0.py <= s0.pz * (float)ycmin);   // Cuda_Render.h:467
+			// does my column draw (or is it too long to tell)?  also: where would its run loop stop
+			bool ev = false;
+			int my_iter = slen, my_proc = 0, my_vox = 0;
+			if (pass)
+			{
+				bool brk = false;
+				#pragma unroll
+				for (int r = 0; r < RLERC_RW; r++)
+				{
+					if (r < nr && !ev && !brk)
+					{
+						if (IDS)
+						{
+							const unsigned rw = run_word(s0.rw, r);
+							if (rw >> 10) { my_proc++; my_vox += (int)(rw >> 10) << s0.cmip; }
+						}
+						if ((flags >> r) & 1u)
+						{
+							const int2 sy = proj[r * 32 + gl];
+							if (sy.y <= ycmin) { brk = true; if (IDS) my_iter = r + 1; }
+							else if (((flags >> (8 + r)) & 1u) && !(sy.x >= ycmax)) ev = true;
+						}
+					}
+				}
+				if (!ev && !brk && longcol) ev = true;
+			}
+			const unsigned eb = __ballot_sync(FULL, ev);
+			const int L = eb ? (__ffs(eb) - 1) : 32;
+			if (IDS)
+			{
+				// every passing column up to (and including) the event column is "fetched" in the serial order
+				const unsigned upto = (L >= 31) ? FULL : ((2u << L) - 1u);
+				if (pass && ((upto >> gl) & 1u))
+				{
+					c_cols++; c_total += slen; if (slen) c_cols1++;
+					if (gl != L) { c_iter += my_iter; c_proc += my_proc; c_vox += my_vox; }
+				}
+			}
+			if (!eb) break;
+			todo &= ~((2u << L) - 1u);
+
+			const bool Llong = __shfl_sync(FULL, (int)longcol, L) != 0;
+			if (!Llong)
+			{
+				// ---- owner lane advances the state through its column, serial statement order ----
+				int rstart = 0;
+				while (true)
+				{
+					int act = 0;      // 0 = column finished, 1 = long pixel span handed to the warp
+					if (gl == L)
+					{
+						int blen = 0, btex = 0;
+						bool fin = false;
+						#pragma unroll
+						for (int r = 0; r < RLERC_RW; r++)
+						{
+							const unsigned rw = run_word(s0.rw, r);
+							const int skip = (int)(rw & 1023u), solid = (int)(rw >> 10);
+							const int top = (blen + skip) << s0.cmip;
+							const int bot = top + (solid << s0.cmip);
+							const int texture = btex, texn = btex + solid;
+							blen += skip + solid; btex += solid;
+							if (r >= rstart && r < nr && !fin && act == 0)
+							{
+								if (IDS) { c_iter++; if (solid > 0) { c_proc++; c_vox += solid << s0.cmip; } }
+								if ((flags >> r) & 1u)
+								{
+									const int2 sy = proj[r * 32 + gl];
+									if (sy.y <= ycmin) fin = true;                                     // Cuda_Render.h:543
+									else if (((flags >> (8 + r)) & 1u) && !(sy.x >= ycmax))
+									{
+										int s2y = sy.y, s1y = sy.x;
+										if (s2y >= ycmax) { s2y = ycmax; ycmax = s1y; }                  // Cuda_Render.h:564-580
+										if (s1y <= ycmin)
+										{
+											s1y = ycmin;
+											ycmin = s2y;
+											ycmin = first_clear(ymask, ycmin, ycmax);
+										}
+										int y = first_clear(ymask, s1y, s2y);                        // Cuda_Render.h:639-640
+										if (y < s2y)
+										{
+											if (IDS) c_rend++;
+											const int n = s2y - y;
+											if (n >= RLERC_COOP_MIN)
+											{
+												job->cpz = s0.pz; job->cpy = s0.py;
+												job->y = y; job->s2 = s2y; job->rtop = top; job->rbot = bot;
+												job->rtex = texture; job->rtexn = texn;
+												job->m = s0.cmip; job->colid = s0.cidx; job->e0 = s0.e0; job->slen = (unsigned)slen;
+												act = 1; rstart = r + 1;
+											}
+											else
+											{
+												// short span: fix WHICH pixels it owns now (that is all the occlusion
+												// state needs) and leave the shading to the end of the batch, where
+												// all lanes shade their spans side by side
+												const int w = y >> 5, sh = y & 31;
+												unsigned bits = ymask[w] >> sh;
+												if (sh) bits |= ymask[w + 1] << (32 - sh);
+												const unsigned clear = ~bits & ((1u << n) - 1u);
+												ymask[w] |= clear << sh;
+												if (sh && (clear >> (32 - sh))) ymask[w + 1] |= clear >> (32 - sh);
+												shade[r * 32 + gl] = (unsigned)y | ((unsigned)n << 16) | (clear << 20);
+												shade_runs |= 1u << r;
+											}
+										}
+									}
+								}
+							}
+						}
+					}
+					act = __shfl_sync(FULL, act, L);
+					__syncwarp();
+					if (act == 0) break;
+
+					// ---- long pixel span: whole warp, 32 pixels at a time --------------------------
+					const DrawJob J = *job;
+					const float ft = (float)J.rtop, fb2 = (float)J.rbot;
+					const float z1r = J.cpz + pz_add * ft, y1r = J.cpy + py_add * ft;
+					const float z2r = J.cpz + pz_add * fb2, y2r = J.cpy + py_add * fb2;
+					const float s2r = res_y2 + y1r / z1r;
+					const float s1r = res_y2 + y2r / z2r;
+					const float u1z = (float)J.rtexn / z2r;
+					float u2dz = (float)J.rtex / z1r - u1z;
+					const float onez1 = 1.0f / z2r;
+					float onedz2 = 1.0f / z1r - onez1;
+					u2dz /= s2r - s1r;
+					onedz2 /= s2r - s1r;
+					const float mult = (float)(J.y + 1) - s1r;
+					float uz = u1z + u2dz * mult;
+					float onez = onez1 + onedz2 * mult;
+					const int tex_hi = J.rtexn - 1;
+					const uint16_t* send = P.level[J.m].slabs + 2 + (size_t)J.e0 + J.slen;
+					const int n = J.s2 - J.y;
+					for (int c0 = 0; c0 < n; c0 += G)
+					{
+						const int steps = (n - c0 < G) ? (n - c0) : G;
+						float muz = uz, monez = onez;
+						for (int t = 0; t < steps; t++)
+						{
+							if (gl == t) { muz = uz; monez = onez; }
+							uz += u2dz; onez += onedz2;
+						}
+						const int yy = J.y + c0 + gl;
+						bool wr = false;
+						if (gl < steps && !((ymask[yy >> 5] >> (yy & 31)) & 1u))
+						{
+							wr = true;
+							int ui = f2i(muz / monez);
+							ui = (ui > J.rtex) ? ui : J.rtex;
+							ui = (ui < tex_hi) ? ui : tex_hi;
+							const unsigned real_z = (unsigned)f2i(1.0f / monez) & 0xfffeu;
+							const unsigned color16 = __ldg(send + ui);
+							row[yy] = color16 + (real_z << 16);
+							if (IDS)
+							{
+								c_pix++;
+								uint32_t* id = P.ids + ((size_t)x * res_y + yy) * 2;
+								id[0] = (uint32_t)J.colid;
+								id[1] = ((uint32_t)J.m << 16) | (uint32_t)ui;
+							}
+						}
+						const unsigned wb = __ballot_sync(FULL, wr);
+						if (wb && gl == 0)
+						{
+							const int y0 = J.y + c0, wi = y0 >> 5, sh = y0 & 31;
+							ymask[wi] |= wb << sh;
+							if (sh && (wb >> (32 - sh))) ymask[wi + 1] |= wb >> (32 - sh);
+						}
+						__syncwarp();
+					}
+				}
+				ycmin = __shfl_sync(FULL, ycmin, L);
+				ycmax = __shfl_sync(FULL, ycmax, L);
+			}
+			else
+			{
+				// ---- long column: lane <-> run, as in k_traverse<32> --------------------------------
+				const float cpz = __shfl_sync(FULL, s0.pz, L);
+				const float cpy = __shfl_sync(FULL, s0.py, L);
+				const float cczz = __shfl_sync(FULL, s0.czz, L);
+				const float ccyy = __shfl_sync(FULL, s0.cyy, L);
+				const int m = __shfl_sync(FULL, s0.cmip, L);
+				const unsigned ce0 = __shfl_sync(FULL, s0.e0, L);
+				const unsigned ce1 = __shfl_sync(FULL, s0.e1, L);
+				const int colid = IDS ? __shfl_sync(FULL, s0.cidx, L) : 0;
+				const int cslen = (int)(ce1 & 0xffffu);
+				const unsigned first = ce1 >> 16;
+				const uint16_t* runs = P.level[m].slabs + 2 + (size_t)ce0;
+				const uint16_t* send = runs + cslen;
+				int base_len = 0, base_tex = 0;
+				bool done = false;
+				for (int c = 0; c < cslen && !done; c += G)
+				{
+					const int j = c + gl;
+					unsigned r = 0;
+					if (j < cslen) r = (j == 0) ? first : (unsigned)__ldg(runs + j);
+					const int skip = (int)(r & 1023u), solid = (int)(r >> 10);
+					const unsigned v = ((unsigned)(skip + solid) << 16) | (unsigned)solid;
+					unsigned inc = v;
+					#pragma unroll
+					for (int d = 1; d < G; d <<= 1)
+					{
+						const unsigned t = __shfl_up_sync(FULL, inc, d);
+						if (gl >= d) inc += t;
+					}
+					const unsigned exc = inc - v;
+					const int top = (base_len + (int)(exc >> 16) + skip) << m;
+					const int bot = top + (solid << m);
+					const int texture = base_tex + (int)(exc & 0xffffu);
+					const int texn = texture + solid;
+					const unsigned tot = __shfl_sync(FULL, inc, G - 1);
+					base_len += (int)(tot >> 16);
+					base_tex += (int)(tot & 0xffffu);
+
+					bool v1 = false, v2 = false;
+					int ry2 = 0, ry1 = 0;
+					if (solid > 0)
+					{
+						const float ft = (float)top, fb = (float)bot;
+						float zz1 = cpz, yy1 = cpy;
+						if (mountain + ft >= 0) { zz1 += cczz; yy1 += ccyy; }
+						const float z1 = zz1 + pz_add * ft;
+						if (!(z1 <= 0))
+						{
+							v1 = true;
+							const float y1 = yy1 + py_add * ft;
+							ry2 = f2i(res_y2 + y1 / z1);
+							float zz2 = cpz, yy2 = cpy;
+							if (mountain + fb < 0) { zz2 += cczz; yy2 += ccyy; }
+							const float z2 = zz2 + pz_add * fb;
+							if (!(z2 <= 0))
+							{
+								v2 = true;
+								const float y2 = yy2 + py_add * fb;
+								ry1 = f2i(res_y2 + y2 / z2 - 1);
+							}
+						}
+					}
+					unsigned rem = (cslen - c >= 32) ? FULL : ((1u << (cslen - c)) - 1u);
+					int limit = G - 1;
+					while (true)
+					{
+						const bool inrem = (rem >> gl) & 1u;
+						const bool brk = inrem && v1 && (ry2 <= ycmin);
+						const bool drw = inrem && v1 && v2 && !brk && !(ry1 >= ycmax);
+						const unsigned bb = __ballot_sync(FULL, brk);
+						const unsigned bd = __ballot_sync(FULL, drw);
+						if (!(bb | bd)) break;
+						const int fb = bb ? (__ffs(bb) - 1) : 64;
+						const int fd = bd ? (__ffs(bd) - 1) : 64;
+						if (fb < fd) { done = true; limit = fb; break; }
+						rem &= ~((2u << fd) - 1u);
+						int s2y = __shfl_sync(FULL, ry2, fd);
+						int s1y = __shfl_sync(FULL, ry1, fd);
+						const int rtop = __shfl_sync(FULL, top, fd);
+						const int rbot = __shfl_sync(FULL, bot, fd);
+						const int rtex = __shfl_sync(FULL, texture, fd);
+						const int rtexn = __shfl_sync(FULL, texn, fd);
+						if (s2y >= ycmax) { s2y = ycmax; ycmax = s1y; }
+						if (s1y <= ycmin)
+						{
+							s1y = ycmin;
+							ycmin = s2y;
+							ycmin = first_clear(ymask, ycmin, ycmax);
+						}
+						int y = first_clear(ymask, s1y, s2y);
+						if (y >= s2y) continue;
+						const float ft = (float)rtop, fb2 = (float)rbot;
+						const float z1r = cpz + pz_add * ft, y1r = cpy + py_add * ft;
+						const float z2r = cpz + pz_add * fb2, y2r = cpy + py_add * fb2;
+						const float s2r = res_y2 + y1r / z1r;
+						const float s1r = res_y2 + y2r / z2r;
+						const float u1z = (float)rtexn / z2r;
+						float u2dz = (float)rtex / z1r - u1z;
+						const float onez1 = 1.0f / z2r;
+						float onedz2 = 1.0f / z1r - onez1;
+						u2dz /= s2r - s1r;
+						onedz2 /= s2r - s1r;
+						if (IDS && gl == 0) c_rend++;
+						const float mult = (float)(y + 1) - s1r;
+						float uz = u1z + u2dz * mult;
+						float onez = onez1 + onedz2 * mult;
+						const int tex_hi = rtexn - 1;
+						const int n = s2y - y;
+						for (int c0 = 0; c0 < n; c0 += G)
+						{
+							const int steps = (n - c0 < G) ? (n - c0) : G;
+							float muz = uz, monez = onez;
+							for (int t = 0; t < steps; t++)
+							{
+								if (gl == t) { muz = uz; monez = onez; }
+								uz += u2dz; onez += onedz2;
+							}
+							const int yy = y + c0 + gl;
+							bool wr = false;
+							if (gl < steps && !((ymask[yy >> 5] >> (yy & 31)) & 1u))
+							{
+								wr = true;
+								int ui = f2i(muz / monez);
+								ui = (ui > rtex) ? ui : rtex;
+								ui = (ui < tex_hi) ? ui : tex_hi;
+								const unsigned real_z = (unsigned)f2i(1.0f / monez) & 0xfffeu;
+								const unsigned color16 = __ldg(send + ui);
+								row[yy] = color16 + (real_z << 16);
+								if (IDS)
+								{
+									c_pix++;
+									uint32_t* id = P.ids + ((size_t)x * res_y + yy) * 2;
+									id[0] = (uint32_t)colid;
+									id[1] = ((uint32_t)m << 16) | (uint32_t)ui;
+								}
+							}
+							const unsigned wb = __ballot_sync(FULL, wr);
+							if (wb && gl == 0)
+							{
+								const int y0 = y + c0, wi = y0 >> 5, sh = y0 & 31;
+								ymask[wi] |= wb << sh;
+								if (sh && (wb >> (32 - sh))) ymask[wi + 1] |= wb >> (32 - sh);
+							}
+							__syncwarp();
+						}
+					}
+					if (IDS)
+					{
+						const unsigned reach = (limit >= 31) ? FULL : ((2u << limit) - 1u);
+						if ((j < cslen) && ((reach >> gl) & 1u) && solid > 0) { c_proc++; c_vox += solid << m; }
+						if (done && gl == 0) c_iter += c + limit + 1;
+					}
+				}
+				if (IDS && !done && gl == 0) c_iter += cslen;
+			}
+		}
+		// ---- S. shade the short spans of this batch: every lane its own column, side by side -------
+		if (shade_runs)
+		{
+			int blen = 0, btex = 0;
+			const uint16_t* send = P.level[s0.cmip].slabs + 2 + (size_t)s0.e0 + slen;
+			#pragma unroll
+			for (int r = 0; r < RLERC_RW; r++)
+			{
+				const unsigned rw = run_word(s0.rw, r);
+				const int skip = (int)(rw & 1023u), solid = (int)(rw >> 10);
+				const int top = (blen + skip) << s0.cmip;
+				const int bot = top + (solid << s0.cmip);
+				const int texture = btex, texn = btex + solid;
+				blen += skip + solid; btex += solid;
+				if ((shade_runs >> r) & 1u)
+				{
+					const unsigned jw = shade[r * 32 + gl];
+					int y = (int)(jw & 0xffffu);
+					const int n = (int)((jw >> 16) & 15u);
+					unsigned clear = jw >> 20;
+					// interpolants (Cuda_Render.h:645-680)
+					const float ft = (float)top, fb2 = (float)bot;
+					const float z1r = s0.pz + pz_add * ft, y1r = s0.py + py_add * ft;
+					const float z2r = s0.pz + pz_add * fb2, y2r = s0.py + py_add * fb2;
+					const float s2r = res_y2 + y1r / z1r;
+					const float s1r = res_y2 + y2r / z2r;
+					const float u1z = (float)texn / z2r;
+					float u2dz = (float)texture / z1r - u1z;
+					const float onez1 = 1.0f / z2r;
+					float onedz2 = 1.0f / z1r - onez1;
+					u2dz /= s2r - s1r;
+					onedz2 /= s2r - s1r;
+					const float mult = (float)(y + 1) - s1r;
+					float uz = u1z + u2dz * mult;
+					float onez = onez1 + onedz2 * mult;
+					const int tex_hi = texn - 1;
+					for (int k = 0; k < n; ++k, ++y, uz += u2dz, onez += onedz2, clear >>= 1)   // Cuda_Render.h:687-733
+					{
+						if (!(clear & 1u)) continue;
+						int ui = f2i(uz / onez);
+						ui = (ui > texture) ? ui : texture;
+						ui = (ui < tex_hi) ? ui : tex_hi;
+						const unsigned real_z = (unsigned)f2i(1.0f / onez) & 0xfffeu;
+						row[y] = (unsigned)__ldg(send + ui) + (real_z << 16);
+						if (IDS)
+						{
+							c_pix++;
+							uint32_t* id = P.ids + ((size_t)x * res_y + y) * 2;
+							id[0] = (uint32_t)s0.cidx;
+							id[1] = ((uint32_t)s0.cmip << 16) | (uint32_t)ui;
+						}
+					}
+				}
+			}
+		}
+		if (finished) break;
+		if (dda_done && s1.nvalid == 0 && s2.nvalid == 0) break;      // pipeline drained (z > z_far, Cuda_Render.h:367)
+	}
+	__syncwarp();
+
+	// sky sentinel on every pixel of the clip range that no run covered
+	for (int y = ymin0 + gl; y <= ymax0; y += G)
+		if (!((ymask[y >> 5] >> (y & 31)) & 1u)) row[y] = RLERC_SKY;
+
+	if (IDS && P.counters)
+	{
+		atomicAdd(P.counters + 0, c_total);
+		atomicAdd(P.counters + 1, c_proc);
+		atomicAdd(P.counters + 2, c_vox);
+		atomicAdd(P.counters + 3, c_rend);
+		atomicAdd(P.counters + 4, c_pix);
+		atomicAdd(P.counters + 5, c_cols);
+		atomicAdd(P.counters + 6, c_iter);
+		atomicAdd(P.counters + 7, c_cols1);
+		if (gl == 0) atomicAdd(P.counters + 8, (unsigned long long)(ymax0 - ymin0 + 1));
+		atomicAdd(P.counters + 9, c_steps);
+	}
+}
+
+template <bool IDS>
+static void launch_w(const TraverseParams& p, cudaStream_t st)
+{
+	const int wpb = RLERC_BLOCK / 32;
+	const int rays = (p.slice_n > 1) ? owned_count(p.ray_end, p.slice_block, p.slice_n, p.slice_rank) : p.ray_end - p.ray_begin;
+	if (rays <= 0) return;
+	const int blocks = (rays + wpb - 1) / wpb;
+	const size_t smem = (size_t)wpb * ((33 * 4 + 16 + RLERC_RW * 96 + p.mask_words + 3) & ~3) * sizeof(uint32_t);
+	static size_t configured = 0;
+	if (smem > configured)
+	{
+		cudaFuncSetAttribute(k_traverse_w<IDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		configured = smem;
+	}
+	k_traverse_w<IDS><<<blocks, RLERC_BLOCK, smem, st>>>(p);
+}
+
+void launch_traverse_warp(const TraverseParams& p, bool ids, cudaStream_t st)
+{
+	if (ids) launch_w<true>(p, st); else launch_w<false>(p, st);
+}
+
+} // namespace rlerc
