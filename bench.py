@@ -41,12 +41,18 @@ WORKLOADS = {
 }
 
 
-def path_pose(R, i, K, sy):
-    """Fly-through of BASELINE config 2; heights scaled to the scene's sy."""
+def path_pose(R, i, K, sy, imrodh=False):
+    """Fly-through of BASELINE config 2: orbit of radius 4000 around (10000, 10000),
+    pitch 0.35 +- 0.3, one full turn in 1000 frames.  The camera's voxel height is -pos.y
+    (Cuda_Render.h:453,534: a run at voxel y sits at y + viewpos.y below the eye), so for the real
+    Imrodh.rle4 the survey's -818 +- 300 is kept, while the synthetic terrain (surface between sy/4
+    and 3*sy/4, volume top at 0) is flown over at 0.15*sy +- 0.08*sy, above its highest peaks."""
     t = (i * 1000) // max(K, 1)
     pos, rot = R.flythrough_pose(t, 1000)
-    s = sy / 1024.0
-    return (pos[0], pos[1] * s, pos[2]), rot
+    if imrodh:
+        return pos, rot
+    a = 2.0 * math.pi * t / 1000.0
+    return (pos[0], -(0.15 + 0.08 * math.sin(2 * a)) * sy, pos[2]), rot
 
 
 def build_scene(R, workload, log):
@@ -158,7 +164,7 @@ def main():
         from oracle import refbind as rb
         scene, scene_name, sy = build_scene(R, args.workload, log)
         threads = os.cpu_count() or 1
-        poses = [path_pose(R, i, K, sy) for i in range(K)]
+        poses = [path_pose(R, i, K, sy, scene_name == "Imrodh.rle4") for i in range(K)]
         cpu_frames(R, rb, scene, cfg, poses[:min(W, 3)], threads)
         t0 = time.perf_counter()
         times, kindname = cpu_frames(R, rb, scene, cfg, poses, threads)
@@ -196,7 +202,7 @@ def main():
     log("replica uploaded in %.1f s" % (time.time() - t0))
     r.set_lanes_per_ray(args.lanes)
     frame = MG.SlicedFrame(r, cfg, torch, rank=rank, world=world, dist=dist if world > 1 else None, block=args.slice_block)
-    poses = [path_pose(R, i, K, sy) for i in range(K)]
+    poses = [path_pose(R, i, K, sy, scene_name == "Imrodh.rle4") for i in range(K)]
     raymaps = [R.RayMap(cfg).get_ray_map(p, q) for p, q in poses]
     flush = None if args.no_flush else torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
 

@@ -55,10 +55,191 @@ struct Stage {
 	bool have;               // this lane's column may be visited
 };
 
-// run word r (0..7) of a stage
+// run word r (0..7) of a stage; r is a run-time value, the words live in registers
 __device__ __forceinline__ unsigned run_word(const unsigned (&rw)[4], int r)
 {
-	return (rw[r >> 1] >> ((r & 1) * 16)) & 0xffffu;
+	const unsigned w = (r < 4) ? ((r < 2) ? rw[0] : rw[1]) : ((r < 6) ? rw[2] : rw[3]);
+	return (w >> ((r & 1) * 16)) & 0xffffu;
+}
+
+// Everything the span shader needs that is per ray plane (kept in one place so that the rarely
+// taken paths can live in non-inlined functions and stay out of the instruction cache)
+struct RayCtx {
+	uint32_t* row;
+	uint32_t* ymask;
+	uint32_t* ids;           // IDS build: id words of this ray plane's row, else null
+	float res_y2, pz_add, py_add, mountain;
+	int gl;
+};
+
+// A pixel span [y, s2) of one run, shaded by the whole warp 32 pixels at a time, stores coalesced
+// (Cuda_Render.h:645-733).  All arguments are warp-uniform.  Returns the number of pixels written.
+template <bool IDS>
+__device__ __noinline__ int coop_span(const RayCtx& R, const uint16_t* send, float cpz, float cpy,
+                                      int y, int s2, int rtop, int rbot, int rtex, int rtexn, int m, int colid)
+{
+	const unsigned FULL = 0xffffffffu;
+	const int gl = R.gl;
+	const float ft = (float)rtop, fb2 = (float)rbot;
+	const float z1r = cpz + R.pz_add * ft, y1r = cpy + R.py_add * ft;
+	const float z2r = cpz + R.pz_add * fb2, y2r = cpy + R.py_add * fb2;
+	const float s2r = R.res_y2 + y1r / z1r;
+	const float s1r = R.res_y2 + y2r / z2r;
+	const float u1z = (float)rtexn / z2r;
+	float u2dz = (float)rtex / z1r - u1z;
+	const float onez1 = 1.0f / z2r;
+	float onedz2 = 1.0f / z1r - onez1;
+	u2dz /= s2r - s1r;
+	onedz2 /= s2r - s1r;
+	const float mult = (float)(y + 1) - s1r;
+	float uz = u1z + u2dz * mult;
+	float onez = onez1 + onedz2 * mult;
+	const int tex_hi = rtexn - 1;                      // int(float(tex-1.0))
+	const int n = s2 - y;
+	int written = 0;
+	for (int c0 = 0; c0 < n; c0 += 32)
+	{
+		const int steps = (n - c0 < 32) ? (n - c0) : 32;
+		float muz = uz, monez = onez;
+		for (int t = 0; t < steps; t++)
+		{
+			if (gl == t) { muz = uz; monez = onez; }
+			uz += u2dz; onez += onedz2;
+		}
+		const int yy = y + c0 + gl;
+		bool wr = false;
+		if (gl < steps && !((R.ymask[yy >> 5] >> (yy & 31)) & 1u))
+		{
+			wr = true;
+			int ui = f2i(muz / monez);
+			ui = (ui > rtex) ? ui : rtex;
+			ui = (ui < tex_hi) ? ui : tex_hi;
+			const unsigned real_z = (unsigned)f2i(1.0f / monez) & 0xfffeu;
+			R.row[yy] = (unsigned)__ldg(send + ui) + (real_z << 16);
+			if (IDS) { R.ids[yy * 2] = (uint32_t)colid; R.ids[yy * 2 + 1] = ((uint32_t)m << 16) | (uint32_t)ui; }
+		}
+		const unsigned wb = __ballot_sync(FULL, wr);
+		if (wb && gl == 0)
+		{
+			const int y0 = y + c0, wi = y0 >> 5, sh = y0 & 31;
+			R.ymask[wi] |= wb << sh;
+			if (sh && (wb >> (32 - sh))) R.ymask[wi + 1] |= wb >> (32 - sh);
+		}
+		written += __popc(wb);
+		__syncwarp();
+	}
+	return written;
+}
+
+// A column with more than RW undecided runs: lane <-> run, 32 runs at a time (the scheme of
+// k_traverse<32>): coalesced run loads, shuffle prefix sum for the y extents and attribute
+// offsets, all runs projected in parallel, ballots find the runs that change state in order.
+// Arguments warp-uniform; ycmin/ycmax are updated.  stats (IDS): [0] iterations [1] processed
+// [2] voxels [3] rendered [4] pixels, per lane partial sums.
+template <bool IDS>
+__device__ __noinline__ void long_column(const RayCtx& R, const uint16_t* slabs, unsigned e0, unsigned e1,
+                                         float cpz, float cpy, float cczz, float ccyy, int m, int colid,
+                                         int& ycmin_io, int& ycmax_io, unsigned long long* stats)
+{
+	const unsigned FULL = 0xffffffffu;
+	const int gl = R.gl;
+	int ycmin = ycmin_io, ycmax = ycmax_io;
+	const int cslen = (int)(e1 & 0xffffu);
+	const unsigned first = e1 >> 16;
+	const uint16_t* runs = slabs + 2 + (size_t)e0;         // Cuda_Render.h:498-499
+	const uint16_t* send = runs + cslen;
+	int base_len = 0, base_tex = 0;
+	bool done = false;
+	for (int c = 0; c < cslen && !done; c += 32)
+	{
+		const int j = c + gl;
+		unsigned r = 0;
+		if (j < cslen) r = (j == 0) ? first : (unsigned)__ldg(runs + j);
+		const int skip = (int)(r & 1023u), solid = (int)(r >> 10);
+		// inclusive prefix sum of {skip+solid, solid}, packed 16:16
+		const unsigned v = ((unsigned)(skip + solid) << 16) | (unsigned)solid;
+		unsigned inc = v;
+		#pragma unroll
+		for (int d = 1; d < 32; d <<= 1)
+		{
+			const unsigned t = __shfl_up_sync(FULL, inc, d);
+			if (gl >= d) inc += t;
+		}
+		const unsigned exc = inc - v;
+		const int top = (base_len + (int)(exc >> 16) + skip) << m;      // sti_general_sti_skip
+		const int bot = top + (solid << m);                              // sti_general
+		const int texture = base_tex + (int)(exc & 0xffffu);
+		const int texn = texture + solid;                                // tex
+		const unsigned tot = __shfl_sync(FULL, inc, 31);
+		base_len += (int)(tot >> 16);
+		base_tex += (int)(tot & 0xffffu);
+
+		bool v1 = false, v2 = false;                                     // Cuda_Render.h:529-560
+		int ry2 = 0, ry1 = 0;
+		if (solid > 0)
+		{
+			const float ft = (float)top, fb = (float)bot;
+			float zz1 = cpz, yy1 = cpy;
+			if (R.mountain + ft >= 0) { zz1 += cczz; yy1 += ccyy; }
+			const float z1 = zz1 + R.pz_add * ft;
+			if (!(z1 <= 0))
+			{
+				v1 = true;
+				const float y1 = yy1 + R.py_add * ft;
+				ry2 = f2i(R.res_y2 + y1 / z1);
+				float zz2 = cpz, yy2 = cpy;
+				if (R.mountain + fb < 0) { zz2 += cczz; yy2 += ccyy; }
+				const float z2 = zz2 + R.pz_add * fb;
+				if (!(z2 <= 0))
+				{
+					v2 = true;
+					const float y2 = yy2 + R.py_add * fb;
+					ry1 = f2i(R.res_y2 + y2 / z2 - 1);
+				}
+			}
+		}
+		// resolve the runs in order: only "break" and "draw" events change state
+		unsigned rem = (cslen - c >= 32) ? FULL : ((1u << (cslen - c)) - 1u);
+		int limit = 31;
+		while (true)
+		{
+			const bool inrem = (rem >> gl) & 1u;
+			const bool brk = inrem && v1 && (ry2 <= ycmin);
+			const bool drw = inrem && v1 && v2 && !brk && !(ry1 >= ycmax);
+			const unsigned bb = __ballot_sync(FULL, brk);
+			const unsigned bd = __ballot_sync(FULL, drw);
+			if (!(bb | bd)) break;
+			const int fb = bb ? (__ffs(bb) - 1) : 64;
+			const int fd = bd ? (__ffs(bd) - 1) : 64;
+			if (fb < fd) { done = true; limit = fb; break; }               // Cuda_Render.h:543
+			rem &= ~((2u << fd) - 1u);
+			int s2y = __shfl_sync(FULL, ry2, fd);
+			int s1y = __shfl_sync(FULL, ry1, fd);
+			const int rtop = __shfl_sync(FULL, top, fd);
+			const int rbot = __shfl_sync(FULL, bot, fd);
+			const int rtex = __shfl_sync(FULL, texture, fd);
+			const int rtexn = __shfl_sync(FULL, texn, fd);
+			if (s2y >= ycmax) { s2y = ycmax; ycmax = s1y; }                 // Cuda_Render.h:564-580
+			if (s1y <= ycmin)
+			{
+				s1y = ycmin;
+				ycmin = s2y;
+				ycmin = first_clear(R.ymask, ycmin, ycmax);
+			}
+			const int y = first_clear(R.ymask, s1y, s2y);                  // Cuda_Render.h:639-640
+			if (y >= s2y) continue;
+			const int w = coop_span<IDS>(R, send, cpz, cpy, y, s2y, rtop, rbot, rtex, rtexn, m, colid);
+			if (IDS && gl == 0) { stats[3]++; stats[4] += w; }
+		}
+		if (IDS)
+		{
+			const unsigned reach = (limit >= 31) ? FULL : ((2u << limit) - 1u);
+			if ((j < cslen) && ((reach >> gl) & 1u) && solid > 0) { stats[1]++; stats[2] += solid << m; }
+			if (done && gl == 0) stats[0] += c + limit + 1;
+		}
+	}
+	if (IDS && !done && gl == 0) stats[0] += cslen;
+	ycmin_io = ycmin; ycmax_io = ycmax;
 }
 
 template <bool IDS>
@@ -142,6 +323,11 @@ k_traverse_w(const __grid_constant__ TraverseParams P)
 	for (int k = 0; k < 4; k++) { s0.rw[k] = 0; s1.rw[k] = 0; s2.rw[k] = 0; }
 	bool dda_done = false;
 
+	RayCtx R;
+	R.row = row; R.ymask = ymask; R.ids = IDS ? P.ids + (size_t)x * res_y * 2 : nullptr;
+	R.res_y2 = res_y2; R.pz_add = pz_add; R.py_add = py_add; R.mountain = mountain; R.gl = gl;
+	unsigned long long lstats[5] = { 0, 0, 0, 0, 0 };              // long_column's share of the counters
+
 	while (true)
 	{
 		if (ycmin >= ycmax) break;                               // Cuda_Render.h:370
@@ -158,46 +344,41 @@ k_traverse_w(const __grid_constant__ TraverseParams P)
 			nr = slen < RLERC_RW ? slen : RLERC_RW;
 			longcol = slen > RLERC_RW;
 			int blen = 0;
-			bool stop = false;
-			#pragma unroll
-			for (int r = 0; r < RLERC_RW; r++)
+			for (int r = 0; r < nr; r++)
 			{
 				const unsigned rw = run_word(s0.rw, r);
 				const int skip = (int)(rw & 1023u), solid = (int)(rw >> 10);
 				const int top = (blen + skip) << s0.cmip;                // sti_general_sti_skip
 				const int bot = top + (solid << s0.cmip);                // sti_general
 				blen += skip + solid;
-				if (r < nr && !stop && solid > 0)
+				if (solid == 0) continue;
+				const float ft = (float)top, fb = (float)bot;           // Cuda_Render.h:529-560
+				float zz1 = s0.pz, yy1 = s0.py;
+				if (mountain + ft >= 0) { zz1 += s0.czz; yy1 += s0.cyy; }
+				const float z1 = zz1 + pz_add * ft;
+				if (z1 <= 0) continue;
+				flags |= 1u << r;
+				const float y1 = yy1 + py_add * ft;
+				const int sy2 = f2i(res_y2 + y1 / z1);
+				int sy1 = 0;
+				if (sy2 > ycmin)
 				{
-					const float ft = (float)top, fb = (float)bot;       // Cuda_Render.h:529-560
-					float zz1 = s0.pz, yy1 = s0.py;
-					if (mountain + ft >= 0) { zz1 += s0.czz; yy1 += s0.cyy; }
-					const float z1 = zz1 + pz_add * ft;
-					if (!(z1 <= 0))
+					float zz2 = s0.pz, yy2 = s0.py;
+					if (mountain + fb < 0) { zz2 += s0.czz; yy2 += s0.cyy; }
+					const float z2 = zz2 + pz_add * fb;
+					if (!(z2 <= 0))
 					{
-						flags |= 1u << r;
-						const float y1 = yy1 + py_add * ft;
-						const int sy2 = f2i(res_y2 + y1 / z1);
-						int sy1 = 0;
-						if (sy2 <= ycmin)
-						{
-							// breaks now, hence under every later (higher) horizon: later runs are dead
-							stop = true; nr = r + 1; longcol = false;
-						}
-						else
-						{
-							float zz2 = s0.pz, yy2 = s0.py;
-							if (mountain + fb < 0) { zz2 += s0.czz; yy2 += s0.cyy; }
-							const float z2 = zz2 + pz_add * fb;
-							if (!(z2 <= 0))
-							{
-								flags |= 1u << (8 + r);
-								const float y2 = yy2 + py_add * fb;
-								sy1 = f2i(res_y2 + y2 / z2 - 1);
-							}
-						}
-						proj[r * 32 + gl] = make_int2(sy1, sy2);
+						flags |= 1u << (8 + r);
+						const float y2 = yy2 + py_add * fb;
+						sy1 = f2i(res_y2 + y2 / z2 - 1);
 					}
+				}
+				proj[r * 32 + gl] = make_int2(sy1, sy2);
+				if (sy2 <= ycmin)
+				{
+					// breaks now, hence under every later (higher) horizon: later runs are dead
+					nr = r + 1; longcol = false;
+					break;
 				}
 			}
 		}
@@ -331,23 +512,17 @@ k_traverse_w(const __grid_constant__ TraverseParams P)
 			if (pass)
 			{
 				bool brk = false;
-				#pragma unroll
-				for (int r = 0; r < RLERC_RW; r++)
+				for (int r = 0; r < nr; r++)
 				{
-					if (r < nr && !ev && !brk)
+					if (IDS)
 					{
-						if (IDS)
-						{
-							const unsigned rw = run_word(s0.rw, r);
-							if (rw >> 10) { my_proc++; my_vox += (int)(rw >> 10) << s0.cmip; }
-						}
-						if ((flags >> r) & 1u)
-						{
-							const int2 sy = proj[r * 32 + gl];
-							if (sy.y <= ycmin) { brk = true; if (IDS) my_iter = r + 1; }
-							else if (((flags >> (8 + r)) & 1u) && !(sy.x >= ycmax)) ev = true;
-						}
+						const unsigned rw = run_word(s0.rw, r);
+						if (rw >> 10) { my_proc++; my_vox += (int)(rw >> 10) << s0.cmip; }
 					}
+					if (!((flags >> r) & 1u)) continue;
+					const int2 sy = proj[r * 32 + gl];
+					if (sy.y <= ycmin) { brk = true; if (IDS) my_iter = r + 1; break; }
+					if (((flags >> (8 + r)) & 1u) && !(sy.x >= ycmax)) { ev = true; break; }
 				}
 				if (!ev && !brk && longcol) ev = true;
 			}
@@ -366,20 +541,16 @@ k_traverse_w(const __grid_constant__ TraverseParams P)
 			if (!eb) break;
 			todo &= ~((2u << L) - 1u);
 
-			const bool Llong = __shfl_sync(FULL, (int)longcol, L) != 0;
-			if (!Llong)
+			if (__shfl_sync(FULL, (int)longcol, L) == 0)
 			{
 				// ---- owner lane advances the state through its column, serial statement order ----
-				int rstart = 0;
+				int rnext = 0, blen = 0, btex = 0;
 				while (true)
 				{
 					int act = 0;      // 0 = column finished, 1 = long pixel span handed to the warp
 					if (gl == L)
 					{
-						int blen = 0, btex = 0;
-						bool fin = false;
-						#pragma unroll
-						for (int r = 0; r < RLERC_RW; r++)
+						for (int r = rnext; r < nr; r++)
 						{
 							const unsigned rw = run_word(s0.rw, r);
 							const int skip = (int)(rw & 1023u), solid = (int)(rw >> 10);
@@ -387,285 +558,74 @@ k_traverse_w(const __grid_constant__ TraverseParams P)
 							const int bot = top + (solid << s0.cmip);
 							const int texture = btex, texn = btex + solid;
 							blen += skip + solid; btex += solid;
-							if (r >= rstart && r < nr && !fin && act == 0)
+							if (IDS) { c_iter++; if (solid > 0) { c_proc++; c_vox += solid << s0.cmip; } }
+							if (!((flags >> r) & 1u)) continue;
+							const int2 sy = proj[r * 32 + gl];
+							if (sy.y <= ycmin) break;                                          // Cuda_Render.h:543
+							if (!((flags >> (8 + r)) & 1u) || sy.x >= ycmax) continue;
+							int s2y = sy.y, s1y = sy.x;
+							if (s2y >= ycmax) { s2y = ycmax; ycmax = s1y; }                      // Cuda_Render.h:564-580
+							if (s1y <= ycmin)
 							{
-								if (IDS) { c_iter++; if (solid > 0) { c_proc++; c_vox += solid << s0.cmip; } }
-								if ((flags >> r) & 1u)
-								{
-									const int2 sy = proj[r * 32 + gl];
-									if (sy.y <= ycmin) fin = true;                                     // Cuda_Render.h:543
-									else if (((flags >> (8 + r)) & 1u) && !(sy.x >= ycmax))
-									{
-										int s2y = sy.y, s1y = sy.x;
-										if (s2y >= ycmax) { s2y = ycmax; ycmax = s1y; }                  // Cuda_Render.h:564-580
-										if (s1y <= ycmin)
-										{
-											s1y = ycmin;
-											ycmin = s2y;
-											ycmin = first_clear(ymask, ycmin, ycmax);
-										}
-										int y = first_clear(ymask, s1y, s2y);                        // Cuda_Render.h:639-640
-										if (y < s2y)
-										{
-											if (IDS) c_rend++;
-											const int n = s2y - y;
-											if (n >= RLERC_COOP_MIN)
-											{
-												job->cpz = s0.pz; job->cpy = s0.py;
-												job->y = y; job->s2 = s2y; job->rtop = top; job->rbot = bot;
-												job->rtex = texture; job->rtexn = texn;
-												job->m = s0.cmip; job->colid = s0.cidx; job->e0 = s0.e0; job->slen = (unsigned)slen;
-												act = 1; rstart = r + 1;
-											}
-											else
-											{
-												// short span: fix WHICH pixels it owns now (that is all the occlusion
-												// state needs) and leave the shading to the end of the batch, where
-												// all lanes shade their spans side by side
-												const int w = y >> 5, sh = y & 31;
-												unsigned bits = ymask[w] >> sh;
-												if (sh) bits |= ymask[w + 1] << (32 - sh);
-												const unsigned clear = ~bits & ((1u << n) - 1u);
-												ymask[w] |= clear << sh;
-												if (sh && (clear >> (32 - sh))) ymask[w + 1] |= clear >> (32 - sh);
-												shade[r * 32 + gl] = (unsigned)y | ((unsigned)n << 16) | (clear << 20);
-												shade_runs |= 1u << r;
-											}
-										}
-									}
-								}
+								s1y = ycmin;
+								ycmin = s2y;
+								ycmin = first_clear(ymask, ycmin, ycmax);
 							}
+							const int y = first_clear(ymask, s1y, s2y);                        // Cuda_Render.h:639-640
+							if (y >= s2y) continue;
+							if (IDS) c_rend++;
+							const int n = s2y - y;
+							if (n >= RLERC_COOP_MIN)
+							{
+								job->cpz = s0.pz; job->cpy = s0.py;
+								job->y = y; job->s2 = s2y; job->rtop = top; job->rbot = bot;
+								job->rtex = texture; job->rtexn = texn;
+								job->m = s0.cmip; job->colid = s0.cidx; job->e0 = s0.e0; job->slen = (unsigned)slen;
+								act = 1; rnext = r + 1;
+								break;
+							}
+							// short span: fix WHICH pixels it owns now (that is all the occlusion state
+							// needs) and leave the shading to the end of the batch, where all lanes
+							// shade their spans side by side
+							const int w = y >> 5, sh = y & 31;
+							unsigned bits = ymask[w] >> sh;
+							if (sh) bits |= ymask[w + 1] << (32 - sh);
+							const unsigned clear = ~bits & ((1u << n) - 1u);
+							ymask[w] |= clear << sh;
+							if (sh && (clear >> (32 - sh))) ymask[w + 1] |= clear >> (32 - sh);
+							shade[r * 32 + gl] = (unsigned)y | ((unsigned)n << 16) | (clear << 20);
+							shade_runs |= 1u << r;
 						}
 					}
 					act = __shfl_sync(FULL, act, L);
 					__syncwarp();
 					if (act == 0) break;
-
-					// ---- long pixel span: whole warp, 32 pixels at a time --------------------------
+					// long pixel span: whole warp, 32 pixels at a time
 					const DrawJob J = *job;
-					const float ft = (float)J.rtop, fb2 = (float)J.rbot;
-					const float z1r = J.cpz + pz_add * ft, y1r = J.cpy + py_add * ft;
-					const float z2r = J.cpz + pz_add * fb2, y2r = J.cpy + py_add * fb2;
-					const float s2r = res_y2 + y1r / z1r;
-					const float s1r = res_y2 + y2r / z2r;
-					const float u1z = (float)J.rtexn / z2r;
-					float u2dz = (float)J.rtex / z1r - u1z;
-					const float onez1 = 1.0f / z2r;
-					float onedz2 = 1.0f / z1r - onez1;
-					u2dz /= s2r - s1r;
-					onedz2 /= s2r - s1r;
-					const float mult = (float)(J.y + 1) - s1r;
-					float uz = u1z + u2dz * mult;
-					float onez = onez1 + onedz2 * mult;
-					const int tex_hi = J.rtexn - 1;
-					const uint16_t* send = P.level[J.m].slabs + 2 + (size_t)J.e0 + J.slen;
-					const int n = J.s2 - J.y;
-					for (int c0 = 0; c0 < n; c0 += G)
-					{
-						const int steps = (n - c0 < G) ? (n - c0) : G;
-						float muz = uz, monez = onez;
-						for (int t = 0; t < steps; t++)
-						{
-							if (gl == t) { muz = uz; monez = onez; }
-							uz += u2dz; onez += onedz2;
-						}
-						const int yy = J.y + c0 + gl;
-						bool wr = false;
-						if (gl < steps && !((ymask[yy >> 5] >> (yy & 31)) & 1u))
-						{
-							wr = true;
-							int ui = f2i(muz / monez);
-							ui = (ui > J.rtex) ? ui : J.rtex;
-							ui = (ui < tex_hi) ? ui : tex_hi;
-							const unsigned real_z = (unsigned)f2i(1.0f / monez) & 0xfffeu;
-							const unsigned color16 = __ldg(send + ui);
-							row[yy] = color16 + (real_z << 16);
-							if (IDS)
-							{
-								c_pix++;
-								uint32_t* id = P.ids + ((size_t)x * res_y + yy) * 2;
-								id[0] = (uint32_t)J.colid;
-								id[1] = ((uint32_t)J.m << 16) | (uint32_t)ui;
-							}
-						}
-						const unsigned wb = __ballot_sync(FULL, wr);
-						if (wb && gl == 0)
-						{
-							const int y0 = J.y + c0, wi = y0 >> 5, sh = y0 & 31;
-							ymask[wi] |= wb << sh;
-							if (sh && (wb >> (32 - sh))) ymask[wi + 1] |= wb >> (32 - sh);
-						}
-						__syncwarp();
-					}
+					const int w = coop_span<IDS>(R, P.level[J.m].slabs + 2 + (size_t)J.e0 + J.slen, J.cpz, J.cpy,
+					                             J.y, J.s2, J.rtop, J.rbot, J.rtex, J.rtexn, J.m, J.colid);
+					if (IDS && gl == 0) c_pix += w;
 				}
 				ycmin = __shfl_sync(FULL, ycmin, L);
 				ycmax = __shfl_sync(FULL, ycmax, L);
 			}
 			else
 			{
-				// ---- long column: lane <-> run, as in k_traverse<32> --------------------------------
-				const float cpz = __shfl_sync(FULL, s0.pz, L);
-				const float cpy = __shfl_sync(FULL, s0.py, L);
-				const float cczz = __shfl_sync(FULL, s0.czz, L);
-				const float ccyy = __shfl_sync(FULL, s0.cyy, L);
+				// ---- long column: lane <-> run -----------------------------------------------------
 				const int m = __shfl_sync(FULL, s0.cmip, L);
-				const unsigned ce0 = __shfl_sync(FULL, s0.e0, L);
-				const unsigned ce1 = __shfl_sync(FULL, s0.e1, L);
-				const int colid = IDS ? __shfl_sync(FULL, s0.cidx, L) : 0;
-				const int cslen = (int)(ce1 & 0xffffu);
-				const unsigned first = ce1 >> 16;
-				const uint16_t* runs = P.level[m].slabs + 2 + (size_t)ce0;
-				const uint16_t* send = runs + cslen;
-				int base_len = 0, base_tex = 0;
-				bool done = false;
-				for (int c = 0; c < cslen && !done; c += G)
-				{
-					const int j = c + gl;
-					unsigned r = 0;
-					if (j < cslen) r = (j == 0) ? first : (unsigned)__ldg(runs + j);
-					const int skip = (int)(r & 1023u), solid = (int)(r >> 10);
-					const unsigned v = ((unsigned)(skip + solid) << 16) | (unsigned)solid;
-					unsigned inc = v;
-					#pragma unroll
-					for (int d = 1; d < G; d <<= 1)
-					{
-						const unsigned t = __shfl_up_sync(FULL, inc, d);
-						if (gl >= d) inc += t;
-					}
-					const unsigned exc = inc - v;
-					const int top = (base_len + (int)(exc >> 16) + skip) << m;
-					const int bot = top + (solid << m);
-					const int texture = base_tex + (int)(exc & 0xffffu);
-					const int texn = texture + solid;
-					const unsigned tot = __shfl_sync(FULL, inc, G - 1);
-					base_len += (int)(tot >> 16);
-					base_tex += (int)(tot & 0xffffu);
-
-					bool v1 = false, v2 = false;
-					int ry2 = 0, ry1 = 0;
-					if (solid > 0)
-					{
-						const float ft = (float)top, fb = (float)bot;
-						float zz1 = cpz, yy1 = cpy;
-						if (mountain + ft >= 0) { zz1 += cczz; yy1 += ccyy; }
-						const float z1 = zz1 + pz_add * ft;
-						if (!(z1 <= 0))
-						{
-							v1 = true;
-							const float y1 = yy1 + py_add * ft;
-							ry2 = f2i(res_y2 + y1 / z1);
-							float zz2 = cpz, yy2 = cpy;
-							if (mountain + fb < 0) { zz2 += cczz; yy2 += ccyy; }
-							const float z2 = zz2 + pz_add * fb;
-							if (!(z2 <= 0))
-							{
-								v2 = true;
-								const float y2 = yy2 + py_add * fb;
-								ry1 = f2i(res_y2 + y2 / z2 - 1);
-							}
-						}
-					}
-					unsigned rem = (cslen - c >= 32) ? FULL : ((1u << (cslen - c)) - 1u);
-					int limit = G - 1;
-					while (true)
-					{
-						const bool inrem = (rem >> gl) & 1u;
-						const bool brk = inrem && v1 && (ry2 <= ycmin);
-						const bool drw = inrem && v1 && v2 && !brk && !(ry1 >= ycmax);
-						const unsigned bb = __ballot_sync(FULL, brk);
-						const unsigned bd = __ballot_sync(FULL, drw);
-						if (!(bb | bd)) break;
-						const int fb = bb ? (__ffs(bb) - 1) : 64;
-						const int fd = bd ? (__ffs(bd) - 1) : 64;
-						if (fb < fd) { done = true; limit = fb; break; }
-						rem &= ~((2u << fd) - 1u);
-						int s2y = __shfl_sync(FULL, ry2, fd);
-						int s1y = __shfl_sync(FULL, ry1, fd);
-						const int rtop = __shfl_sync(FULL, top, fd);
-						const int rbot = __shfl_sync(FULL, bot, fd);
-						const int rtex = __shfl_sync(FULL, texture, fd);
-						const int rtexn = __shfl_sync(FULL, texn, fd);
-						if (s2y >= ycmax) { s2y = ycmax; ycmax = s1y; }
-						if (s1y <= ycmin)
-						{
-							s1y = ycmin;
-							ycmin = s2y;
-							ycmin = first_clear(ymask, ycmin, ycmax);
-						}
-						int y = first_clear(ymask, s1y, s2y);
-						if (y >= s2y) continue;
-						const float ft = (float)rtop, fb2 = (float)rbot;
-						const float z1r = cpz + pz_add * ft, y1r = cpy + py_add * ft;
-						const float z2r = cpz + pz_add * fb2, y2r = cpy + py_add * fb2;
-						const float s2r = res_y2 + y1r / z1r;
-						const float s1r = res_y2 + y2r / z2r;
-						const float u1z = (float)rtexn / z2r;
-						float u2dz = (float)rtex / z1r - u1z;
-						const float onez1 = 1.0f / z2r;
-						float onedz2 = 1.0f / z1r - onez1;
-						u2dz /= s2r - s1r;
-						onedz2 /= s2r - s1r;
-						if (IDS && gl == 0) c_rend++;
-						const float mult = (float)(y + 1) - s1r;
-						float uz = u1z + u2dz * mult;
-						float onez = onez1 + onedz2 * mult;
-						const int tex_hi = rtexn - 1;
-						const int n = s2y - y;
-						for (int c0 = 0; c0 < n; c0 += G)
-						{
-							const int steps = (n - c0 < G) ? (n - c0) : G;
-							float muz = uz, monez = onez;
-							for (int t = 0; t < steps; t++)
-							{
-								if (gl == t) { muz = uz; monez = onez; }
-								uz += u2dz; onez += onedz2;
-							}
-							const int yy = y + c0 + gl;
-							bool wr = false;
-							if (gl < steps && !((ymask[yy >> 5] >> (yy & 31)) & 1u))
-							{
-								wr = true;
-								int ui = f2i(muz / monez);
-								ui = (ui > rtex) ? ui : rtex;
-								ui = (ui < tex_hi) ? ui : tex_hi;
-								const unsigned real_z = (unsigned)f2i(1.0f / monez) & 0xfffeu;
-								const unsigned color16 = __ldg(send + ui);
-								row[yy] = color16 + (real_z << 16);
-								if (IDS)
-								{
-									c_pix++;
-									uint32_t* id = P.ids + ((size_t)x * res_y + yy) * 2;
-									id[0] = (uint32_t)colid;
-									id[1] = ((uint32_t)m << 16) | (uint32_t)ui;
-								}
-							}
-							const unsigned wb = __ballot_sync(FULL, wr);
-							if (wb && gl == 0)
-							{
-								const int y0 = y + c0, wi = y0 >> 5, sh = y0 & 31;
-								ymask[wi] |= wb << sh;
-								if (sh && (wb >> (32 - sh))) ymask[wi + 1] |= wb >> (32 - sh);
-							}
-							__syncwarp();
-						}
-					}
-					if (IDS)
-					{
-						const unsigned reach = (limit >= 31) ? FULL : ((2u << limit) - 1u);
-						if ((j < cslen) && ((reach >> gl) & 1u) && solid > 0) { c_proc++; c_vox += solid << m; }
-						if (done && gl == 0) c_iter += c + limit + 1;
-					}
-				}
-				if (IDS && !done && gl == 0) c_iter += cslen;
+				long_column<IDS>(R, P.level[m].slabs, __shfl_sync(FULL, s0.e0, L), __shfl_sync(FULL, s0.e1, L),
+				                 __shfl_sync(FULL, s0.pz, L), __shfl_sync(FULL, s0.py, L),
+				                 __shfl_sync(FULL, s0.czz, L), __shfl_sync(FULL, s0.cyy, L),
+				                 m, __shfl_sync(FULL, s0.cidx, L), ycmin, ycmax, lstats);
 			}
 		}
+
 		// ---- S. shade the short spans of this batch: every lane its own column, side by side -------
 		if (shade_runs)
 		{
 			int blen = 0, btex = 0;
 			const uint16_t* send = P.level[s0.cmip].slabs + 2 + (size_t)s0.e0 + slen;
-			#pragma unroll
-			for (int r = 0; r < RLERC_RW; r++)
+			for (int r = 0; r < nr; r++)
 			{
 				const unsigned rw = run_word(s0.rw, r);
 				const int skip = (int)(rw & 1023u), solid = (int)(rw >> 10);
@@ -673,49 +633,50 @@ k_traverse_w(const __grid_constant__ TraverseParams P)
 				const int bot = top + (solid << s0.cmip);
 				const int texture = btex, texn = btex + solid;
 				blen += skip + solid; btex += solid;
-				if ((shade_runs >> r) & 1u)
+				if (!((shade_runs >> r) & 1u)) continue;
+				const unsigned jw = shade[r * 32 + gl];
+				int y = (int)(jw & 0xffffu);
+				const int n = (int)((jw >> 16) & 15u);
+				unsigned clear = jw >> 20;
+				// interpolants (Cuda_Render.h:645-680)
+				const float ft = (float)top, fb2 = (float)bot;
+				const float z1r = s0.pz + pz_add * ft, y1r = s0.py + py_add * ft;
+				const float z2r = s0.pz + pz_add * fb2, y2r = s0.py + py_add * fb2;
+				const float s2r = res_y2 + y1r / z1r;
+				const float s1r = res_y2 + y2r / z2r;
+				const float u1z = (float)texn / z2r;
+				float u2dz = (float)texture / z1r - u1z;
+				const float onez1 = 1.0f / z2r;
+				float onedz2 = 1.0f / z1r - onez1;
+				u2dz /= s2r - s1r;
+				onedz2 /= s2r - s1r;
+				const float mult = (float)(y + 1) - s1r;
+				float uz = u1z + u2dz * mult;
+				float onez = onez1 + onedz2 * mult;
+				const int tex_hi = texn - 1;
+				for (int k = 0; k < n; ++k, ++y, uz += u2dz, onez += onedz2, clear >>= 1)   // Cuda_Render.h:687-733
 				{
-					const unsigned jw = shade[r * 32 + gl];
-					int y = (int)(jw & 0xffffu);
-					const int n = (int)((jw >> 16) & 15u);
-					unsigned clear = jw >> 20;
-					// interpolants (Cuda_Render.h:645-680)
-					const float ft = (float)top, fb2 = (float)bot;
-					const float z1r = s0.pz + pz_add * ft, y1r = s0.py + py_add * ft;
-					const float z2r = s0.pz + pz_add * fb2, y2r = s0.py + py_add * fb2;
-					const float s2r = res_y2 + y1r / z1r;
-					const float s1r = res_y2 + y2r / z2r;
-					const float u1z = (float)texn / z2r;
-					float u2dz = (float)texture / z1r - u1z;
-					const float onez1 = 1.0f / z2r;
-					float onedz2 = 1.0f / z1r - onez1;
-					u2dz /= s2r - s1r;
-					onedz2 /= s2r - s1r;
-					const float mult = (float)(y + 1) - s1r;
-					float uz = u1z + u2dz * mult;
-					float onez = onez1 + onedz2 * mult;
-					const int tex_hi = texn - 1;
-					for (int k = 0; k < n; ++k, ++y, uz += u2dz, onez += onedz2, clear >>= 1)   // Cuda_Render.h:687-733
+					if (!(clear & 1u)) continue;
+					int ui = f2i(uz / onez);
+					ui = (ui > texture) ? ui : texture;
+					ui = (ui < tex_hi) ? ui : tex_hi;
+					const unsigned real_z = (unsigned)f2i(1.0f / onez) & 0xfffeu;
+					row[y] = (unsigned)__ldg(send + ui) + (real_z << 16);
+					if (IDS)
 					{
-						if (!(clear & 1u)) continue;
-						int ui = f2i(uz / onez);
-						ui = (ui > texture) ? ui : texture;
-						ui = (ui < tex_hi) ? ui : tex_hi;
-						const unsigned real_z = (unsigned)f2i(1.0f / onez) & 0xfffeu;
-						row[y] = (unsigned)__ldg(send + ui) + (real_z << 16);
-						if (IDS)
-						{
-							c_pix++;
-							uint32_t* id = P.ids + ((size_t)x * res_y + y) * 2;
-							id[0] = (uint32_t)s0.cidx;
-							id[1] = ((uint32_t)s0.cmip << 16) | (uint32_t)ui;
-						}
+						c_pix++;
+						R.ids[y * 2] = (uint32_t)s0.cidx;
+						R.ids[y * 2 + 1] = ((uint32_t)s0.cmip << 16) | (uint32_t)ui;
 					}
 				}
 			}
 		}
 		if (finished) break;
 		if (dda_done && s1.nvalid == 0 && s2.nvalid == 0) break;      // pipeline drained (z > z_far, Cuda_Render.h:367)
+	}
+	if (IDS)
+	{
+		c_iter += lstats[0]; c_proc += lstats[1]; c_vox += lstats[2]; c_rend += lstats[3]; c_pix += lstats[4];
 	}
 	__syncwarp();
 

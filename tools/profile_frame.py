@@ -22,7 +22,7 @@ def main():
     r.all_to_gpu(scene)
     r.set_timing(True)
     r.set_lanes_per_ray(lanes)
-    pos, rot = bench.path_pose(R, t, 1000, sy)
+    pos, rot = bench.path_pose(R, t, 1000, sy, name == "Imrodh.rle4")
     rm = R.RayMap(cfg).get_ray_map(pos, rot)
     ts = []
     for _ in range(reps):
