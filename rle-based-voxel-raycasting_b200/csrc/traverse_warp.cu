@@ -391,7 +391,7 @@ k_traverse_w(const __grid_constant__ TraverseParams P)
 			// loop runs without per-step tests.  Slot s+1 receives the state after crossing s; slot
 			// 0 carries the state before the batch.  All lanes store the same words (uniform address).
 			int nvalid = G;
-			rec[0] = make_float4(dist_now, posx, posy, __int_as_float(index));
+			rec[0] = make_float4(index ? -dist_now : dist_now, posx, posy, 0.0f);
 			for (int s = 0; s < G;)
 			{
 				while (zi > mapswitch)                               // Cuda_Render.h:343-365
@@ -408,7 +408,8 @@ k_traverse_w(const __grid_constant__ TraverseParams P)
 				int n = G - s;
 				n = n < lod_free ? n : lod_free;
 				n = n < far_free ? n : far_free;
-				const int mipbits = mip << 1;
+				// record of a crossing: {dist (negated when the z-track fired), pos.x, pos.y, mip}
+				const float mipf = __int_as_float(mip);
 				float4* out = rec + s + 1;
 				#define RLERC_DDA_STEP(K)                                                         \
 					{                                                                             \
@@ -416,9 +417,9 @@ k_traverse_w(const __grid_constant__ TraverseParams P)
 						dist_now = t1 ? d1 : d0;                                                  \
 						posx = t1 ? i1x : i0x;                                                    \
 						posy = t1 ? i1y : i0y;                                                    \
+						out[K] = make_float4(t1 ? -d1 : d0, posx, posy, mipf);                    \
 						if (t1) { d1 += gd1; i1x += g1x; i1y += g1y; }                            \
 						else    { d0 += gd0; i0x += g0x; i0y += g0y; }                            \
-						out[K] = make_float4(dist_now, posx, posy, __int_as_float(mipbits | (t1 ? 1 : 0))); \
 					}
 				int j = 0;
 				for (; j + 4 <= n; j += 4)
@@ -427,7 +428,7 @@ k_traverse_w(const __grid_constant__ TraverseParams P)
 				}
 				for (; j < n; j++) RLERC_DDA_STEP(j)
 				#undef RLERC_DDA_STEP
-				index = __float_as_int(out[n - 1].w) & 1;
+				index = __float_as_int(out[n - 1].x) < 0 ? 1 : 0;
 				zi += n * dzi;
 				s += n;
 			}
@@ -437,9 +438,9 @@ k_traverse_w(const __grid_constant__ TraverseParams P)
 			if (gl < nvalid)
 			{
 				const float4 ra = rec[gl], rb = rec[gl + 1];        // state before / after crossing gl
-				const float db = ra.x, dn = rb.x;
-				const int ib = __float_as_int(ra.w) & 1;
-				s2.cmip = __float_as_int(rb.w) >> 1;
+				const float db = fabsf(ra.x), dn = fabsf(rb.x);
+				const int ib = __float_as_int(ra.x) < 0 ? 1 : 0;        // index_before: sign bit of the record
+				s2.cmip = __float_as_int(rb.w);
 				const int fix_x = (1 - ib) * fixx, fix_z = ib * fixz;    // Cuda_Render.h:418-419
 				const float ddelta = dn - db;
 				const float vsx = ray_x * db, vsz = ray_z * db;

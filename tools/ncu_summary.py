@@ -1,0 +1,32 @@
+"""Text summary of an ncu --set full report (the metrics B200_PROFILING.md names + stall picture).
+usage: python tools/ncu_summary.py report.ncu-rep"""
+import csv, io, subprocess, sys
+raw = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], check=True, capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(raw)))
+hdr, units, vals = rows[0], rows[1], rows[2]
+want = ["Kernel Name", "launch__grid_size", "launch__block_size", "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic",
+        "launch__waves_per_multiprocessor", "launch__occupancy_limit_registers", "gpu__time_duration.sum",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__t_bytes.sum", "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
+        "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum",
+        "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_st.sum",
+        "smsp__inst_executed.sum", "sm__inst_executed.avg.per_cycle_active", "smsp__thread_inst_executed_per_inst_executed.ratio",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio"]
+for k in want:
+    for i, h in enumerate(hdr):
+        if h == k:
+            print("%-78s %s %s" % (k, vals[i], units[i]))
+ld_s = ld_r = None
+for i, h in enumerate(hdr):
+    if h == "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum": ld_s = float(vals[i].replace(",", ""))
+    if h == "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum": ld_r = float(vals[i].replace(",", ""))
+if ld_s and ld_r:
+    print("%-78s %.2f" % ("global load sectors per request (RLE-run fetch efficiency)", ld_s / ld_r))
