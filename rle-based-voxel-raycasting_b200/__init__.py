@@ -24,7 +24,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librlerc.so")
+LIB_PATH = os.environ.get("RLERC_LIB") or os.path.join(_HERE, "librlerc.so")   # RLERC_LIB: A/B builds (tools/)
 MAX_MAPS = 16
 
 

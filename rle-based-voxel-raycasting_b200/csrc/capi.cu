@@ -192,7 +192,7 @@ int rlerc_create(int device, rlerc_ctx** out)
 	CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
 	for (int i = 0; i < 4; i++) CK(cudaEventCreate(&c->ev[i]));
 	for (int i = 0; i < rlerc_ctx::kSlots; i++) CK(cudaEventCreateWithFlags(&c->slot[i].done, cudaEventDisableTiming));
-	CK(cudaMalloc((void**)&c->d_counters, 16 * sizeof(unsigned long long)));
+	CK(cudaMalloc((void**)&c->d_counters, 32 * sizeof(unsigned long long)));
 	*out = c;
 	return RLERC_OK;
 }
@@ -336,7 +336,7 @@ static int render_impl(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_c
 		if (!d_ids) { set_error("rlerc_render_ids: null ids buffer"); return RLERC_ERR_ARG; }
 		P.ids = d_ids;
 		P.counters = c->d_counters;
-		CK(cudaMemsetAsync(c->d_counters, 0, 16 * sizeof(unsigned long long), c->stream));
+		CK(cudaMemsetAsync(c->d_counters, 0, 32 * sizeof(unsigned long long), c->stream));
 	}
 	if (c->timing) CK(cudaEventRecord(c->ev[0], c->stream));
 	launch_traverse(P, pick_lanes(c, P.ray_end - P.ray_begin), ids, c->stream);
@@ -364,6 +364,17 @@ int rlerc_render_counters(rlerc_ctx* c, uint64_t out[10])
 	unsigned long long h[10];
 	CK(cudaMemcpy(h, c->d_counters, sizeof(h), cudaMemcpyDeviceToHost));
 	for (int i = 0; i < 10; i++) out[i] = h[i];
+	return RLERC_OK;
+}
+
+/* undocumented: raw copy of all 32 debug counter slots (tools/ only) */
+int rlerc_debug_counters(rlerc_ctx* c, uint64_t out[32])
+{
+	if (!c || !out) return RLERC_ERR_ARG;
+	int rc = set_dev(c);
+	if (rc) return rc;
+	CK(cudaStreamSynchronize(c->stream));
+	CK(cudaMemcpy(out, c->d_counters, 32 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
 	return RLERC_OK;
 }
 

@@ -134,12 +134,12 @@ __device__ __noinline__ int coop_span(const RayCtx& R, const uint16_t* send, flo
 // A column with more than RW undecided runs: lane <-> run, 32 runs at a time (the scheme of
 // k_traverse<32>): coalesced run loads, shuffle prefix sum for the y extents and attribute
 // offsets, all runs projected in parallel, ballots find the runs that change state in order.
-// Arguments warp-uniform; ycmin/ycmax are updated.  stats (IDS): [0] iterations [1] processed
+// Arguments warp-uniform; ycmin/ycmax/hiw (one past the highest mask row set) are updated.  stats (IDS): [0] iterations [1] processed
 // [2] voxels [3] rendered [4] pixels, per lane partial sums.
 template <bool IDS>
 __device__ __noinline__ void long_column(const RayCtx& R, const uint16_t* slabs, unsigned e0, unsigned e1,
                                          float cpz, float cpy, float cczz, float ccyy, int m, int colid,
-                                         int& ycmin_io, int& ycmax_io, unsigned long long* stats)
+                                         int& ycmin_io, int& ycmax_io, int& hiw_io, unsigned long long* stats)
 {
 	const unsigned FULL = 0xffffffffu;
 	const int gl = R.gl;
@@ -228,6 +228,7 @@ __device__ __noinline__ void long_column(const RayCtx& R, const uint16_t* slabs,
 			}
 			const int y = first_clear(R.ymask, s1y, s2y);                  // Cuda_Render.h:639-640
 			if (y >= s2y) continue;
+			hiw_io = hiw_io > s2y ? hiw_io : s2y;
 			const int w = coop_span<IDS>(R, send, cpz, cpy, y, s2y, rtop, rbot, rtex, rtexn, m, colid);
 			if (IDS && gl == 0) { stats[3]++; stats[4] += w; }
 		}
@@ -243,7 +244,7 @@ __device__ __noinline__ void long_column(const RayCtx& R, const uint16_t* slabs,
 }
 
 template <bool IDS>
-__global__ void __launch_bounds__(RLERC_BLOCK, 3)
+__global__ void __launch_bounds__(RLERC_BLOCK, 4)
 k_traverse_w(const __grid_constant__ TraverseParams P)
 {
 	extern __shared__ __align__(16) uint32_t smem[];
@@ -314,6 +315,9 @@ k_traverse_w(const __grid_constant__ TraverseParams P)
 	// per-lane statistics (IDS build only)
 	unsigned long long c_total = 0, c_proc = 0, c_vox = 0, c_rend = 0, c_pix = 0, c_cols = 0, c_iter = 0, c_cols1 = 0, c_steps = 0;
 
+	// one past the highest row of the occlusion mask that is set: above it the mask is clean
+	int hiw = 0;
+
 	Stage s0, s1, s2;
 	s0.nvalid = s1.nvalid = s2.nvalid = 0;
 	s0.have = s1.have = s2.have = false;
@@ -327,6 +331,7 @@ k_traverse_w(const __grid_constant__ TraverseParams P)
 	R.row = row; R.ymask = ymask; R.ids = IDS ? P.ids + (size_t)x * res_y * 2 : nullptr;
 	R.res_y2 = res_y2; R.pz_add = pz_add; R.py_add = py_add; R.mountain = mountain; R.gl = gl;
 	unsigned long long lstats[5] = { 0, 0, 0, 0, 0 };              // long_column's share of the counters
+	unsigned long long dbg[11] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };  // IDS build: fast-path statistics
 
 	while (true)
 	{
@@ -502,6 +507,103 @@ k_traverse_w(const __grid_constant__ TraverseParams P)
 		unsigned todo = (s0.nvalid >= 32) ? FULL : ((1u << s0.nvalid) - 1u);
 		bool finished = false;
 		unsigned shade_runs = 0;          // runs of my column with a deferred short span
+
+		// ---- B0. rising-horizon fast path -----------------------------------------------------------
+		// The common far-field batch: the mask is clean above y_clip_min and every column either does
+		// nothing or draws ONE bottom-attached short span [y_clip_min, sy2) and thereby raises
+		// y_clip_min to sy2 (classic floating horizon).  Then the serial recurrence over the 32 columns
+		// is y_{c+1} = max(y_c, sy2_c): a warp prefix maximum.  Every lane proves that its own column
+		// is of that kind under ANY horizon it can meet in this batch; one failed proof sends the
+		// whole batch through the general event loop below.
+		if (IDS && gl == 0 && todo) dbg[0]++;
+		if (todo && hiw <= ycmin)
+		{
+			if (IDS && gl == 0) dbg[1]++;
+			const int y0 = ycmin;
+			const bool mine = (todo >> gl) & 1u;
+			const bool pass0 = mine && s0.have && !(s0.pz * res_y2 + s0.py <= s0.pz * (float)y0);
+			bool ok = true;
+			int T = INT_MIN, ra = -1;
+			int why = 0;
+			if (mine && s0.have && !pass0 && !(s0.pz > 0)) { ok = false; why |= 1; }      // culled now, may pass later
+			if (pass0)
+			{
+				if (longcol) { ok = false; why |= 2; }
+				int min_before = INT_MAX;
+				for (int r = 0; r < nr; r++)
+				{
+					if (!((flags >> r) & 1u)) continue;
+					const int2 sy = proj[r * 32 + gl];
+					if (ra < 0)
+					{
+						if (!((flags >> (8 + r)) & 1u) || sy.x >= ycmax) { min_before = min_before < sy.y ? min_before : sy.y; continue; }
+						ra = r; T = sy.y;
+						if (T <= y0) { T = INT_MIN; break; }                  // breaks here under every horizon >= y0
+						if (sy.x > y0) { ok = false; why |= 4; }
+						if (T >= ycmax) { ok = false; why |= 8; }
+						if (min_before < T) { ok = false; why |= 16; }
+						if (T - y0 >= RLERC_COOP_MIN) { ok = false; why |= 32; }
+					}
+					else if (sy.y > T) { ok = false; why |= 64; }               // a later run must break after this one drew
+				}
+				if (ra < 0) T = INT_MIN;
+			}
+			// exclusive prefix maximum of T in column order = the horizon each column meets
+			int inc = T;
+			#pragma unroll
+			for (int d = 1; d < 32; d <<= 1)
+			{
+				const int t = __shfl_up_sync(FULL, inc, d);
+				if (gl >= d) inc = inc > t ? inc : t;
+			}
+			int yc = __shfl_up_sync(FULL, inc, 1);
+			if (gl == 0) yc = INT_MIN;
+			yc = yc > y0 ? yc : y0;
+			const bool draws = pass0 && T > yc;
+			// a column that draws must still pass the top-clip test under the horizon it meets
+			if (draws && (s0.pz * res_y2 + s0.py <= s0.pz * (float)yc)) { ok = false; why |= 128; }
+			if (IDS)
+			{
+				const unsigned allwhy = __reduce_or_sync(FULL, (unsigned)why);
+				if (gl == 0) for (int k = 0; k < 8; k++) if ((allwhy >> k) & 1u) dbg[3 + k]++;
+			}
+			if (__all_sync(FULL, ok))
+			{
+				if (IDS && gl == 0) dbg[2]++;
+				int yend = __shfl_sync(FULL, inc, 31);
+				yend = yend > y0 ? yend : y0;
+				if (draws)
+				{
+					shade[ra * 32 + gl] = (unsigned)yc | ((unsigned)(T - yc) << 16) | (0xfffu << 20);
+					shade_runs |= 1u << ra;
+				}
+				for (int w = (y0 >> 5) + gl; w <= ((yend - 1) >> 5) && yend > y0; w += 32)
+				{
+					const int wlo = w << 5;
+					const int a = (y0 > wlo ? y0 : wlo) - wlo, b = (yend < wlo + 32 ? yend : wlo + 32) - wlo;
+					ymask[w] |= ((b >= 32) ? 0xffffffffu : ((1u << b) - 1u)) & ~((1u << a) - 1u);
+				}
+				if (IDS && mine && s0.have && !(s0.pz * res_y2 + s0.py <= s0.pz * (float)yc))
+				{
+					c_cols++; c_total += slen; if (slen) c_cols1++;
+					int y = yc, it = slen;
+					for (int r = 0; r < nr; r++)
+					{
+						const unsigned rw = run_word(s0.rw, r);
+						if (rw >> 10) { c_proc++; c_vox += (int)(rw >> 10) << s0.cmip; }
+						if (!((flags >> r) & 1u)) continue;
+						if (proj[r * 32 + gl].y <= y) { it = r + 1; break; }
+						if (r == ra) { y = T; c_rend++; }
+					}
+					c_iter += it;
+				}
+				ycmin = yend;
+				hiw = hiw > yend ? hiw : yend;
+				todo = 0;
+				__syncwarp();
+			}
+		}
+
 		while (todo)
 		{
 			if (ycmin >= ycmax) { finished = true; break; }
@@ -575,6 +677,7 @@ k_traverse_w(const __grid_constant__ TraverseParams P)
 							const int y = first_clear(ymask, s1y, s2y);                        // Cuda_Render.h:639-640
 							if (y >= s2y) continue;
 							if (IDS) c_rend++;
+							hiw = hiw > s2y ? hiw : s2y;
 							const int n = s2y - y;
 							if (n >= RLERC_COOP_MIN)
 							{
@@ -609,6 +712,7 @@ k_traverse_w(const __grid_constant__ TraverseParams P)
 				}
 				ycmin = __shfl_sync(FULL, ycmin, L);
 				ycmax = __shfl_sync(FULL, ycmax, L);
+				hiw = __shfl_sync(FULL, hiw, L);
 			}
 			else
 			{
@@ -617,7 +721,7 @@ k_traverse_w(const __grid_constant__ TraverseParams P)
 				long_column<IDS>(R, P.level[m].slabs, __shfl_sync(FULL, s0.e0, L), __shfl_sync(FULL, s0.e1, L),
 				                 __shfl_sync(FULL, s0.pz, L), __shfl_sync(FULL, s0.py, L),
 				                 __shfl_sync(FULL, s0.czz, L), __shfl_sync(FULL, s0.cyy, L),
-				                 m, __shfl_sync(FULL, s0.cidx, L), ycmin, ycmax, lstats);
+				                 m, __shfl_sync(FULL, s0.cidx, L), ycmin, ycmax, hiw, lstats);
 			}
 		}
 
@@ -697,6 +801,9 @@ k_traverse_w(const __grid_constant__ TraverseParams P)
 		atomicAdd(P.counters + 7, c_cols1);
 		if (gl == 0) atomicAdd(P.counters + 8, (unsigned long long)(ymax0 - ymin0 + 1));
 		atomicAdd(P.counters + 9, c_steps);
+		if (gl == 0) for (int k = 0; k < 6; k++) atomicAdd(P.counters + 10 + k, k < 3 ? dbg[k] : 0ull);
+		if (gl == 0) P.counters[15] = 0;
+		if (gl == 0) for (int k = 0; k < 8; k++) atomicAdd(P.counters + 16 + k, dbg[3 + k]);
 	}
 }
 
