@@ -156,6 +156,8 @@ def main():
     R = g.build(quiet=True)
     kind, _, _, (WW, HH), desc = WORKLOADS[args.workload]
     cfg = R.FrameConfig.default(WW, HH)
+    # torchrun exports OMP_NUM_THREADS=1: give every rank its share of the host cores for scene construction
+    R.lib().rlerc_set_host_threads(max(1, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world)))))
 
     # ------------------------------------------------------------------ reference arm (host CPU)
     if args.impl == "reference":

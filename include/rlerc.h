@@ -86,6 +86,9 @@ typedef struct rlerc_scene rlerc_scene;   /* host-side RLE4 (R/src/Rle4.h:25-52)
 
 const char* rlerc_last_error(void);
 const char* rlerc_version(void);
+/* Host worker threads of the scene tools (compressor, tiler, synth); n <= 0 only queries. Launchers such
+ * as torchrun export OMP_NUM_THREADS=1, which would make scene construction single-threaded. */
+int  rlerc_set_host_threads(int n);
 
 /* ---- scene: replaces RLE4::load/save/clear/compress_all (R/src/Rle4.cpp:16-384) ---- */
 
@@ -122,6 +125,8 @@ int  rlerc_scene_upload(rlerc_ctx* c, const rlerc_scene* s);
 int  rlerc_scene_device_maps(rlerc_ctx* c, rlerc_map4* out16, int* nummaps);
 /* Traversal kernel variant: lanes cooperating on one ray plane (1,2,4,8,16,32; 0 = auto). */
 int  rlerc_set_lanes_per_ray(rlerc_ctx* c, int lanes);
+/* k_traverse_w only: run the DDA in dedicated producer blocks (default on) or inside every warp. */
+int  rlerc_set_dda_producer(rlerc_ctx* c, int on);
 
 /* ---- frame setup: replaces RayMap::set_border/set_ray_limit/get_ray_map ------------ */
 

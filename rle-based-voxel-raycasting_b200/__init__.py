@@ -77,6 +77,7 @@ _SIGS = {
     "rlerc_frame_config_default": (None, [C.c_int, C.c_int, _P]),
     "rlerc_last_error": (C.c_char_p, []),
     "rlerc_version": (C.c_char_p, []),
+    "rlerc_set_host_threads": (C.c_int, [C.c_int]),
     "rlerc_scene_load": (C.c_int, [C.c_char_p, C.POINTER(_P)]),
     "rlerc_scene_save": (C.c_int, [_P, C.c_char_p]),
     "rlerc_scene_from_maps": (C.c_int, [_P, C.c_int, C.POINTER(_P)]),
@@ -91,6 +92,7 @@ _SIGS = {
     "rlerc_scene_upload": (C.c_int, [_P, _P]),
     "rlerc_scene_device_maps": (C.c_int, [_P, _P, C.POINTER(C.c_int)]),
     "rlerc_set_lanes_per_ray": (C.c_int, [_P, C.c_int]),
+    "rlerc_set_dda_producer": (C.c_int, [_P, C.c_int]),
     "rlerc_frame_setup": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_float), _P, _P]),
     "rlerc_render": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P]),
     "rlerc_render_ids": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, _P]),
@@ -301,6 +303,9 @@ class Renderer:
 
     def set_lanes_per_ray(self, lanes):
         _check(lib().rlerc_set_lanes_per_ray(self._c, lanes))
+
+    def set_dda_producer(self, on):
+        _check(lib().rlerc_set_dda_producer(self._c, 1 if on else 0))
 
     def set_timing(self, on):
         _check(lib().rlerc_set_timing(self._c, 1 if on else 0))

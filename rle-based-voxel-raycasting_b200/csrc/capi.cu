@@ -54,6 +54,11 @@ struct rlerc_ctx {
 	uint32_t* d_ids_scratch = nullptr;
 	unsigned long long* d_counters = nullptr;
 	int lanes = 0;                      // 0 = auto
+	int producer = 0;                   // decoupled DDA producer blocks (k_traverse_w): optional, off by default
+	float4* d_ring = nullptr;
+	size_t ring_bytes = 0;
+	int* d_ring_ctl = nullptr;          // head[rays] | tail[rays] | err
+	size_t ring_ctl_bytes = 0;
 	bool timing = false;
 	bool own_stream = true;
 	cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
@@ -206,6 +211,8 @@ void rlerc_destroy(rlerc_ctx* c)
 	if (c->d_warp) cudaFree(c->d_warp);
 	if (c->d_rgba) cudaFree(c->d_rgba);
 	if (c->d_counters) cudaFree(c->d_counters);
+	if (c->d_ring) cudaFree(c->d_ring);
+	if (c->d_ring_ctl) cudaFree(c->d_ring_ctl);
 	for (int i = 0; i < rlerc_ctx::kSlots; i++)
 	{
 		if (c->slot[i].d_warp) cudaFree(c->slot[i].d_warp);
@@ -295,6 +302,13 @@ int rlerc_set_lanes_per_ray(rlerc_ctx* c, int lanes)
 	return RLERC_OK;
 }
 
+int rlerc_set_dda_producer(rlerc_ctx* c, int on)
+{
+	if (!c) return RLERC_ERR_ARG;
+	c->producer = on != 0;
+	return RLERC_OK;
+}
+
 int rlerc_set_timing(rlerc_ctx* c, int on)
 {
 	if (!c) return RLERC_ERR_ARG;
@@ -337,6 +351,14 @@ static int render_impl(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_c
 		P.ids = d_ids;
 		P.counters = c->d_counters;
 		CK(cudaMemsetAsync(c->d_counters, 0, 32 * sizeof(unsigned long long), c->stream));
+	}
+	if (c->lanes == 0 && c->producer)
+	{
+		const int cap = cfg->rays_casted;
+		if ((rc = ensure((void**)&c->d_ring, &c->ring_bytes, traverse_ring_bytes(cap)))) return rc;
+		if ((rc = ensure((void**)&c->d_ring_ctl, &c->ring_ctl_bytes, (size_t)(2 * cap + 4) * sizeof(int)))) return rc;
+		CK(cudaMemsetAsync(c->d_ring_ctl, 0, (size_t)(2 * cap + 4) * sizeof(int), c->stream));
+		P.dda_ring = c->d_ring; P.dda_head = c->d_ring_ctl; P.dda_tail = c->d_ring_ctl + cap; P.dda_err = c->d_ring_ctl + 2 * cap;
 	}
 	if (c->timing) CK(cudaEventRecord(c->ev[0], c->stream));
 	launch_traverse(P, pick_lanes(c, P.ray_end - P.ray_begin), ids, c->stream);

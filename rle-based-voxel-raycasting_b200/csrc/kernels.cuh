@@ -37,6 +37,11 @@ struct TraverseParams {
 	uint32_t* warp;          // [rays_casted][res_y]
 	uint32_t* ids;           // optional [rays_casted][res_y][2]
 	unsigned long long* counters; // optional [10]
+	// decoupled DDA producer (traverse_warp.cu); dda_ring == nullptr: every warp runs its own DDA
+	float4* dda_ring;        // [rays][RING_DEPTH][33]
+	int* dda_head;           // [rays] batches produced
+	int* dda_tail;           // [rays] batches consumed, -1 = ray plane finished
+	int* dda_err;            // protocol time-out flag
 };
 
 struct UnwarpParams {
@@ -55,6 +60,7 @@ struct UnwarpParams {
 
 void launch_traverse(const TraverseParams& p, int lanes_per_ray, bool ids, cudaStream_t st);
 void launch_traverse_warp(const TraverseParams& p, bool ids, cudaStream_t st);   // traverse_warp.cu
+size_t traverse_ring_bytes(int rays);
 void launch_unwarp(const UnwarpParams& p, cudaStream_t st);
 void launch_fill_u32(uint32_t* p, uint32_t v, size_t n, cudaStream_t st);
 

@@ -10,6 +10,9 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include "rlerc_internal.h"
 
 namespace rlerc {
@@ -324,6 +327,17 @@ extern "C" {
 
 const char* rlerc_last_error(void) { return g_err; }
 const char* rlerc_version(void) { return "rlerc 0.1 (sm_100a)"; }
+
+int rlerc_set_host_threads(int n)
+{
+#ifdef _OPENMP
+	if (n > 0) omp_set_num_threads(n);
+	return omp_get_max_threads();
+#else
+	(void)n;
+	return 1;
+#endif
+}
 
 int rlerc_scene_nummaps(const rlerc_scene* s) { return s ? (int)s->levels.size() : RLERC_ERR_ARG; }
 

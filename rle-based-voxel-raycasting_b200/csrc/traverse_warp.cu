@@ -46,13 +46,17 @@ struct DrawJob {            // owner lane -> warp hand-off for a long pixel span
 };
 
 // One batch of 32 columns in flight: what a lane knows about its column.
+// What stays in registers between iterations is only what is in flight from memory; the
+// projected cell geometry of the two younger batches waits in shared memory (geo ring).
 struct Stage {
-	float pz, py, czz, cyy;  // pos3d_z, pos3d_y (scaled), corr_zz, corr_yy (Cuda_Render.h:459-464,483-486)
-	int cmip, cidx;          // mip level and column index vx + vz*gridx
 	unsigned e0, e1;         // pointer-map entry
 	unsigned rw[4];          // run words 0..7, two per register
 	int nvalid;              // crossings in this batch (uniform); 0 = empty stage
 	bool have;               // this lane's column may be visited
+};
+struct Geo {
+	float pz, py, czz, cyy;  // pos3d_z, pos3d_y (scaled), corr_zz, corr_yy (Cuda_Render.h:459-464,483-486)
+	int cmip, cidx;          // mip level and column index vx + vz*gridx
 };
 
 // run word r (0..7) of a stage; r is a run-time value, the words live in registers
@@ -243,9 +247,103 @@ __device__ __noinline__ void long_column(const RayCtx& R, const uint16_t* slabs,
 	ycmin_io = ycmin; ycmax_io = ycmax;
 }
 
-template <bool IDS>
+// ---- decoupled DDA producer ---------------------------------------------------------------------
+// The DDA of a ray plane is a serial float recurrence that a consumer warp would execute redundantly
+// in all 32 lanes (a third of its instructions).  With PC = true the first blocks of the grid are
+// PRODUCERS instead: one lane per ray plane (32 independent recurrences per warp, no redundancy)
+// writing batches of 32 crossing records into a small per-ray ring in global memory (L2-resident),
+// DEPTH batches ahead of the consumer warp that owns the ray plane.  head[i] / tail[i] are the
+// produced / consumed batch counts of launch-local ray i (tail = -1: the consumer is finished).
+#define RLERC_RING_DEPTH 8
+#define RLERC_RING_SLOT 33          // float4 records per batch: carry + 32 crossings
+#define RLERC_SPIN_LIMIT (1 << 22)  // ~0.5 s of polling: a protocol failure must not hang the GPU
+
+__device__ __forceinline__ int ld_volatile(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
+__device__ __forceinline__ void st_volatile(int* p, int v) { asm volatile("st.volatile.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
+
+__device__ __noinline__ void dda_producer(const TraverseParams& P, int rays)
+{
+	const unsigned FULL = 0xffffffffu;
+	const int i = blockIdx.x * RLERC_BLOCK + threadIdx.x;      // launch-local ray index of this lane
+	bool done = i >= rays;
+	Dda dd;
+	float posx = 0, posy = 0, dist_now = 0;
+	int index = 0, mip = 0, zi = 0, dzi = 1, mapswitch = P.mapswitch0;
+	const int last_map = P.nummaps - 1;
+	dd.g0x = dd.g0y = dd.g1x = dd.g1y = dd.i0x = dd.i0y = dd.i1x = dd.i1y = dd.gd0 = dd.gd1 = dd.d0 = dd.d1 = 0; dd.fixx = dd.fixz = 0;
+	if (!done)
+	{
+		const int x = owned_ray(P, i);
+		RayInit ri;
+		ray_init(P, x, ri);
+		if (x >= P.ray_end || ri.skip) done = true;          // the consumer returns before it ever looks at the ring
+		else
+		{
+			dda_init(P, ri.ray_x, ri.ray_z, dd);
+			for (float yms = P.viewpos[1]; yms > 512.0f; yms = yms * 0.5f)     // Cuda_Render.h:343 (first crossing only)
+			{
+				if (mip < last_map) mip++;
+				dd.g0x *= 2; dd.g0y *= 2; dd.g1x *= 2; dd.g1y *= 2; dd.gd0 *= 2; dd.gd1 *= 2;
+				mapswitch *= 2; dzi *= 2;
+			}
+		}
+	}
+	int head = 0, spins = 0;
+	while (true)
+	{
+		int tail = 0;
+		if (!done) { tail = ld_volatile(P.dda_tail + i); if (tail < 0) done = true; }
+		const bool can = !done && (head - tail) < RLERC_RING_DEPTH;
+		if (!__any_sync(FULL, can))
+		{
+			if (__all_sync(FULL, done)) break;
+			if (ld_volatile(P.dda_err) || ++spins > RLERC_SPIN_LIMIT) { st_volatile(P.dda_err, 1); break; }
+			__nanosleep(256);
+			continue;
+		}
+		spins = 0;
+		// every lane fills all the room its ring has (up to DEPTH batches), then ONE fence and ONE
+		// publication of head: the fence (all scattered record stores must be visible) is the expensive part
+		int made = 0;
+		while (__any_sync(FULL, !done && (head + made - tail) < RLERC_RING_DEPTH))
+		{
+			if (!done && (head + made - tail) < RLERC_RING_DEPTH)
+			{
+				float4* slot = P.dda_ring + ((size_t)i * RLERC_RING_DEPTH + ((head + made) & (RLERC_RING_DEPTH - 1))) * RLERC_RING_SLOT;
+				const float4 carry = make_float4(index ? -dist_now : dist_now, posx, posy, 0.0f);
+				int nvalid = 32;
+				for (int s = 0; s < 32; s++)
+				{
+					while (zi > mapswitch)                               // Cuda_Render.h:343-365
+					{
+						if (mip < last_map) mip++;
+						dd.g0x *= 2; dd.g0y *= 2; dd.g1x *= 2; dd.g1y *= 2; dd.gd0 *= 2; dd.gd1 *= 2;
+						mapswitch *= 2; dzi *= 2;
+					}
+					if (zi + dzi > P.z_far) { nvalid = s; break; }       // Cuda_Render.h:366-367
+					zi += dzi;
+					const bool t1 = dd.d1 < dd.d0;                       // Cuda_Render.h:398-414
+					dist_now = t1 ? dd.d1 : dd.d0;
+					posx = t1 ? dd.i1x : dd.i0x;
+					posy = t1 ? dd.i1y : dd.i0y;
+					index = t1 ? 1 : 0;
+					__stcg(slot + s + 1, make_float4(t1 ? -dist_now : dist_now, posx, posy, __int_as_float(mip)));
+					if (t1) { dd.d1 += dd.gd1; dd.i1x += dd.g1x; dd.i1y += dd.g1y; }
+					else    { dd.d0 += dd.gd0; dd.i0x += dd.g0x; dd.i0y += dd.g0y; }
+				}
+				__stcg(slot, make_float4(carry.x, carry.y, carry.z, __int_as_float(nvalid)));
+				made++;
+				if (nvalid < 32) done = true;
+			}
+		}
+		__threadfence();
+		if (made) { head += made; st_volatile(P.dda_head + i, head); }
+	}
+}
+
+template <bool IDS, bool PC>
 __global__ void __launch_bounds__(RLERC_BLOCK, 4)
-k_traverse_w(const __grid_constant__ TraverseParams P)
+k_traverse_w(const __grid_constant__ TraverseParams P, int rays, int producer_blocks)
 {
 	extern __shared__ __align__(16) uint32_t smem[];
 	constexpr int G = 32;
@@ -254,18 +352,21 @@ k_traverse_w(const __grid_constant__ TraverseParams P)
 	const int wid = threadIdx.x >> 5;
 	const unsigned FULL = 0xffffffffu;
 
-	const int x = owned_ray(P, blockIdx.x * WPB + wid);
+	if (PC && (int)blockIdx.x < producer_blocks) { dda_producer(P, rays); return; }
+	const int ray_i = ((int)blockIdx.x - (PC ? producer_blocks : 0)) * WPB + wid;    // launch-local ray index
+	const int x = owned_ray(P, ray_i);
 	if (x >= P.ray_end) return;
 
 	// shared per warp: 33 crossing records (float4) | DrawJob (16 words) | RW x 32 projected runs (int2) |
-	//                  RW x 32 deferred short spans | occlusion bits
-	const int per_warp = ((G + 1) * 4 + 16 + RLERC_RW * 96 + P.mask_words + 3) & ~3;
+	//                  RW x 32 deferred short spans | geometry of 3 batches | occlusion bits
+	const int per_warp = ((G + 1) * 4 + 16 + RLERC_RW * 96 + 3 * 6 * 32 + P.mask_words + 3) & ~3;
 	uint32_t* wbase = smem + (size_t)wid * per_warp;
 	float4* rec = reinterpret_cast<float4*>(wbase);
 	DrawJob* job = reinterpret_cast<DrawJob*>(wbase + (G + 1) * 4);
 	int2* proj = reinterpret_cast<int2*>(wbase + (G + 1) * 4 + 16);     // [r][lane] = {scr_y1, scr_y2}
 	uint32_t* shade = wbase + (G + 1) * 4 + 16 + RLERC_RW * 64;         // [r][lane] deferred short spans
-	uint32_t* ymask = wbase + (G + 1) * 4 + 16 + RLERC_RW * 96;
+	uint32_t* geo = wbase + (G + 1) * 4 + 16 + RLERC_RW * 96;            // [3 batches][6 fields][lane]
+	uint32_t* ymask = wbase + (G + 1) * 4 + 16 + RLERC_RW * 96 + 3 * 6 * 32;
 
 	const int res_y = P.res_y;
 	const float res_y2 = (float)(res_y / 2);             // Cuda_Render.h:108 (integer division)
@@ -321,11 +422,16 @@ k_traverse_w(const __grid_constant__ TraverseParams P)
 	Stage s0, s1, s2;
 	s0.nvalid = s1.nvalid = s2.nvalid = 0;
 	s0.have = s1.have = s2.have = false;
-	s0.pz = s0.py = s0.czz = s0.cyy = 0; s0.cmip = s0.cidx = 0; s0.e0 = s0.e1 = 0;
+	s0.e0 = s0.e1 = 0;
 	s1 = s0; s2 = s0;
+	int bslot = 0;                    // geo ring slot of the batch produced by A in this iteration
 	#pragma unroll
 	for (int k = 0; k < 4; k++) { s0.rw[k] = 0; s1.rw[k] = 0; s2.rw[k] = 0; }
 	bool dda_done = false;
+	int consumed = 0;                 // PC: batches taken from the producer's ring
+	float4 pra = make_float4(0, 0, 0, 0), prb = pra, nra = pra, nrb = pra;
+	bool have_next = false;
+	int known_head = 0;
 
 	RayCtx R;
 	R.row = row; R.ymask = ymask; R.ids = IDS ? P.ids + (size_t)x * res_y * 2 : nullptr;
@@ -338,6 +444,16 @@ k_traverse_w(const __grid_constant__ TraverseParams P)
 		if (ycmin >= ycmax) break;                               // Cuda_Render.h:370
 		s0 = s1; s1 = s2;
 		s2.nvalid = 0; s2.have = false;
+		bslot = bslot == 2 ? 0 : bslot + 1;
+		const int slot0 = bslot == 2 ? 0 : bslot + 1;            // written two iterations ago: batch s0
+		const int slot1 = slot0 == 2 ? 0 : slot0 + 1;            // written one iteration ago: batch s1
+		Geo g0;
+		{
+			const uint32_t* gp = geo + slot0 * 192 + gl;
+			g0.pz = __uint_as_float(gp[0]); g0.py = __uint_as_float(gp[32]);
+			g0.czz = __uint_as_float(gp[64]); g0.cyy = __uint_as_float(gp[96]);
+			g0.cmip = (int)gp[128]; g0.cidx = (int)gp[160];
+		}
 
 		// ---- C2. project the runs of batch s0 (their words were requested one iteration ago) ----
 		int slen = 0, nr = 0;
@@ -353,13 +469,13 @@ k_traverse_w(const __grid_constant__ TraverseParams P)
 			{
 				const unsigned rw = run_word(s0.rw, r);
 				const int skip = (int)(rw & 1023u), solid = (int)(rw >> 10);
-				const int top = (blen + skip) << s0.cmip;                // sti_general_sti_skip
-				const int bot = top + (solid << s0.cmip);                // sti_general
+				const int top = (blen + skip) << g0.cmip;                // sti_general_sti_skip
+				const int bot = top + (solid << g0.cmip);                // sti_general
 				blen += skip + solid;
 				if (solid == 0) continue;
 				const float ft = (float)top, fb = (float)bot;           // Cuda_Render.h:529-560
-				float zz1 = s0.pz, yy1 = s0.py;
-				if (mountain + ft >= 0) { zz1 += s0.czz; yy1 += s0.cyy; }
+				float zz1 = g0.pz, yy1 = g0.py;
+				if (mountain + ft >= 0) { zz1 += g0.czz; yy1 += g0.cyy; }
 				const float z1 = zz1 + pz_add * ft;
 				if (z1 <= 0) continue;
 				flags |= 1u << r;
@@ -368,8 +484,8 @@ k_traverse_w(const __grid_constant__ TraverseParams P)
 				int sy1 = 0;
 				if (sy2 > ycmin)
 				{
-					float zz2 = s0.pz, yy2 = s0.py;
-					if (mountain + fb < 0) { zz2 += s0.czz; yy2 += s0.cyy; }
+					float zz2 = g0.pz, yy2 = g0.py;
+					if (mountain + fb < 0) { zz2 += g0.czz; yy2 += g0.cyy; }
 					const float z2 = zz2 + pz_add * fb;
 					if (!(z2 <= 0))
 					{
@@ -391,85 +507,130 @@ k_traverse_w(const __grid_constant__ TraverseParams P)
 		// ---- A. next batch of crossings: DDA, column address, conservative top clip, map gather ---
 		if (!dda_done)
 		{
-			// z, dz, mapswitch and z_far are integer valued (z counts steps of 2^k), so the number of
-			// crossings before the next LOD switch / before z_far is known up front and the inner
-			// loop runs without per-step tests.  Slot s+1 receives the state after crossing s; slot
-			// 0 carries the state before the batch.  All lanes store the same words (uniform address).
 			int nvalid = G;
-			rec[0] = make_float4(index ? -dist_now : dist_now, posx, posy, 0.0f);
-			for (int s = 0; s < G;)
+			if (PC)
 			{
-				while (zi > mapswitch)                               // Cuda_Render.h:343-365
+				// the records of this batch were normally requested one iteration ago (see the end of A)
+				if (!have_next)
 				{
-					if (mip < last_map) mip++;
-					g0x *= 2; g0y *= 2; g1x *= 2; g1y *= 2;
-					gd0 *= 2; gd1 *= 2;
-					mapswitch *= 2;
-					dzi *= 2;
-				}
-				const int lod_free = (mapswitch - zi) / dzi + 1;     // crossings before z > mapswitch
-				const int far_free = (zfar_i - zi) / dzi;            // crossings with z + dz <= z_far (Cuda_Render.h:366-367)
-				if (far_free <= 0) { nvalid = s; break; }
-				int n = G - s;
-				n = n < lod_free ? n : lod_free;
-				n = n < far_free ? n : far_free;
-				// record of a crossing: {dist (negated when the z-track fired), pos.x, pos.y, mip}
-				const float mipf = __int_as_float(mip);
-				float4* out = rec + s + 1;
-				#define RLERC_DDA_STEP(K)                                                         \
-					{                                                                             \
-						const bool t1 = d1 < d0;                      /* Cuda_Render.h:398-414 */ \
-						dist_now = t1 ? d1 : d0;                                                  \
-						posx = t1 ? i1x : i0x;                                                    \
-						posy = t1 ? i1y : i0y;                                                    \
-						out[K] = make_float4(t1 ? -d1 : d0, posx, posy, mipf);                    \
-						if (t1) { d1 += gd1; i1x += g1x; i1y += g1y; }                            \
-						else    { d0 += gd0; i0x += g0x; i0y += g0y; }                            \
+					int spins = 0;
+					while ((known_head = ld_volatile(P.dda_head + ray_i)) <= consumed)
+					{
+						if (ld_volatile(P.dda_err) || ++spins > RLERC_SPIN_LIMIT) { st_volatile(P.dda_err, 1); nvalid = 0; break; }
+						__nanosleep(128);
 					}
-				int j = 0;
-				for (; j + 4 <= n; j += 4)
-				{
-					RLERC_DDA_STEP(j) RLERC_DDA_STEP(j + 1) RLERC_DDA_STEP(j + 2) RLERC_DDA_STEP(j + 3)
+					const float4* slot = P.dda_ring + ((size_t)ray_i * RLERC_RING_DEPTH + (consumed & (RLERC_RING_DEPTH - 1))) * RLERC_RING_SLOT;
+					nra = __ldcg(slot + gl);
+					nrb = __ldcg(slot + gl + 1);
 				}
-				for (; j < n; j++) RLERC_DDA_STEP(j)
-				#undef RLERC_DDA_STEP
-				index = __float_as_int(out[n - 1].x) < 0 ? 1 : 0;
-				zi += n * dzi;
-				s += n;
+				pra = nra;                                            // state before crossing gl
+				prb = nrb;                                            // state after crossing gl
+				have_next = false;
+				const int nv = __float_as_int(__shfl_sync(FULL, pra.w, 0));
+				if (nvalid) nvalid = nv;
+				// the slot of the PREVIOUS batch is free again: its records were consumed a whole iteration ago
+				if (gl == 0 && consumed > 0) st_volatile(P.dda_tail + ray_i, consumed);
+				consumed++;
+			}
+			else
+			{
+				// z, dz, mapswitch and z_far are integer valued (z counts steps of 2^k), so the number of
+				// crossings before the next LOD switch / before z_far is known up front and the inner
+				// loop runs without per-step tests.  Slot s+1 receives the state after crossing s; slot
+				// 0 carries the state before the batch.  All lanes store the same words (uniform address).
+				rec[0] = make_float4(index ? -dist_now : dist_now, posx, posy, 0.0f);
+				for (int s = 0; s < G;)
+				{
+					while (zi > mapswitch)                               // Cuda_Render.h:343-365
+					{
+						if (mip < last_map) mip++;
+						g0x *= 2; g0y *= 2; g1x *= 2; g1y *= 2;
+						gd0 *= 2; gd1 *= 2;
+						mapswitch *= 2;
+						dzi *= 2;
+					}
+					const int lod_free = (mapswitch - zi) / dzi + 1;     // crossings before z > mapswitch
+					const int far_free = (zfar_i - zi) / dzi;            // crossings with z + dz <= z_far (Cuda_Render.h:366-367)
+					if (far_free <= 0) { nvalid = s; break; }
+					int n = G - s;
+					n = n < lod_free ? n : lod_free;
+					n = n < far_free ? n : far_free;
+					// record of a crossing: {dist (negated when the z-track fired), pos.x, pos.y, mip}
+					const float mipf = __int_as_float(mip);
+					float4* out = rec + s + 1;
+					#define RLERC_DDA_STEP(K)                                                         \
+						{                                                                             \
+							const bool t1 = d1 < d0;                      /* Cuda_Render.h:398-414 */ \
+							dist_now = t1 ? d1 : d0;                                                  \
+							posx = t1 ? i1x : i0x;                                                    \
+							posy = t1 ? i1y : i0y;                                                    \
+							out[K] = make_float4(t1 ? -d1 : d0, posx, posy, mipf);                    \
+							if (t1) { d1 += gd1; i1x += g1x; i1y += g1y; }                            \
+							else    { d0 += gd0; i0x += g0x; i0y += g0y; }                            \
+						}
+					int j = 0;
+					for (; j + 4 <= n; j += 4)
+					{
+						RLERC_DDA_STEP(j) RLERC_DDA_STEP(j + 1) RLERC_DDA_STEP(j + 2) RLERC_DDA_STEP(j + 3)
+					}
+					for (; j < n; j++) RLERC_DDA_STEP(j)
+					#undef RLERC_DDA_STEP
+					index = __float_as_int(out[n - 1].x) < 0 ? 1 : 0;
+					zi += n * dzi;
+					s += n;
+				}
 			}
 			if (nvalid < G) dda_done = true;
 			if (IDS && gl == 0) c_steps += nvalid;
 			s2.nvalid = nvalid;
 			if (gl < nvalid)
 			{
-				const float4 ra = rec[gl], rb = rec[gl + 1];        // state before / after crossing gl
+				Geo g2;
+				const float4 ra = PC ? pra : rec[gl], rb = PC ? prb : rec[gl + 1];   // state before / after crossing gl
 				const float db = fabsf(ra.x), dn = fabsf(rb.x);
 				const int ib = __float_as_int(ra.x) < 0 ? 1 : 0;        // index_before: sign bit of the record
-				s2.cmip = __float_as_int(rb.w);
+				g2.cmip = __float_as_int(rb.w);
 				const int fix_x = (1 - ib) * fixx, fix_z = ib * fixz;    // Cuda_Render.h:418-419
 				const float ddelta = dn - db;
 				const float vsx = ray_x * db, vsz = ray_z * db;
 				const int voxel_x = f2i(vpx + ra.y) + fix_x;             // Cuda_Render.h:429-430
 				const int voxel_z = f2i(vpz + ra.z) + fix_z;
-				const int gx = P.level[s2.cmip].sx, gz = P.level[s2.cmip].sz;
-				const int vx = (voxel_x >> s2.cmip) & (gx - 1);          // Cuda_Render.h:441-442
-				const int vz = (voxel_z >> s2.cmip) & (gz - 1);
-				s2.cidx = vx + vz * gx;
+				const int gx = P.level[g2.cmip].sx, gz = P.level[g2.cmip].sz;
+				const int vx = (voxel_x >> g2.cmip) & (gx - 1);          // Cuda_Render.h:441-442
+				const int vz = (voxel_z >> g2.cmip) & (gz - 1);
+				g2.cidx = vx + vz * gx;
 				const float corx = ray_x * ddelta, corz = ray_z * ddelta;
-				s2.pz = cos_x * vsz + sin_x * mountain;                  // Cuda_Render.h:459-464
-				s2.py = vertical ? (cos_x * mountain - sin_x * vsz) : vsx;
-				s2.py *= rx2mr;
-				s2.czz = cos_x * corz;                                   // Cuda_Render.h:483-486
-				s2.cyy = vertical ? (-sin_x * corz) : corx;
-				s2.cyy *= rx2mr;
+				g2.pz = cos_x * vsz + sin_x * mountain;                  // Cuda_Render.h:459-464
+				g2.py = vertical ? (cos_x * mountain - sin_x * vsz) : vsx;
+				g2.py *= rx2mr;
+				g2.czz = cos_x * corz;                                   // Cuda_Render.h:483-486
+				g2.cyy = vertical ? (-sin_x * corz) : corx;
+				g2.cyy *= rx2mr;
 				// The horizon only rises until this batch is consumed.  For pz > 0 a column culled
 				// now stays culled; for pz <= 0 (or NaN) the test can flip, so keep those.
-				s2.have = !(s2.pz * res_y2 + s2.py <= s2.pz * (float)ycmin) || !(s2.pz > 0);
+				s2.have = !(g2.pz * res_y2 + g2.py <= g2.pz * (float)ycmin) || !(g2.pz > 0);
 				if (s2.have)
 				{
-					const uint2 ent = __ldg(P.level[s2.cmip].map + s2.cidx);     // Cuda_Render.h:474-478
+					const uint2 ent = __ldg(P.level[g2.cmip].map + g2.cidx);     // Cuda_Render.h:474-478
 					s2.e0 = ent.x; s2.e1 = ent.y;
+					uint32_t* gp = geo + bslot * 192 + gl;
+					gp[0] = __float_as_uint(g2.pz); gp[32] = __float_as_uint(g2.py);
+					gp[64] = __float_as_uint(g2.czz); gp[96] = __float_as_uint(g2.cyy);
+					gp[128] = (uint32_t)g2.cmip; gp[160] = (uint32_t)g2.cidx;
 				}
+			}
+		}
+
+		// PC: request the crossing records of the next batch now; they land while this batch is consumed
+		if (PC && !dda_done && !have_next)
+		{
+			if (known_head <= consumed) known_head = ld_volatile(P.dda_head + ray_i);
+			if (known_head > consumed)
+			{
+				const float4* slot = P.dda_ring + ((size_t)ray_i * RLERC_RING_DEPTH + (consumed & (RLERC_RING_DEPTH - 1))) * RLERC_RING_SLOT;
+				nra = __ldcg(slot + gl);
+				nrb = __ldcg(slot + gl + 1);
+				have_next = true;
 			}
 		}
 
@@ -479,7 +640,7 @@ k_traverse_w(const __grid_constant__ TraverseParams P)
 			const int sl = (int)(s1.e1 & 0xffffu);
 			// element i0 of the slab stream is run 0; runs 0..7 are fetched as aligned 32-bit words
 			const unsigned i0 = 2u + s1.e0;
-			const uint32_t* w32 = reinterpret_cast<const uint32_t*>(P.level[s1.cmip].slabs);
+			const uint32_t* w32 = reinterpret_cast<const uint32_t*>(P.level[geo[slot1 * 192 + 128 + gl]].slabs);
 			const unsigned first = s1.e1 >> 16;
 			if (!(i0 & 1u))
 			{
@@ -521,11 +682,11 @@ k_traverse_w(const __grid_constant__ TraverseParams P)
 			if (IDS && gl == 0) dbg[1]++;
 			const int y0 = ycmin;
 			const bool mine = (todo >> gl) & 1u;
-			const bool pass0 = mine && s0.have && !(s0.pz * res_y2 + s0.py <= s0.pz * (float)y0);
+			const bool pass0 = mine && s0.have && !(g0.pz * res_y2 + g0.py <= g0.pz * (float)y0);
 			bool ok = true;
 			int T = INT_MIN, ra = -1;
 			int why = 0;
-			if (mine && s0.have && !pass0 && !(s0.pz > 0)) { ok = false; why |= 1; }      // culled now, may pass later
+			if (mine && s0.have && !pass0 && !(g0.pz > 0)) { ok = false; why |= 1; }      // culled now, may pass later
 			if (pass0)
 			{
 				if (longcol) { ok = false; why |= 2; }
@@ -561,7 +722,7 @@ k_traverse_w(const __grid_constant__ TraverseParams P)
 			yc = yc > y0 ? yc : y0;
 			const bool draws = pass0 && T > yc;
 			// a column that draws must still pass the top-clip test under the horizon it meets
-			if (draws && (s0.pz * res_y2 + s0.py <= s0.pz * (float)yc)) { ok = false; why |= 128; }
+			if (draws && (g0.pz * res_y2 + g0.py <= g0.pz * (float)yc)) { ok = false; why |= 128; }
 			if (IDS)
 			{
 				const unsigned allwhy = __reduce_or_sync(FULL, (unsigned)why);
@@ -583,14 +744,14 @@ k_traverse_w(const __grid_constant__ TraverseParams P)
 					const int a = (y0 > wlo ? y0 : wlo) - wlo, b = (yend < wlo + 32 ? yend : wlo + 32) - wlo;
 					ymask[w] |= ((b >= 32) ? 0xffffffffu : ((1u << b) - 1u)) & ~((1u << a) - 1u);
 				}
-				if (IDS && mine && s0.have && !(s0.pz * res_y2 + s0.py <= s0.pz * (float)yc))
+				if (IDS && mine && s0.have && !(g0.pz * res_y2 + g0.py <= g0.pz * (float)yc))
 				{
 					c_cols++; c_total += slen; if (slen) c_cols1++;
 					int y = yc, it = slen;
 					for (int r = 0; r < nr; r++)
 					{
 						const unsigned rw = run_word(s0.rw, r);
-						if (rw >> 10) { c_proc++; c_vox += (int)(rw >> 10) << s0.cmip; }
+						if (rw >> 10) { c_proc++; c_vox += (int)(rw >> 10) << g0.cmip; }
 						if (!((flags >> r) & 1u)) continue;
 						if (proj[r * 32 + gl].y <= y) { it = r + 1; break; }
 						if (r == ra) { y = T; c_rend++; }
@@ -608,7 +769,7 @@ k_traverse_w(const __grid_constant__ TraverseParams P)
 		{
 			if (ycmin >= ycmax) { finished = true; break; }
 			const bool mine = (todo >> gl) & 1u;
-			const bool pass = mine && s0.have && !(s0.pz * res_y2 + s0.py <= s0.pz * (float)ycmin);   // Cuda_Render.h:467
+			const bool pass = mine && s0.have && !(g0.pz * res_y2 + g0.py <= g0.pz * (float)ycmin);   // Cuda_Render.h:467
 			// does my column draw (or is it too long to tell)?  also: where would its run loop stop
 			bool ev = false;
 			int my_iter = slen, my_proc = 0, my_vox = 0;
@@ -620,7 +781,7 @@ k_traverse_w(const __grid_constant__ TraverseParams P)
 					if (IDS)
 					{
 						const unsigned rw = run_word(s0.rw, r);
-						if (rw >> 10) { my_proc++; my_vox += (int)(rw >> 10) << s0.cmip; }
+						if (rw >> 10) { my_proc++; my_vox += (int)(rw >> 10) << g0.cmip; }
 					}
 					if (!((flags >> r) & 1u)) continue;
 					const int2 sy = proj[r * 32 + gl];
@@ -657,11 +818,11 @@ k_traverse_w(const __grid_constant__ TraverseParams P)
 						{
 							const unsigned rw = run_word(s0.rw, r);
 							const int skip = (int)(rw & 1023u), solid = (int)(rw >> 10);
-							const int top = (blen + skip) << s0.cmip;
-							const int bot = top + (solid << s0.cmip);
+							const int top = (blen + skip) << g0.cmip;
+							const int bot = top + (solid << g0.cmip);
 							const int texture = btex, texn = btex + solid;
 							blen += skip + solid; btex += solid;
-							if (IDS) { c_iter++; if (solid > 0) { c_proc++; c_vox += solid << s0.cmip; } }
+							if (IDS) { c_iter++; if (solid > 0) { c_proc++; c_vox += solid << g0.cmip; } }
 							if (!((flags >> r) & 1u)) continue;
 							const int2 sy = proj[r * 32 + gl];
 							if (sy.y <= ycmin) break;                                          // Cuda_Render.h:543
@@ -681,10 +842,10 @@ k_traverse_w(const __grid_constant__ TraverseParams P)
 							const int n = s2y - y;
 							if (n >= RLERC_COOP_MIN)
 							{
-								job->cpz = s0.pz; job->cpy = s0.py;
+								job->cpz = g0.pz; job->cpy = g0.py;
 								job->y = y; job->s2 = s2y; job->rtop = top; job->rbot = bot;
 								job->rtex = texture; job->rtexn = texn;
-								job->m = s0.cmip; job->colid = s0.cidx; job->e0 = s0.e0; job->slen = (unsigned)slen;
+								job->m = g0.cmip; job->colid = g0.cidx; job->e0 = s0.e0; job->slen = (unsigned)slen;
 								act = 1; rnext = r + 1;
 								break;
 							}
@@ -717,11 +878,11 @@ k_traverse_w(const __grid_constant__ TraverseParams P)
 			else
 			{
 				// ---- long column: lane <-> run -----------------------------------------------------
-				const int m = __shfl_sync(FULL, s0.cmip, L);
+				const int m = __shfl_sync(FULL, g0.cmip, L);
 				long_column<IDS>(R, P.level[m].slabs, __shfl_sync(FULL, s0.e0, L), __shfl_sync(FULL, s0.e1, L),
-				                 __shfl_sync(FULL, s0.pz, L), __shfl_sync(FULL, s0.py, L),
-				                 __shfl_sync(FULL, s0.czz, L), __shfl_sync(FULL, s0.cyy, L),
-				                 m, __shfl_sync(FULL, s0.cidx, L), ycmin, ycmax, hiw, lstats);
+				                 __shfl_sync(FULL, g0.pz, L), __shfl_sync(FULL, g0.py, L),
+				                 __shfl_sync(FULL, g0.czz, L), __shfl_sync(FULL, g0.cyy, L),
+				                 m, __shfl_sync(FULL, g0.cidx, L), ycmin, ycmax, hiw, lstats);
 			}
 		}
 
@@ -729,13 +890,13 @@ k_traverse_w(const __grid_constant__ TraverseParams P)
 		if (shade_runs)
 		{
 			int blen = 0, btex = 0;
-			const uint16_t* send = P.level[s0.cmip].slabs + 2 + (size_t)s0.e0 + slen;
+			const uint16_t* send = P.level[g0.cmip].slabs + 2 + (size_t)s0.e0 + slen;
 			for (int r = 0; r < nr; r++)
 			{
 				const unsigned rw = run_word(s0.rw, r);
 				const int skip = (int)(rw & 1023u), solid = (int)(rw >> 10);
-				const int top = (blen + skip) << s0.cmip;
-				const int bot = top + (solid << s0.cmip);
+				const int top = (blen + skip) << g0.cmip;
+				const int bot = top + (solid << g0.cmip);
 				const int texture = btex, texn = btex + solid;
 				blen += skip + solid; btex += solid;
 				if (!((shade_runs >> r) & 1u)) continue;
@@ -745,8 +906,8 @@ k_traverse_w(const __grid_constant__ TraverseParams P)
 				unsigned clear = jw >> 20;
 				// interpolants (Cuda_Render.h:645-680)
 				const float ft = (float)top, fb2 = (float)bot;
-				const float z1r = s0.pz + pz_add * ft, y1r = s0.py + py_add * ft;
-				const float z2r = s0.pz + pz_add * fb2, y2r = s0.py + py_add * fb2;
+				const float z1r = g0.pz + pz_add * ft, y1r = g0.py + py_add * ft;
+				const float z2r = g0.pz + pz_add * fb2, y2r = g0.py + py_add * fb2;
 				const float s2r = res_y2 + y1r / z1r;
 				const float s1r = res_y2 + y2r / z2r;
 				const float u1z = (float)texn / z2r;
@@ -770,8 +931,8 @@ k_traverse_w(const __grid_constant__ TraverseParams P)
 					if (IDS)
 					{
 						c_pix++;
-						R.ids[y * 2] = (uint32_t)s0.cidx;
-						R.ids[y * 2 + 1] = ((uint32_t)s0.cmip << 16) | (uint32_t)ui;
+						R.ids[y * 2] = (uint32_t)g0.cidx;
+						R.ids[y * 2 + 1] = ((uint32_t)g0.cmip << 16) | (uint32_t)ui;
 					}
 				}
 			}
@@ -779,6 +940,7 @@ k_traverse_w(const __grid_constant__ TraverseParams P)
 		if (finished) break;
 		if (dda_done && s1.nvalid == 0 && s2.nvalid == 0) break;      // pipeline drained (z > z_far, Cuda_Render.h:367)
 	}
+	if (PC && gl == 0) st_volatile(P.dda_tail + ray_i, -1);
 	if (IDS)
 	{
 		c_iter += lstats[0]; c_proc += lstats[1]; c_vox += lstats[2]; c_rend += lstats[3]; c_pix += lstats[4];
@@ -807,26 +969,31 @@ k_traverse_w(const __grid_constant__ TraverseParams P)
 	}
 }
 
-template <bool IDS>
+template <bool IDS, bool PC>
 static void launch_w(const TraverseParams& p, cudaStream_t st)
 {
 	const int wpb = RLERC_BLOCK / 32;
 	const int rays = (p.slice_n > 1) ? owned_count(p.ray_end, p.slice_block, p.slice_n, p.slice_rank) : p.ray_end - p.ray_begin;
 	if (rays <= 0) return;
-	const int blocks = (rays + wpb - 1) / wpb;
-	const size_t smem = (size_t)wpb * ((33 * 4 + 16 + RLERC_RW * 96 + p.mask_words + 3) & ~3) * sizeof(uint32_t);
+	const int producers = PC ? (rays + RLERC_BLOCK - 1) / RLERC_BLOCK : 0;
+	const int blocks = producers + (rays + wpb - 1) / wpb;
+	const size_t smem = (size_t)wpb * ((33 * 4 + 16 + RLERC_RW * 96 + 3 * 6 * 32 + p.mask_words + 3) & ~3) * sizeof(uint32_t);
 	static size_t configured = 0;
 	if (smem > configured)
 	{
-		cudaFuncSetAttribute(k_traverse_w<IDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		cudaFuncSetAttribute(k_traverse_w<IDS, PC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		configured = smem;
 	}
-	k_traverse_w<IDS><<<blocks, RLERC_BLOCK, smem, st>>>(p);
+	k_traverse_w<IDS, PC><<<blocks, RLERC_BLOCK, smem, st>>>(p, rays, producers);
 }
+
+size_t traverse_ring_bytes(int rays) { return (size_t)rays * RLERC_RING_DEPTH * RLERC_RING_SLOT * sizeof(float4); }
 
 void launch_traverse_warp(const TraverseParams& p, bool ids, cudaStream_t st)
 {
-	if (ids) launch_w<true>(p, st); else launch_w<false>(p, st);
+	const bool pc = p.dda_ring != nullptr;
+	if (ids) { if (pc) launch_w<true, true>(p, st); else launch_w<true, false>(p, st); }
+	else     { if (pc) launch_w<false, true>(p, st); else launch_w<false, false>(p, st); }
 }
 
 } // namespace rlerc

@@ -11,6 +11,7 @@ scene, name, sy = bench.build_scene(R, workload, lambda m: None)
 W, H = bench.WORKLOADS[workload][3]
 cfg = R.FrameConfig.default(W, H)
 r = R.Renderer(0); r.all_to_gpu(scene); r.set_timing(True); r.set_lanes_per_ray(lanes)
+if len(sys.argv) > 4: r.set_dda_producer(int(sys.argv[4]))
 ids = torch.empty((cfg.rays_casted, cfg.render_size, 2), dtype=torch.int32, device="cuda")
 names = ["elems_total", "elems_processed", "voxels_processed", "elems_rendered", "pixels", "cols_fetched", "run_iters", "cols_nonempty", "cleared", "dda_steps"]
 for t in range(0, 1000, stride):
