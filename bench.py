@@ -145,6 +145,8 @@ def main():
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--slice-block", type=int, default=32)
+    ap.add_argument("--mp", default="frames", choices=["frames", "slices"],
+                    help="N > 1: deal whole frames to the GPUs (throughput, default) or split every frame into ray-plane slices (latency, north-star mode)")
     args = ap.parse_args()
     K, W = max(1, args.steps), max(3, args.warmup)
     rank = int(os.environ.get("RANK", "0"))
@@ -213,29 +215,61 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up
+    farm = MG.FrameFarm(r, cfg, torch, rank, world, dist) if (world > 1 and args.mp == "frames") else None
+    rounds = (K + world - 1) // world
+
+    # ---- warm-up (also initialises NCCL's channels: the first collectives take 100+ ms)
     for i in range(W):
         frame.render(raymaps[i % K])
+    if farm is not None:
+        for rd in range(max(W, 4)):
+            farm.render_round(rd, raymaps[(rd * world + rank) % K])
+        farm.finish()
     barrier()
 
-    # ---- timed region: K steps, device time per step from CUDA events on the launching stream
+    # ---- timed region: K steps (frames), device time per step from CUDA events on the launching stream
     sampler = ClockSampler(local)
     sampler.start()
     r.set_timing(True)
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     trav_ms, unwarp_ms = 0.0, 0.0
+    ev = []
     barrier()
     wall0 = time.perf_counter()
-    for i in range(K):
-        if flush is not None:
-            flush.fill_(i & 255)
-        ev[i][0].record()
-        frame.render(raymaps[i])
-        ev[i][1].record()
-        ev[i][1].synchronize()
-        a, b = r.last_kernel_ms()
-        trav_ms += a
-        unwarp_ms += b
+    if farm is None:
+        # 1 GPU, or every frame split into ray-plane slices over all GPUs
+        for i in range(K):
+            if flush is not None:
+                flush.fill_(i & 255)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            frame.render(raymaps[i])
+            e1.record()
+            e1.synchronize()
+            ev.append((e0, e1))
+            a, b_ = r.last_kernel_ms()
+            trav_ms += a
+            unwarp_ms += b_
+    else:
+        # whole frames dealt round-robin; the gather of round rd overlaps the rendering of round rd+1
+        for rd in range(rounds):
+            i = rd * world + rank
+            if flush is not None:
+                flush.fill_(rd & 255)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            farm.render_round(rd, raymaps[i] if i < K else None)
+            e1.record()
+            e1.synchronize()
+            ev.append((e0, e1))
+            if i < K:
+                a, b_ = r.last_kernel_ms()
+                trav_ms += a
+                unwarp_ms += b_
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        farm.finish()
+        e1.record()
+        ev.append((e0, e1))
     barrier()
     wall = time.perf_counter() - wall0
     clocks = sampler.summary()
@@ -247,16 +281,20 @@ def main():
     dev_ms, trav_ms_max, unwarp_ms_max = (float(v) for v in t.cpu())
     fps = K / (dev_ms / 1e3)
     value = WW * HH * fps / 1e6
+    launches_per_rank = (K if farm is None else len(range(rank, K, world)))
+    kernels_timed = launches_per_rank               # traversal launches behind trav_ms on the slowest rank
 
     # ---- warm-L2 variant (no flush), for information
-    barrier()
-    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s0.record()
-    for i in range(K):
-        frame.render(raymaps[i])
-    s1.record()
-    barrier()
-    warm_ms = s0.elapsed_time(s1)
+    warm_ms = None
+    if farm is None:
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for i in range(K):
+            frame.render(raymaps[i])
+        s1.record()
+        barrier()
+        warm_ms = s0.elapsed_time(s1)
 
     # ---- roofline of the traversal kernel: algorithmic bytes from the instrumented kernel (N=1 semantics)
     roof = None
@@ -285,13 +323,15 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         # per-rank launches traverse 1/world of the ray planes
-        achieved = (bytes_per_frame / world) / (trav_ms_max / K / 1e3) / 1e9
+        sliced = world > 1 and farm is None
+        per_launch_bytes = bytes_per_frame / (world if sliced else 1)
+        achieved = per_launch_bytes / (trav_ms_max / max(kernels_timed, 1) / 1e3) / 1e9
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "kernel": "k_traverse_w" if args.lanes == 0 else "k_traverse<%d>" % args.lanes,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
-                "algorithmic_bytes_per_launch": bytes_per_frame / world,
-                "traverse_ms_per_launch": trav_ms_max / K, "unwarp_ms_per_launch": unwarp_ms_max / K,
-                "unwarp_achieved_gbs": 8.0 * WW * HH / (max(unwarp_ms_max, 1e-9) / K / 1e3) / 1e9,
+                "algorithmic_bytes_per_launch": per_launch_bytes,
+                "traverse_ms_per_launch": trav_ms_max / max(kernels_timed, 1), "unwarp_ms_per_launch": unwarp_ms_max / max(kernels_timed, 1),
+                "unwarp_achieved_gbs": 8.0 * WW * HH / (max(unwarp_ms_max, 1e-9) / max(kernels_timed, 1) / 1e3) / 1e9,
                 "counters_per_frame": {k_: v / len(sample_idx) for k_, v in agg.items()},
                 "plane_rays_per_frame": tot_rays / len(sample_idx)}
 
@@ -320,7 +360,7 @@ def main():
         for p in pins:
             p.free()
         r2.close()
-    else:
+    elif farm is None:
         host = torch.empty((HH, WW, 4), dtype=torch.uint8).pin_memory() if rank == 0 else None
         barrier()
         t0 = time.perf_counter()
@@ -332,6 +372,24 @@ def main():
         barrier()
         e2e_wall = time.perf_counter() - t0
         checksum = int(host[::16, ::16].to(torch.int64).sum()) if rank == 0 else 0
+    else:
+        hosts = [torch.empty((HH, WW, 4), dtype=torch.uint8).pin_memory() for _ in range(world)] if rank == 0 else None
+        barrier()
+        t0 = time.perf_counter()
+        for rd in range(rounds + 1):
+            if rd < rounds:
+                i = rd * world + rank
+                rm = R.RayMap(cfg).get_ray_map(poses[i][0], poses[i][1]) if i < K else None
+                farm.render_round(rd, rm)
+            if rd > 0 and rank == 0:
+                done = farm.wait_round(rd - 1)          # frames of the previous round are on rank 0: D2H them
+                for j in range(world):
+                    if (rd - 1) * world + j < K:
+                        hosts[j].copy_(done[j], non_blocking=True)
+        farm.finish()
+        barrier()
+        e2e_wall = time.perf_counter() - t0
+        checksum = int(hosts[(K - 1) % world][::16, ::16].to(torch.int64).sum()) if rank == 0 else 0
     tt = torch.tensor([e2e_wall], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -340,7 +398,8 @@ def main():
     e2e = {"value": WW * HH * e2e_fps / 1e6, "unit": "Mrays/s", "frames_per_s": e2e_fps,
            "h2d_bytes_per_step": 1024 * world, "d2h_bytes_per_step": WW * HH * 4,
            "how": "pinned host RGBA out, camera pose in; %s" % ("rlerc_frame_submit/wait, 3 frames in flight" if world == 1
-                                                                 else "per-rank kernels + NCCL reduce + D2H on rank 0"),
+                                                                 else ("per-rank slices + NCCL reduce + D2H on rank 0" if farm is None
+                                                                       else "whole frames per rank + NCCL gather + D2H of every frame on rank 0")),
            "checksum": checksum}
 
     # ---- CPU baseline on the box's host cores (rank 0, N=1 only), bounded sample
@@ -368,10 +427,14 @@ def main():
                 "dtype": "f32", "data": "synthetic" if scene_name != "Imrodh.rle4" else "Imrodh.rle4",
                 "frames_per_s": fps,
                 "config": {"workload": args.workload, "scene": scene_name, "scene_mb": scene.nbytes() / 1e6, "window": [WW, HH],
+                           "steps_are": "frames of the fly-through; the K frames of the job are the same for every N",
                            "render_size": cfg.render_size, "rays_casted": cfg.rays_casted, "z_far": cfg.z_far,
                            "description": desc, "l2": "flushed between timed steps (512 MiB write)" if flush is not None else "not flushed",
-                           "warm_l2_value": WW * HH * (K / (warm_ms / 1e3)) / 1e6, "lanes": args.lanes,
-                           "parallelism": "ray-plane slices x%d, interleaved blocks of %d, NCCL reduce" % (world, args.slice_block) if world > 1 else "1 GPU",
+                           "warm_l2_value": (WW * HH * (K / (warm_ms / 1e3)) / 1e6) if warm_ms else None, "lanes": args.lanes,
+                           "parallelism": ("1 GPU" if world == 1 else
+                                           ("whole frames dealt round-robin to %d GPUs (full replica each), NCCL gather of finished frames to rank 0, overlapped" % world
+                                            if farm is not None else
+                                            "every frame split into ray-plane slices x%d, interleaved blocks of %d, NCCL reduce to rank 0" % (world, args.slice_block))),
                            "wall_s_timed_region": wall},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": 2 * K, "roofline": roof}
         if cpu:

@@ -54,3 +54,44 @@ class SlicedFrame:
         self.r.render_interleaved(raymap_gpu, self.cfg, self.block, self.world, self.rank)
         self.r.unwarp_interleaved(raymap_gpu, self.cfg, self.block, self.world, self.rank, d_rgba=self.rgba.data_ptr())
         return composite(self.rgba, self.dist)
+
+
+class FrameFarm:
+    """Alternate-frame rendering for throughput: the frames of a sequence are dealt round-robin to the
+    ranks (rank r renders frames r, r+N, ...), every rank renders WHOLE frames from its own replica,
+    and the finished frames of a round are gathered on rank 0 with one NCCL gather that overlaps the
+    next round's rendering (double-buffered).  This is BASELINE config 5's "one camera per GPU with
+    NVLink compositing" applied to the fly-through; per-frame latency is that of one GPU."""
+
+    def __init__(self, renderer, cfg, torch, rank, world, dist):
+        self.r, self.cfg, self.torch, self.rank, self.world, self.dist = renderer, cfg, torch, rank, world, dist
+        dev = torch.device("cuda", renderer.device)
+        shape = (cfg.height, cfg.width, 4)
+        self.bufs = [torch.zeros(shape, dtype=torch.uint8, device=dev) for _ in range(2)]
+        self.lists = [[torch.empty(shape, dtype=torch.uint8, device=dev) for _ in range(world)] if rank == 0 else None
+                      for _ in range(2)]
+        self.handles = [None, None]
+        renderer.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+
+    def render_round(self, rd, raymap_gpu):
+        """Render this rank's frame of round `rd` (None: no frame left) and start gathering the round."""
+        k = rd & 1
+        if self.handles[k] is not None:
+            self.handles[k].wait()          # buffer k is free again (stream-ordered, no host block)
+        if raymap_gpu is not None:
+            self.r.render(raymap_gpu, self.cfg)
+            self.r.unwarp(raymap_gpu, self.cfg, d_rgba=self.bufs[k].data_ptr())
+        self.handles[k] = self.dist.gather(self.bufs[k], self.lists[k], dst=0, async_op=True)
+
+    def wait_round(self, rd):
+        k = rd & 1
+        if self.handles[k] is not None:
+            self.handles[k].wait()
+            self.handles[k] = None
+        return self.lists[k]
+
+    def finish(self):
+        for k in (0, 1):
+            if self.handles[k] is not None:
+                self.handles[k].wait()
+                self.handles[k] = None
