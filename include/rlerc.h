@@ -168,6 +168,11 @@ int  rlerc_unwarp(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_config
 int  rlerc_unwarp_slice(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_config* cfg,
                         const uint32_t* d_warp, uint8_t* d_rgba, int ray_begin, int ray_end);
 
+/* Depth-aware smoothing: replaces GLSL pass 2 (R/bin/shader/soft.frag:1-75, R/src/main.cpp:628-653).
+ * d_rgba_in = rlerc_unwarp output (alpha = quantised 0.001/z), d_rgba_out = RGBA8 [height][width][4]; not in place.
+ * The reference's 2048^2 FBO is enlarged to the next power of two that holds the window. */
+int  rlerc_soft(rlerc_ctx* c, const rlerc_frame_config* cfg, const uint8_t* d_rgba_in, uint8_t* d_rgba_out);
+
 /* Interleaved multi-GPU slices: ray plane r belongs to `rank` iff
  * (r / block) % nranks == rank.  render: traverses only the owned ray planes; unwarp: writes
  * only pixels whose ray plane is owned, 0 elsewhere (sum over ranks == single-GPU image). */

@@ -242,3 +242,14 @@ def attach_host_scene(rm, levels):
         e.map, e.slabs = mp.ctypes.data, sl.ctypes.data
     rm.nummaps = len(levels)
     return rm
+
+
+def orc_soft(rgba):
+    """GLSL pass 2 (soft.frag) on an RGBA8 image [H][W][4] (row 0 = top)."""
+    rgba = np.ascontiguousarray(rgba, dtype=np.uint8)
+    H, W = rgba.shape[:2]
+    out = np.zeros_like(rgba)
+    lib = port()
+    lib.orc_soft.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.orc_soft(W, H, rgba.ctypes.data, out.ctypes.data)
+    return out

@@ -497,6 +497,84 @@ int orc_unwarp(const void* raymap, int W, int H, int RS, int RC, int rays_casted
 	return 0;
 }
 
+
+/* Depth-aware smoothing: R/bin/shader/soft.frag:1-75 on the pass-1 image as it sits in the lower-left
+ * W x H corner of the reference's square GL_RGBA8 FBO texture (GL_LINEAR, CLAMP_TO_EDGE, R/src/GL_Main.h:151-164;
+ * texCoord spans 0..W/fbo, 0..H/fbo, R/src/main.cpp:606-607,639-643).  Texels outside the window are never
+ * rendered by the reference and read as 0.  in/out: RGBA8 [H][W][4], row 0 = top.  Parity unpinned (GLSL). */
+namespace {
+struct F4 { float x, y, z, w; };
+inline F4 soft_texel(const uint8_t* in, int W, int H, int i, int j)
+{
+	F4 r = { 0, 0, 0, 0 };
+	if (i >= W || j >= H) return r;
+	const uint8_t* p = in + ((size_t)(H - 1 - j) * W + i) * 4;
+	r.x = (float)p[0] / 255.0f; r.y = (float)p[1] / 255.0f; r.z = (float)p[2] / 255.0f; r.w = (float)p[3] / 255.0f;
+	return r;
+}
+inline F4 soft_fetch(const uint8_t* in, int W, int H, int fbo, float x, float y)
+{
+	const float u = x * (float)fbo - 0.5f, v = y * (float)fbo - 0.5f;
+	const float fu0 = floorf(u), fv0 = floorf(v);
+	const float fu = u - fu0, fv = v - fv0;
+	int i0 = f2i(fu0), j0 = f2i(fv0), i1 = i0 + 1, j1 = j0 + 1;
+	const int hi = fbo - 1;
+	i0 = i0 < 0 ? 0 : (i0 > hi ? hi : i0); i1 = i1 < 0 ? 0 : (i1 > hi ? hi : i1);
+	j0 = j0 < 0 ? 0 : (j0 > hi ? hi : j0); j1 = j1 < 0 ? 0 : (j1 > hi ? hi : j1);
+	const F4 a = soft_texel(in, W, H, i0, j0), b = soft_texel(in, W, H, i1, j0), c = soft_texel(in, W, H, i0, j1), d = soft_texel(in, W, H, i1, j1);
+	F4 r;
+	r.x = (a.x * (1.0f - fu) + b.x * fu) * (1.0f - fv) + (c.x * (1.0f - fu) + d.x * fu) * fv;
+	r.y = (a.y * (1.0f - fu) + b.y * fu) * (1.0f - fv) + (c.y * (1.0f - fu) + d.y * fu) * fv;
+	r.z = (a.z * (1.0f - fu) + b.z * fu) * (1.0f - fv) + (c.z * (1.0f - fu) + d.z * fu) * fv;
+	r.w = (a.w * (1.0f - fu) + b.w * fu) * (1.0f - fv) + (c.w * (1.0f - fu) + d.w * fu) * fv;
+	return r;
+}
+} /* namespace */
+
+int orc_soft(int W, int H, const uint8_t* in, uint8_t* out)
+{
+	int fbo = 2048;                                                /* FBO fbo1(2048,2048), R/src/main.cpp:540 */
+	while (fbo < W || fbo < H) fbo *= 2;
+	float tap_x[7], tap_y[7];
+	{	/* soft.frag:16: for (float a = 0; a < 3.1415*2.0; a += 3.1415*1.9/6.0), float like GLSL: 7 taps */
+		float a = 0.0f;
+		const float step = (3.1415f * 1.9f) / 6.0f, lim = 3.1415f * 2.0f;
+		for (int k = 0; k < 7 && a < lim; k++, a += step) { tap_x[k] = std::sin(a) * 0.005f; tap_y[k] = std::cos(a) * 0.005f; }
+	}
+	/* soft.frag:38-39: for (float a = -1.0; a < 1.0; a += 2.0/5.0): five values, accumulated in float */
+	float ofs[8]; int nofs = 0;
+	for (float a = -1.0f; a < 1.0f; a += 2.0f / 5.0f) ofs[nofs++] = a;
+	#pragma omp parallel for schedule(static)
+	for (int row = 0; row < H; row++)
+	for (int px = 0; px < W; px++)
+	{
+		const int j = H - 1 - row;
+		const float tx = ((float)px + 0.5f) / (float)fbo, ty = ((float)j + 0.5f) / (float)fbo;
+		F4 col = soft_fetch(in, W, H, fbo, tx, ty);                                   /* :8 */
+		float radmax = col.w;                                                        /* :11-24 */
+		for (int k = 0; k < 7; k++)
+		{
+			const float w = soft_fetch(in, W, H, fbo, tap_x[k] + tx, tap_y[k] + ty).w;
+			radmax = radmax > w ? radmax : w;
+		}
+		const float rad = 0.0023f * radmax;                                          /* :28 */
+		if (rad > 0.00008f)                                                          /* :31 */
+		{
+			F4 avg = col; float n = 1.0f;
+			for (int ia = 0; ia < nofs; ia++)
+			for (int ib = 0; ib < nofs; ib++)
+			{
+				const F4 cin = soft_fetch(in, W, H, fbo, tx + ofs[ia] * rad, ty + ofs[ib] * rad);
+				if (cin.w >= radmax * 0.7f) { avg.x += cin.x; avg.y += cin.y; avg.z += cin.z; avg.w += cin.w; n += 1.0f; }
+			}
+			if (n > 6.0f) { const float s = 1.0f / n; col.x = avg.x * s; col.y = avg.y * s; col.z = avg.z * s; col.w = avg.w * s; }   /* :58-66 */
+		}
+		uint8_t* o = out + ((size_t)row * W + px) * 4;
+		o[0] = (uint8_t)quant8(col.x); o[1] = (uint8_t)quant8(col.y); o[2] = (uint8_t)quant8(col.z); o[3] = (uint8_t)quant8(col.w);
+	}
+	return 0;
+}
+
 /* RayMap::get_ray_map, R/src/RayMap.h:98-402 (+ Nebula matrix44 helpers R/inc/mathlib/_matrix44.h:
  * rotate_x/y :529-560, translate :583-588, invert_simpler :431-441, m*v :863-869).
  * out: RayMap_GPU bytes; map4_gpu/nummaps are left untouched. */

@@ -99,6 +99,7 @@ _SIGS = {
     "rlerc_render_counters": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "rlerc_unwarp": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int]),
     "rlerc_unwarp_slice": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int]),
+    "rlerc_soft": (C.c_int, [_P, _P, _P, _P]),
     "rlerc_render_interleaved": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "rlerc_unwarp_interleaved": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
     "rlerc_set_stream": (C.c_int, [_P, _P]),
@@ -332,6 +333,10 @@ class Renderer:
 
     def unwarp_slice(self, raymap_gpu, cfg, ray_begin, ray_end, d_warp=None, d_rgba=None):
         _check(lib().rlerc_unwarp_slice(self._c, C.byref(raymap_gpu), C.byref(cfg), d_warp, d_rgba, ray_begin, ray_end))
+
+    def soft(self, cfg, d_rgba_in, d_rgba_out):
+        """Depth-aware smoothing, GLSL pass 2 (R/bin/shader/soft.frag)."""
+        _check(lib().rlerc_soft(self._c, C.byref(cfg), d_rgba_in, d_rgba_out))
 
     def render_interleaved(self, raymap_gpu, cfg, block, nranks, rank, d_warp=None):
         _check(lib().rlerc_render_interleaved(self._c, C.byref(raymap_gpu), C.byref(cfg), block, nranks, rank, d_warp))

@@ -475,6 +475,31 @@ int rlerc_set_stream(rlerc_ctx* c, void* cuda_stream)
 	return RLERC_OK;
 }
 
+// soft.frag:16: for (float a = 0; a < 3.1415*2.0; a += 3.1415*1.9/6.0) -> 7 taps, evaluated in float like GLSL
+static void soft_taps(float* tx, float* ty)
+{
+	float a = 0.0f;
+	const float step = (3.1415f * 1.9f) / 6.0f, lim = 3.1415f * 2.0f;
+	for (int k = 0; k < 7 && a < lim; k++, a += step) { tx[k] = std::sin(a) * 0.005f; ty[k] = std::cos(a) * 0.005f; }
+}
+
+int rlerc_soft(rlerc_ctx* c, const rlerc_frame_config* cfg, const uint8_t* d_rgba_in, uint8_t* d_rgba_out)
+{
+	if (!c || !d_rgba_in || !d_rgba_out || d_rgba_in == d_rgba_out) { set_error("rlerc_soft: bad argument (in-place is not supported)"); return RLERC_ERR_ARG; }
+	int rc = check_cfg(cfg);
+	if (rc) return rc;
+	if ((rc = set_dev(c))) return rc;
+	SoftParams S;
+	memset(&S, 0, sizeof(S));
+	S.in = d_rgba_in; S.out = d_rgba_out; S.W = cfg->width; S.H = cfg->height;
+	S.fbo = 2048;                                  // static FBO fbo1(2048,2048), R/src/main.cpp:540
+	while (S.fbo < cfg->width || S.fbo < cfg->height) S.fbo *= 2;
+	soft_taps(S.tap_x, S.tap_y);
+	launch_soft(S, c->stream);
+	CK(cudaGetLastError());
+	return RLERC_OK;
+}
+
 int rlerc_render_frame(rlerc_ctx* c, const float pos[3], const float rot[3], const rlerc_frame_config* cfg, uint8_t* host_rgba, rlerc_raymap* out_raymap)
 {
 	if (!c || !pos || !rot || !host_rgba) { set_error("rlerc_render_frame: null argument"); return RLERC_ERR_ARG; }

@@ -525,6 +525,86 @@ void launch_unwarp(const UnwarpParams& p, cudaStream_t st)
 	k_unwarp<<<grid, block, 0, st>>>(p);
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Depth-aware smoothing: GLSL pass 2 (R/bin/shader/soft.frag:1-75, drawn by R/src/main.cpp:628-653).
+// The pass-1 image sits in the lower-left W x H corner of a square GL_RGBA8 FBO texture with
+// GL_LINEAR / CLAMP_TO_EDGE sampling (R/src/GL_Main.h:151-164); texels outside the window are
+// never rendered by the reference (undefined) and read as 0 here.  One thread per output pixel.
+__device__ __forceinline__ float4 soft_texel(const SoftParams& P, int i, int j)
+{
+	if (i >= P.W || j >= P.H) return make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+	const uint32_t t = __ldg(reinterpret_cast<const uint32_t*>(P.in) + (size_t)(P.H - 1 - j) * P.W + i);
+	return make_float4((float)(t & 255u) / 255.0f, (float)((t >> 8) & 255u) / 255.0f,
+	                   (float)((t >> 16) & 255u) / 255.0f, (float)(t >> 24) / 255.0f);
+}
+
+// texture2D with GL_LINEAR, CLAMP_TO_EDGE at normalised coordinates (x, y)
+__device__ __forceinline__ float4 soft_fetch(const SoftParams& P, float x, float y)
+{
+	const float u = x * (float)P.fbo - 0.5f, v = y * (float)P.fbo - 0.5f;
+	const float fu0 = floorf(u), fv0 = floorf(v);
+	const float fu = u - fu0, fv = v - fv0;
+	int i0 = f2i(fu0), j0 = f2i(fv0), i1 = i0 + 1, j1 = j0 + 1;
+	const int hi = P.fbo - 1;
+	i0 = i0 < 0 ? 0 : (i0 > hi ? hi : i0); i1 = i1 < 0 ? 0 : (i1 > hi ? hi : i1);
+	j0 = j0 < 0 ? 0 : (j0 > hi ? hi : j0); j1 = j1 < 0 ? 0 : (j1 > hi ? hi : j1);
+	const float4 a = soft_texel(P, i0, j0), b = soft_texel(P, i1, j0), c = soft_texel(P, i0, j1), d = soft_texel(P, i1, j1);
+	float4 r;
+	r.x = (a.x * (1.0f - fu) + b.x * fu) * (1.0f - fv) + (c.x * (1.0f - fu) + d.x * fu) * fv;
+	r.y = (a.y * (1.0f - fu) + b.y * fu) * (1.0f - fv) + (c.y * (1.0f - fu) + d.y * fu) * fv;
+	r.z = (a.z * (1.0f - fu) + b.z * fu) * (1.0f - fv) + (c.z * (1.0f - fu) + d.z * fu) * fv;
+	r.w = (a.w * (1.0f - fu) + b.w * fu) * (1.0f - fv) + (c.w * (1.0f - fu) + d.w * fu) * fv;
+	return r;
+}
+
+__global__ void __launch_bounds__(256) k_soft(const __grid_constant__ SoftParams P)
+{
+	const int px = blockIdx.x * blockDim.x + threadIdx.x;
+	const int row = blockIdx.y;
+	if (px >= P.W || row >= P.H) return;
+	const int j = P.H - 1 - row;                                       // GL row
+	const float tx = ((float)px + 0.5f) / (float)P.fbo, ty = ((float)j + 0.5f) / (float)P.fbo;   // texCoord
+	float4 col = soft_fetch(P, tx, ty);                                // soft.frag:8
+	float radmax = col.w;                                              // soft.frag:11-24 (radmin/radavg are dead)
+	#pragma unroll
+	for (int k = 0; k < 7; k++)
+	{
+		const float w = soft_fetch(P, P.tap_x[k] + tx, P.tap_y[k] + ty).w;
+		radmax = fmaxf(radmax, w);
+	}
+	const float rad = 0.0023f * radmax;                                // soft.frag:28
+	if (rad > 0.00008f)                                                // soft.frag:31
+	{
+		float4 avg = col;
+		float n = 1.0f;
+		const float ofs[5] = { -1.0f, -0.6000000238418579f, -0.20000001788139343f, 0.19999998807907104f, 0.6000000238418579f };
+		for (int ia = 0; ia < 5; ia++)                                 // soft.frag:38-56: a, b = -1 + k*(2.0/5.0) in float
+		for (int ib = 0; ib < 5; ib++)
+		{
+			const float4 cin = soft_fetch(P, tx + ofs[ia] * rad, ty + ofs[ib] * rad);
+			if (cin.w >= radmax * 0.7f)
+			{
+				avg.x += cin.x; avg.y += cin.y; avg.z += cin.z; avg.w += cin.w;
+				n += 1.0f;
+			}
+		}
+		if (n > 6.0f)                                                  // soft.frag:58-66 (colavg2/numtodiv2 mirror colavg/numtodiv)
+		{
+			const float s = 1.0f / n;
+			col = make_float4(avg.x * s, avg.y * s, avg.z * s, avg.w * s);
+		}
+	}
+	reinterpret_cast<uint32_t*>(P.out)[(size_t)row * P.W + px] =
+		quant8(col.x) | (quant8(col.y) << 8) | (quant8(col.z) << 16) | (quant8(col.w) << 24);
+}
+
+void launch_soft(const SoftParams& p, cudaStream_t st)
+{
+	dim3 block(128, 1, 1), grid((p.W + 127) / 128, p.H, 1);
+	k_soft<<<grid, block, 0, st>>>(p);
+}
+
 __global__ void k_fill_u32(uint32_t* p, uint32_t v, size_t n)
 {
 	size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -58,6 +58,15 @@ struct UnwarpParams {
 	int slice_block, slice_n, slice_rank;   // interleaved slice mode (slice_n <= 1: off)
 };
 
+struct SoftParams {
+	const uint8_t* in;       // RGBA8 [H][W][4], row 0 = top, A = quantised 0.001/z (k_unwarp output)
+	uint8_t* out;            // RGBA8 [H][W][4]
+	int W, H;
+	int fbo;                 // edge of the square FBO texture the reference renders pass 1 into (2048)
+	float tap_x[7], tap_y[7];   // depth probe offsets sin(a)*0.005, cos(a)*0.005 (soft.frag:16-18)
+};
+
+void launch_soft(const SoftParams& p, cudaStream_t st);
 void launch_traverse(const TraverseParams& p, int lanes_per_ray, bool ids, cudaStream_t st);
 void launch_traverse_warp(const TraverseParams& p, bool ids, cudaStream_t st);   // traverse_warp.cu
 size_t traverse_ring_bytes(int rays);

@@ -45,3 +45,16 @@ def test_raw_golden_rows(R, rb):
     # layout of a texel: attr16 | depth16<<16, depth even, sky sentinel 0xff8844 (Cuda_Render.h:257,708,723)
     hit = gold[(gold != 0) & (gold != 0xff8844)]
     assert hit.size > 0 and np.all(((hit >> 16) & 1) == 0)
+
+
+def test_soft_pass_oracle_properties(rb):
+    """soft.frag restatement: sky (alpha 0 -> rad 0) is left alone; a flat opaque image stays flat away from the
+    top/right window edges (beyond them the reference's FBO was never rendered: read as 0)."""
+    sky = np.zeros((96, 128, 4), np.uint8)
+    sky[..., :3] = (178, 204, 255)
+    assert np.array_equal(rb.orc_soft(sky), sky)
+    flat = np.zeros((300, 400, 4), np.uint8)
+    flat[...] = (90, 120, 150, 40)
+    out = rb.orc_soft(flat)
+    assert np.all(np.abs(out[40:, :360].astype(int) - flat[40:, :360].astype(int)) <= 1)
+    assert not np.array_equal(out[:8], flat[:8])              # top edge mixes in the unrendered FBO

@@ -153,6 +153,27 @@ def _rgba_ptr(gpu, cfg, rm):
     return buf.data_ptr()
 
 
+def test_soft_pass_parity(R, rb, gpu, scene_mid):
+    """Depth-aware smoothing (GLSL pass 2, soft.frag) against its oracle restatement: <= 1 LSB, >= 99.9 % identical."""
+    import torch
+    gpu.all_to_gpu(scene_mid)
+    for wh in ((640, 480), (1920, 1080), (2560, 1440)):          # the last one needs the 4096^2 FBO
+        cfg = R.FrameConfig.default(*wh)
+        for pos, rot in few_cameras(-100.0)[:3]:
+            rm = R.RayMap(cfg).get_ray_map(pos, rot)
+            a = torch.zeros((cfg.height, cfg.width, 4), dtype=torch.uint8, device="cuda")
+            b = torch.zeros_like(a)
+            gpu.render(rm, cfg)
+            gpu.unwarp(rm, cfg, d_rgba=a.data_ptr())
+            gpu.soft(cfg, a.data_ptr(), b.data_ptr())
+            gpu.sync()
+            want = rb.orc_soft(a.cpu().numpy())
+            mx, same = rgb_parity(b.cpu().numpy(), want)
+            assert mx <= 1 and same >= 0.999, (wh, rot, mx, same)
+    with pytest.raises(R.RlercError):
+        gpu.soft(cfg, a.data_ptr(), a.data_ptr())                # in place is refused
+
+
 def test_render_frame_host_buffers_and_pipeline(R, rb, gpu, scene_mid):
     """The all-in-one C-ABI call with HOST buffers, synchronous and pipelined, equals the staged calls."""
     gpu.all_to_gpu(scene_mid)
