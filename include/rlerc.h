@@ -127,6 +127,8 @@ int  rlerc_scene_device_maps(rlerc_ctx* c, rlerc_map4* out16, int* nummaps);
 int  rlerc_set_lanes_per_ray(rlerc_ctx* c, int lanes);
 /* k_traverse_w only: run the DDA in dedicated producer blocks (default on) or inside every warp. */
 int  rlerc_set_dda_producer(rlerc_ctx* c, int on);
+/* k_traverse_w only: 0 = serial DDA recurrence in every warp (default), 2 = merge-path DDA. Same results. */
+int  rlerc_set_dda_mode(rlerc_ctx* c, int mode);
 
 /* ---- frame setup: replaces RayMap::set_border/set_ray_limit/get_ray_map ------------ */
 

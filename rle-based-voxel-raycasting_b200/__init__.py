@@ -93,6 +93,7 @@ _SIGS = {
     "rlerc_scene_device_maps": (C.c_int, [_P, _P, C.POINTER(C.c_int)]),
     "rlerc_set_lanes_per_ray": (C.c_int, [_P, C.c_int]),
     "rlerc_set_dda_producer": (C.c_int, [_P, C.c_int]),
+    "rlerc_set_dda_mode": (C.c_int, [_P, C.c_int]),
     "rlerc_frame_setup": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_float), _P, _P]),
     "rlerc_render": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P]),
     "rlerc_render_ids": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, _P]),
@@ -304,6 +305,9 @@ class Renderer:
 
     def set_lanes_per_ray(self, lanes):
         _check(lib().rlerc_set_lanes_per_ray(self._c, lanes))
+
+    def set_dda_mode(self, mode):
+        _check(lib().rlerc_set_dda_mode(self._c, mode))
 
     def set_dda_producer(self, on):
         _check(lib().rlerc_set_dda_producer(self._c, 1 if on else 0))

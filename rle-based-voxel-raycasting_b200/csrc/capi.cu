@@ -54,6 +54,7 @@ struct rlerc_ctx {
 	uint32_t* d_ids_scratch = nullptr;
 	unsigned long long* d_counters = nullptr;
 	int lanes = 0;                      // 0 = auto
+	int dda_mode = 0;                   // 0 serial (default: fastest measured), 2 merge path (k_traverse_w)
 	int producer = 0;                   // decoupled DDA producer blocks (k_traverse_w): optional, off by default
 	float4* d_ring = nullptr;
 	size_t ring_bytes = 0;
@@ -309,6 +310,13 @@ int rlerc_set_dda_producer(rlerc_ctx* c, int on)
 	return RLERC_OK;
 }
 
+int rlerc_set_dda_mode(rlerc_ctx* c, int mode)
+{
+	if (!c || (mode != 0 && mode != 2)) { set_error("dda mode must be 0 (serial) or 2 (merge path)"); return RLERC_ERR_ARG; }
+	c->dda_mode = mode;
+	return RLERC_OK;
+}
+
 int rlerc_set_timing(rlerc_ctx* c, int on)
 {
 	if (!c) return RLERC_ERR_ARG;
@@ -352,6 +360,7 @@ static int render_impl(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_c
 		P.counters = c->d_counters;
 		CK(cudaMemsetAsync(c->d_counters, 0, 32 * sizeof(unsigned long long), c->stream));
 	}
+	P.dda_mode = c->dda_mode;
 	if (c->lanes == 0 && c->producer)
 	{
 		const int cap = cfg->rays_casted;

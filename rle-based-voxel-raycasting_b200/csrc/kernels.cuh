@@ -42,6 +42,7 @@ struct TraverseParams {
 	int* dda_head;           // [rays] batches produced
 	int* dda_tail;           // [rays] batches consumed, -1 = ray plane finished
 	int* dda_err;            // protocol time-out flag
+	int dda_mode;            // 0: serial DDA in every warp, otherwise merge-path DDA (ignored when dda_ring is set)
 };
 
 struct UnwarpParams {

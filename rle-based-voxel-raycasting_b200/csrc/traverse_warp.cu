@@ -36,6 +36,7 @@
 namespace rlerc {
 
 #define RLERC_RW 8          // runs pre-projected per column (first 8 run words)
+#define RLERC_DDA_WORDS (66 * 4 + 72)   // shared words per warp for the DDA hand-over (merge path: 66 float4 + 72 float)
 #define RLERC_COOP_MIN 12   // pixel spans at least this long are shaded by the whole warp
 
 struct DrawJob {            // owner lane -> warp hand-off for a long pixel span (shared memory)
@@ -247,6 +248,129 @@ __device__ __noinline__ void long_column(const RayCtx& R, const uint16_t* slabs,
 	ycmin_io = ycmin; ycmax_io = ycmax;
 }
 
+
+// ---- the DDA of one ray plane (state shared by the three ways of advancing it) ----------------------
+struct DdaState {
+	float g0x, g0y, g1x, g1y, i0x, i0y, i1x, i1y, gd0, gd1, d0, d1;   // Cuda_Render.h:286-300
+	float posx, posy, dist_now;                                       // last crossing (pos_vxl, dds_dist_now)
+	int index, mip, zi, dzi, mapswitch;                               // z and dz are integer valued
+};
+
+__device__ __forceinline__ void dda_lod_switch(DdaState& S, int last_map)          // Cuda_Render.h:343-365
+{
+	if (S.mip < last_map) S.mip++;
+	S.g0x *= 2; S.g0y *= 2; S.g1x *= 2; S.g1y *= 2;
+	S.gd0 *= 2; S.gd1 *= 2;
+	S.mapswitch *= 2;
+	S.dzi *= 2;
+}
+
+// Serial batch: up to 32 crossings, all lanes in lockstep; rec[s+1] = state after crossing s, rec[0] = state
+// before the batch; record = {dist (negated when the z-track fired), pos.x, pos.y, mip}.  Returns the number
+// of crossings made (< 32 only when z_far was reached, Cuda_Render.h:366-367).
+__device__ __forceinline__ int dda_serial_batch_inl(DdaState& S, float4* rec, int last_map, int zfar_i)
+{
+	int nvalid = 32;
+	rec[0] = make_float4(S.index ? -S.dist_now : S.dist_now, S.posx, S.posy, 0.0f);
+	for (int s = 0; s < 32;)
+	{
+		while (S.zi > S.mapswitch) dda_lod_switch(S, last_map);
+		const int lod_free = (S.mapswitch - S.zi) / S.dzi + 1;     // crossings before z > mapswitch
+		const int far_free = (zfar_i - S.zi) / S.dzi;              // crossings with z + dz <= z_far
+		if (far_free <= 0) { nvalid = s; break; }
+		int n = 32 - s;
+		n = n < lod_free ? n : lod_free;
+		n = n < far_free ? n : far_free;
+		const float mipf = __int_as_float(S.mip);
+		float4* out = rec + s + 1;
+		for (int j = 0; j < n; j++)
+		{
+			const bool t1 = S.d1 < S.d0;                           // Cuda_Render.h:398-414
+			S.dist_now = t1 ? S.d1 : S.d0;
+			S.posx = t1 ? S.i1x : S.i0x;
+			S.posy = t1 ? S.i1y : S.i0y;
+			out[j] = make_float4(t1 ? -S.d1 : S.d0, S.posx, S.posy, mipf);
+			if (t1) { S.d1 += S.gd1; S.i1x += S.g1x; S.i1y += S.g1y; }
+			else    { S.d0 += S.gd0; S.i0x += S.g0x; S.i0y += S.g0y; }
+		}
+		S.index = __float_as_int(out[n - 1].x) < 0 ? 1 : 0;
+		S.zi += n * S.dzi;
+		s += n;
+	}
+	return nvalid;
+}
+
+// out-of-line copy for the rare NaN fallback of the merge-path build
+__device__ __noinline__ int dda_serial_batch(DdaState& S, float4* rec, int last_map, int zfar_i)
+{
+	return dda_serial_batch_inl(S, rec, last_map, zfar_i);
+}
+
+// Merge-path batch.  The two tracks of the DDA (x-crossings and z-crossings) are independent recurrences
+// state += gradient; the serial loop only MERGES them (fire the z-track when d1 < d0, else the x-track).
+// So: lanes 0-15 generate the next 33 states of the x-track, lanes 16-31 those of the z-track (33 x 3 adds in
+// lockstep instead of 32 x the whole step), and lane s finds crossing s of the merged order with a 5-step
+// binary search along its merge-path diagonal (ties go to the x-track, exactly like the serial compare).
+// A batch ends early at a LOD switch (the gradients change there).  trk: float4[66], trd: float[72] in shared
+// memory.  Returns the crossings made; ra/rb = this lane's records before/after its crossing; *ended = z_far.
+// Requires d0, d1 free of NaN (sorted tracks); callers route other rays through dda_serial_batch.
+__device__ __forceinline__ int dda_merge_batch(DdaState& S, float4* trk, float* trd, int last_map, int zfar_i, int gl,
+                                               float4& ra, float4& rb, bool& ended)
+{
+	const unsigned FULL = 0xffffffffu;
+	while (S.zi > S.mapswitch) dda_lod_switch(S, last_map);
+	const int lod_free = (S.mapswitch - S.zi) / S.dzi + 1;
+	const int far_free = (zfar_i - S.zi) / S.dzi;
+	if (far_free <= 0) { ended = true; return 0; }
+	int n = 32;
+	n = n < lod_free ? n : lod_free;
+	n = n < far_free ? n : far_free;
+	{
+		const bool zt = gl >= 16;
+		float hd = zt ? S.d1 : S.d0, hx = zt ? S.i1x : S.i0x, hy = zt ? S.i1y : S.i0y;
+		const float ad = zt ? S.gd1 : S.gd0, ax = zt ? S.g1x : S.g0x, ay = zt ? S.g1y : S.g0y;
+		float4* T = trk + (zt ? 33 : 0);
+		float* D = trd + (zt ? 36 : 0);
+		#pragma unroll 11
+		for (int k = 0; k < 33; k++)
+		{
+			T[k] = make_float4(hd, hx, hy, 0.0f);
+			D[k] = hd;
+			hd += ad; hx += ax; hy += ay;
+		}
+	}
+	__syncwarp();
+	int lo = 0, hi = gl;                                  // x-track elements among the first gl crossings
+	#pragma unroll
+	for (int it = 0; it < 5; it++)
+	{
+		if (lo < hi)
+		{
+			const int mid = (lo + hi) >> 1;
+			if (trd[mid] <= trd[36 + gl - mid - 1]) lo = mid + 1; else hi = mid;
+		}
+	}
+	const int ia = lo, jb = gl - lo;
+	const bool t1 = trd[36 + jb] < trd[ia];               // Cuda_Render.h:398
+	const float4 me = t1 ? trk[33 + jb] : trk[ia];
+	rb = make_float4(t1 ? -me.x : me.x, me.y, me.z, __int_as_float(S.mip));
+	ra.x = __shfl_up_sync(FULL, rb.x, 1); ra.y = __shfl_up_sync(FULL, rb.y, 1); ra.z = __shfl_up_sync(FULL, rb.z, 1);
+	ra.w = 0.0f;
+	if (gl == 0) ra = make_float4(S.index ? -S.dist_now : S.dist_now, S.posx, S.posy, 0.0f);
+	// state after the n-th crossing: last record + the heads of both tracks
+	const int last = n - 1;
+	const float lx = __shfl_sync(FULL, rb.x, last);
+	S.dist_now = fabsf(lx); S.index = __float_as_int(lx) < 0 ? 1 : 0;
+	S.posx = __shfl_sync(FULL, rb.y, last); S.posy = __shfl_sync(FULL, rb.z, last);
+	const int in = __shfl_sync(FULL, ia + (t1 ? 0 : 1), last), jn = n - in;
+	const float4 ha = trk[in], hb = trk[33 + jn];
+	S.d0 = ha.x; S.i0x = ha.y; S.i0y = ha.z;
+	S.d1 = hb.x; S.i1x = hb.y; S.i1y = hb.z;
+	S.zi += n * S.dzi;
+	__syncwarp();
+	return n;
+}
+
 // ---- decoupled DDA producer ---------------------------------------------------------------------
 // The DDA of a ray plane is a serial float recurrence that a consumer warp would execute redundantly
 // in all 32 lanes (a third of its instructions).  With PC = true the first blocks of the grid are
@@ -341,7 +465,8 @@ __device__ __noinline__ void dda_producer(const TraverseParams& P, int rays)
 	}
 }
 
-template <bool IDS, bool PC>
+// MODE: how the DDA advances — 0 serial in every warp (default), 1 producer blocks + ring, 2 merge path
+template <bool IDS, int MODE>
 __global__ void __launch_bounds__(RLERC_BLOCK, 4)
 k_traverse_w(const __grid_constant__ TraverseParams P, int rays, int producer_blocks)
 {
@@ -351,6 +476,7 @@ k_traverse_w(const __grid_constant__ TraverseParams P, int rays, int producer_bl
 	const int gl = threadIdx.x & 31;
 	const int wid = threadIdx.x >> 5;
 	const unsigned FULL = 0xffffffffu;
+	constexpr bool PC = (MODE == 1);
 
 	if (PC && (int)blockIdx.x < producer_blocks) { dda_producer(P, rays); return; }
 	const int ray_i = ((int)blockIdx.x - (PC ? producer_blocks : 0)) * WPB + wid;    // launch-local ray index
@@ -359,14 +485,16 @@ k_traverse_w(const __grid_constant__ TraverseParams P, int rays, int producer_bl
 
 	// shared per warp: 33 crossing records (float4) | DrawJob (16 words) | RW x 32 projected runs (int2) |
 	//                  RW x 32 deferred short spans | geometry of 3 batches | occlusion bits
-	const int per_warp = ((G + 1) * 4 + 16 + RLERC_RW * 96 + 3 * 6 * 32 + P.mask_words + 3) & ~3;
+	const int per_warp = (RLERC_DDA_WORDS + 16 + RLERC_RW * 96 + 3 * 6 * 32 + P.mask_words + 3) & ~3;
 	uint32_t* wbase = smem + (size_t)wid * per_warp;
-	float4* rec = reinterpret_cast<float4*>(wbase);
-	DrawJob* job = reinterpret_cast<DrawJob*>(wbase + (G + 1) * 4);
-	int2* proj = reinterpret_cast<int2*>(wbase + (G + 1) * 4 + 16);     // [r][lane] = {scr_y1, scr_y2}
-	uint32_t* shade = wbase + (G + 1) * 4 + 16 + RLERC_RW * 64;         // [r][lane] deferred short spans
-	uint32_t* geo = wbase + (G + 1) * 4 + 16 + RLERC_RW * 96;            // [3 batches][6 fields][lane]
-	uint32_t* ymask = wbase + (G + 1) * 4 + 16 + RLERC_RW * 96 + 3 * 6 * 32;
+	float4* rec = reinterpret_cast<float4*>(wbase);                 // serial DDA: 33 crossing records
+	float4* trk = reinterpret_cast<float4*>(wbase);                 // merge-path DDA: 2 x 33 track states (same space)
+	float* trd = reinterpret_cast<float*>(wbase + 66 * 4);          //                 2 x 36 track distances
+	DrawJob* job = reinterpret_cast<DrawJob*>(wbase + RLERC_DDA_WORDS);
+	int2* proj = reinterpret_cast<int2*>(wbase + RLERC_DDA_WORDS + 16);     // [r][lane] = {scr_y1, scr_y2}
+	uint32_t* shade = wbase + RLERC_DDA_WORDS + 16 + RLERC_RW * 64;         // [r][lane] deferred short spans
+	uint32_t* geo = wbase + RLERC_DDA_WORDS + 16 + RLERC_RW * 96;            // [3 batches][6 fields][lane]
+	uint32_t* ymask = wbase + RLERC_DDA_WORDS + 16 + RLERC_RW * 96 + 3 * 6 * 32;
 
 	const int res_y = P.res_y;
 	const float res_y2 = (float)(res_y / 2);             // Cuda_Render.h:108 (integer division)
@@ -391,27 +519,22 @@ k_traverse_w(const __grid_constant__ TraverseParams P, int rays, int producer_bl
 	Dda dd;
 	dda_init(P, ray_x, ray_z, dd);
 	const int fixx = dd.fixx, fixz = dd.fixz;
-	float g0x = dd.g0x, g0y = dd.g0y, g1x = dd.g1x, g1y = dd.g1y, i0x = dd.i0x, i0y = dd.i0y, i1x = dd.i1x, i1y = dd.i1y;
-	float gd0 = dd.gd0, gd1 = dd.gd1, d0 = dd.d0, d1 = dd.d1;
-	float posx = 0, posy = 0, dist_now = 0;
-	int index = 0;
-	int mip = 0;
+	DdaState S;
+	S.g0x = dd.g0x; S.g0y = dd.g0y; S.g1x = dd.g1x; S.g1y = dd.g1y; S.i0x = dd.i0x; S.i0y = dd.i0y; S.i1x = dd.i1x; S.i1y = dd.i1y;
+	S.gd0 = dd.gd0; S.gd1 = dd.gd1; S.d0 = dd.d0; S.d1 = dd.d1;
+	S.posx = 0; S.posy = 0; S.dist_now = 0; S.index = 0; S.mip = 0;
+	S.zi = 0; S.dzi = 1;                                         // z and dz (Cuda_Render.h:181,325), integer valued
+	S.mapswitch = P.mapswitch0;
 	const float pz_add = sin_x;                                  // pos3d_z_add (Cuda_Render.h:313)
 	const float py_add = (vertical ? cos_x : 0.0f) * rx2mr;      // pos3d_y_add (Cuda_Render.h:314-315)
-	int zi = 0, dzi = 1;                                         // z and dz (Cuda_Render.h:181,325), integer valued
-	int mapswitch = P.mapswitch0;
 	const int zfar_i = P.z_far;
 	const int last_map = P.nummaps - 1;
 	// The y_map_switch half of the LOD loop condition (Cuda_Render.h:343) can only be true on
 	// the first crossing (it halves until <= 512 and never grows), where z = 0 < mapswitch.
-	for (float yms = mountain; yms > 512.0f; yms = yms * 0.5f)
-	{
-		if (mip < last_map) mip++;
-		g0x *= 2; g0y *= 2; g1x *= 2; g1y *= 2;
-		gd0 *= 2; gd1 *= 2;
-		mapswitch *= 2;
-		dzi *= 2;
-	}
+	for (float yms = mountain; yms > 512.0f; yms = yms * 0.5f) dda_lod_switch(S, last_map);
+	// merge path needs sorted tracks: a NaN distance (ray exactly along a grid axis through a lattice point)
+	// falls back to the serial recurrence
+	const bool merge_ok = (MODE == 2) && !(S.d0 != S.d0) && !(S.d1 != S.d1) && !(S.gd0 != S.gd0) && !(S.gd1 != S.gd1);
 
 	// per-lane statistics (IDS build only)
 	unsigned long long c_total = 0, c_proc = 0, c_vox = 0, c_rend = 0, c_pix = 0, c_cols = 0, c_iter = 0, c_cols1 = 0, c_steps = 0;
@@ -532,61 +655,31 @@ k_traverse_w(const __grid_constant__ TraverseParams P, int rays, int producer_bl
 				if (gl == 0 && consumed > 0) st_volatile(P.dda_tail + ray_i, consumed);
 				consumed++;
 			}
+			else if (merge_ok)
+			{
+				bool ended = false;
+				nvalid = dda_merge_batch(S, trk, trd, last_map, zfar_i, gl, pra, prb, ended);
+				if (ended) dda_done = true;
+			}
 			else
 			{
-				// z, dz, mapswitch and z_far are integer valued (z counts steps of 2^k), so the number of
-				// crossings before the next LOD switch / before z_far is known up front and the inner
-				// loop runs without per-step tests.  Slot s+1 receives the state after crossing s; slot
-				// 0 carries the state before the batch.  All lanes store the same words (uniform address).
-				rec[0] = make_float4(index ? -dist_now : dist_now, posx, posy, 0.0f);
-				for (int s = 0; s < G;)
+				if (MODE == 0) nvalid = dda_serial_batch_inl(S, rec, last_map, zfar_i);
+				else
 				{
-					while (zi > mapswitch)                               // Cuda_Render.h:343-365
-					{
-						if (mip < last_map) mip++;
-						g0x *= 2; g0y *= 2; g1x *= 2; g1y *= 2;
-						gd0 *= 2; gd1 *= 2;
-						mapswitch *= 2;
-						dzi *= 2;
-					}
-					const int lod_free = (mapswitch - zi) / dzi + 1;     // crossings before z > mapswitch
-					const int far_free = (zfar_i - zi) / dzi;            // crossings with z + dz <= z_far (Cuda_Render.h:366-367)
-					if (far_free <= 0) { nvalid = s; break; }
-					int n = G - s;
-					n = n < lod_free ? n : lod_free;
-					n = n < far_free ? n : far_free;
-					// record of a crossing: {dist (negated when the z-track fired), pos.x, pos.y, mip}
-					const float mipf = __int_as_float(mip);
-					float4* out = rec + s + 1;
-					#define RLERC_DDA_STEP(K)                                                         \
-						{                                                                             \
-							const bool t1 = d1 < d0;                      /* Cuda_Render.h:398-414 */ \
-							dist_now = t1 ? d1 : d0;                                                  \
-							posx = t1 ? i1x : i0x;                                                    \
-							posy = t1 ? i1y : i0y;                                                    \
-							out[K] = make_float4(t1 ? -d1 : d0, posx, posy, mipf);                    \
-							if (t1) { d1 += gd1; i1x += g1x; i1y += g1y; }                            \
-							else    { d0 += gd0; i0x += g0x; i0y += g0y; }                            \
-						}
-					int j = 0;
-					for (; j + 4 <= n; j += 4)
-					{
-						RLERC_DDA_STEP(j) RLERC_DDA_STEP(j + 1) RLERC_DDA_STEP(j + 2) RLERC_DDA_STEP(j + 3)
-					}
-					for (; j < n; j++) RLERC_DDA_STEP(j)
-					#undef RLERC_DDA_STEP
-					index = __float_as_int(out[n - 1].x) < 0 ? 1 : 0;
-					zi += n * dzi;
-					s += n;
+					DdaState T = S;      // by reference into a non-inlined function: keep S itself in registers
+					nvalid = dda_serial_batch(T, rec, last_map, zfar_i);
+					S = T;
 				}
+				if (nvalid < G) dda_done = true;
+				pra = rec[gl]; prb = rec[gl + 1];
 			}
-			if (nvalid < G) dda_done = true;
+			if (PC && nvalid < G) dda_done = true;
 			if (IDS && gl == 0) c_steps += nvalid;
 			s2.nvalid = nvalid;
 			if (gl < nvalid)
 			{
 				Geo g2;
-				const float4 ra = PC ? pra : rec[gl], rb = PC ? prb : rec[gl + 1];   // state before / after crossing gl
+				const float4 ra = pra, rb = prb;                      // state before / after crossing gl
 				const float db = fabsf(ra.x), dn = fabsf(rb.x);
 				const int ib = __float_as_int(ra.x) < 0 ? 1 : 0;        // index_before: sign bit of the record
 				g2.cmip = __float_as_int(rb.w);
@@ -969,31 +1062,37 @@ k_traverse_w(const __grid_constant__ TraverseParams P, int rays, int producer_bl
 	}
 }
 
-template <bool IDS, bool PC>
+template <bool IDS, int MODE>
 static void launch_w(const TraverseParams& p, cudaStream_t st)
 {
 	const int wpb = RLERC_BLOCK / 32;
 	const int rays = (p.slice_n > 1) ? owned_count(p.ray_end, p.slice_block, p.slice_n, p.slice_rank) : p.ray_end - p.ray_begin;
 	if (rays <= 0) return;
-	const int producers = PC ? (rays + RLERC_BLOCK - 1) / RLERC_BLOCK : 0;
+	const int producers = (MODE == 1) ? (rays + RLERC_BLOCK - 1) / RLERC_BLOCK : 0;
 	const int blocks = producers + (rays + wpb - 1) / wpb;
-	const size_t smem = (size_t)wpb * ((33 * 4 + 16 + RLERC_RW * 96 + 3 * 6 * 32 + p.mask_words + 3) & ~3) * sizeof(uint32_t);
+	const size_t smem = (size_t)wpb * ((RLERC_DDA_WORDS + 16 + RLERC_RW * 96 + 3 * 6 * 32 + p.mask_words + 3) & ~3) * sizeof(uint32_t);
 	static size_t configured = 0;
 	if (smem > configured)
 	{
-		cudaFuncSetAttribute(k_traverse_w<IDS, PC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		cudaFuncSetAttribute(k_traverse_w<IDS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		configured = smem;
 	}
-	k_traverse_w<IDS, PC><<<blocks, RLERC_BLOCK, smem, st>>>(p, rays, producers);
+	k_traverse_w<IDS, MODE><<<blocks, RLERC_BLOCK, smem, st>>>(p, rays, producers);
 }
 
 size_t traverse_ring_bytes(int rays) { return (size_t)rays * RLERC_RING_DEPTH * RLERC_RING_SLOT * sizeof(float4); }
 
 void launch_traverse_warp(const TraverseParams& p, bool ids, cudaStream_t st)
 {
-	const bool pc = p.dda_ring != nullptr;
-	if (ids) { if (pc) launch_w<true, true>(p, st); else launch_w<true, false>(p, st); }
-	else     { if (pc) launch_w<false, true>(p, st); else launch_w<false, false>(p, st); }
+	const int mode = p.dda_ring != nullptr ? 1 : (p.dda_mode == 0 ? 0 : 2);
+	if (ids)
+	{
+		if (mode == 1) launch_w<true, 1>(p, st); else if (mode == 0) launch_w<true, 0>(p, st); else launch_w<true, 2>(p, st);
+	}
+	else
+	{
+		if (mode == 1) launch_w<false, 1>(p, st); else if (mode == 0) launch_w<false, 0>(p, st); else launch_w<false, 2>(p, st);
+	}
 }
 
 } // namespace rlerc

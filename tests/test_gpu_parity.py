@@ -55,6 +55,32 @@ def test_warp_buffer_bit_exact_camera_grid(R, rb, gpu, scene_mid, lanes):
     gpu.set_lanes_per_ray(0)
 
 
+@pytest.mark.parametrize("variant", ["serial", "merge", "producer"])
+def test_dda_variants_bit_exact(R, rb, gpu, scene_mid, variant):
+    """k_traverse_w can advance the DDA three ways (serial recurrence in every warp, merge path over the two
+    tracks, dedicated producer blocks + ring in global memory): same warped buffer, bit for bit."""
+    gpu.all_to_gpu(scene_mid)
+    gpu.set_lanes_per_ray(0)
+    gpu.set_dda_mode(2 if variant == "merge" else 0)
+    gpu.set_dda_producer(variant == "producer")
+    try:
+        for wh in ((640, 480), (1920, 1080)):
+            cfg = R.FrameConfig.default(*wh)
+            cams = list(camera_grid(-100.0))[::2] if wh[0] == 640 else few_cameras(-100.0)
+            # a camera exactly on a lattice point looking along a grid axis: NaN/inf tracks (merge path falls back)
+            cams = cams + [((10000.0, -100.0, 10000.0), (0.3, math.pi / 2, 0.0)), ((10000.0, -100.0, 10000.0), (0.3, 0.0, 0.0))]
+            for pos, rot in cams:
+                rm = R.RayMap(cfg).get_ray_map(pos, rot)
+                _, want, _, _ = _oracle(rb, rm, scene_mid, cfg)
+                _fresh_warp(gpu, cfg)
+                gpu.render(rm, cfg)
+                got = gpu.read_warp(cfg)
+                assert np.array_equal(got, want), (variant, wh, rot, int((got != want).sum()))
+    finally:
+        gpu.set_dda_mode(0)
+        gpu.set_dda_producer(False)
+
+
 @pytest.mark.parametrize("lanes", [0, 32])
 def test_warp_buffer_bit_exact_short_run_scene(R, rb, gpu, scene_runs, lanes):
     """Columns with dozens of runs: the lane<->run path."""

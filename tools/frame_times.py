@@ -12,6 +12,7 @@ W, H = bench.WORKLOADS[workload][3]
 cfg = R.FrameConfig.default(W, H)
 r = R.Renderer(0); r.all_to_gpu(scene); r.set_timing(True); r.set_lanes_per_ray(lanes)
 if len(sys.argv) > 4: r.set_dda_producer(int(sys.argv[4]))
+if len(sys.argv) > 5: r.set_dda_mode(int(sys.argv[5]))
 ids = torch.empty((cfg.rays_casted, cfg.render_size, 2), dtype=torch.int32, device="cuda")
 names = ["elems_total", "elems_processed", "voxels_processed", "elems_rendered", "pixels", "cols_fetched", "run_iters", "cols_nonempty", "cleared", "dda_steps"]
 for t in range(0, 1000, stride):
