@@ -584,6 +584,18 @@ k_traverse_w(const __grid_constant__ TraverseParams P, int rays, int producer_bl
 		unsigned flags = 0;               // bit r: run r can be seen (z1 > 0); bit 8+r: its bottom too (z2 > 0)
 		if (s0.have)
 		{
+			{	// run words as loaded in C1 -> runs 0..7, two per register (run 0 rides in the map entry)
+				const unsigned first = s0.e1 >> 16;
+				const unsigned a = s0.rw[0], b = s0.rw[1], c = s0.rw[2], d = s0.rw[3];
+				if (!((2u + s0.e0) & 1u)) s0.rw[0] = first | (a & 0xffff0000u);
+				else
+				{
+					s0.rw[0] = first | (a << 16);
+					s0.rw[1] = __funnelshift_r(a, b, 16);
+					s0.rw[2] = __funnelshift_r(b, c, 16);
+					s0.rw[3] = __funnelshift_r(c, d, 16);
+				}
+			}
 			slen = (int)(s0.e1 & 0xffffu);
 			nr = slen < RLERC_RW ? slen : RLERC_RW;
 			longcol = slen > RLERC_RW;
@@ -735,26 +747,15 @@ k_traverse_w(const __grid_constant__ TraverseParams P, int rays, int producer_bl
 			const unsigned i0 = 2u + s1.e0;
 			const uint32_t* w32 = reinterpret_cast<const uint32_t*>(P.level[geo[slot1 * 192 + 128 + gl]].slabs);
 			const unsigned first = s1.e1 >> 16;
-			if (!(i0 & 1u))
-			{
-				const uint32_t* p = w32 + (i0 >> 1);
-				s1.rw[0] = first | ((sl > 1) ? (__ldg(p) & 0xffff0000u) : 0u);
-				s1.rw[1] = (sl > 2) ? __ldg(p + 1) : 0u;
-				s1.rw[2] = (sl > 4) ? __ldg(p + 2) : 0u;
-				s1.rw[3] = (sl > 6) ? __ldg(p + 3) : 0u;
-			}
-			else
-			{
-				const uint32_t* p = w32 + ((i0 + 1) >> 1);              // words hold runs (1,2) (3,4) (5,6) (7,8)
-				const unsigned a = (sl > 1) ? __ldg(p) : 0u;
-				const unsigned b = (sl > 3) ? __ldg(p + 1) : 0u;
-				const unsigned c = (sl > 5) ? __ldg(p + 2) : 0u;
-				const unsigned d = (sl > 7) ? __ldg(p + 3) : 0u;
-				s1.rw[0] = first | (a << 16);
-				s1.rw[1] = __funnelshift_r(a, b, 16);
-				s1.rw[2] = __funnelshift_r(b, c, 16);
-				s1.rw[3] = __funnelshift_r(c, d, 16);
-			}
+			// only ISSUE the loads here (raw words); they are shifted into place in C2, one iteration later,
+			// so that nothing in this iteration waits for them
+			const uint32_t* p = w32 + ((i0 + (i0 & 1u)) >> 1);
+			const int odd = (int)(i0 & 1u);                            // odd: words hold runs (1,2) (3,4) (5,6) (7,8)
+			s1.rw[0] = (sl > 1) ? __ldg(p) : 0u;
+			s1.rw[1] = (sl > 2 + odd) ? __ldg(p + 1) : 0u;
+			s1.rw[2] = (sl > 4 + odd) ? __ldg(p + 2) : 0u;
+			s1.rw[3] = (sl > 6 + odd) ? __ldg(p + 3) : 0u;
+			(void)first;
 		}
 
 		// ---- B. consume batch s0: only columns that draw under the current bounds change anything ---
@@ -1013,20 +1014,38 @@ k_traverse_w(const __grid_constant__ TraverseParams P, int rays, int producer_bl
 				float uz = u1z + u2dz * mult;
 				float onez = onez1 + onedz2 * mult;
 				const int tex_hi = texn - 1;
-				for (int k = 0; k < n; ++k, ++y, uz += u2dz, onez += onedz2, clear >>= 1)   // Cuda_Render.h:687-733
+				// Cuda_Render.h:687-733, four pixels at a time: all attribute gathers of a group are in flight
+				// before the first store needs one
+				for (int k0 = 0; k0 < n; k0 += 4)
 				{
-					if (!(clear & 1u)) continue;
-					int ui = f2i(uz / onez);
-					ui = (ui > texture) ? ui : texture;
-					ui = (ui < tex_hi) ? ui : tex_hi;
-					const unsigned real_z = (unsigned)f2i(1.0f / onez) & 0xfffeu;
-					row[y] = (unsigned)__ldg(send + ui) + (real_z << 16);
-					if (IDS)
+					unsigned colr[4], zz[4];
+					#pragma unroll
+					for (int k = 0; k < 4; k++)
 					{
-						c_pix++;
-						R.ids[y * 2] = (uint32_t)g0.cidx;
-						R.ids[y * 2 + 1] = ((uint32_t)g0.cmip << 16) | (uint32_t)ui;
+						colr[k] = 0; zz[k] = 0;
+						if (k0 + k < n)
+						{
+							if ((clear >> k) & 1u)
+							{
+								int ui = f2i(uz / onez);
+								ui = (ui > texture) ? ui : texture;
+								ui = (ui < tex_hi) ? ui : tex_hi;
+								zz[k] = (unsigned)f2i(1.0f / onez) & 0xfffeu;
+								colr[k] = __ldg(send + ui);
+								if (IDS)
+								{
+									c_pix++;
+									R.ids[(y + k) * 2] = (uint32_t)g0.cidx;
+									R.ids[(y + k) * 2 + 1] = ((uint32_t)g0.cmip << 16) | (uint32_t)ui;
+								}
+							}
+							uz += u2dz; onez += onedz2;
+						}
 					}
+					#pragma unroll
+					for (int k = 0; k < 4; k++)
+						if (k0 + k < n && ((clear >> k) & 1u)) row[y + k] = colr[k] + (zz[k] << 16);
+					y += 4; clear >>= 4;
 				}
 			}
 		}
