@@ -132,6 +132,8 @@ def lib():
     """Load librlerc.so (built in-tree by ``__graft_entry__.build()``). Fails loudly."""
     global _lib
     if _lib is None:
+        # RLERC_LIBRARY: an alternative build of the same library (kernel tuning experiments, tools/)
+        LIB_PATH = os.environ.get("RLERC_LIBRARY") or globals()["LIB_PATH"]
         if not os.path.exists(LIB_PATH):
             raise RlercError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                              "(there is no CPU fallback)" % LIB_PATH)

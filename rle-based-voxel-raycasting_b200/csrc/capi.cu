@@ -30,6 +30,8 @@ struct FrameSlot {            // one in-flight frame of the pipelined path
 	uint8_t* d_rgba = nullptr;
 	size_t warp_bytes = 0, rgba_bytes = 0;
 	cudaEvent_t done = nullptr;
+	cudaStream_t stream = nullptr;   // each in-flight frame renders on its own stream: the tail of one
+	                                 // frame's traversal (a few long ray planes) overlaps the next frame
 	uint8_t* host_dst = nullptr;
 	bool busy = false;
 };
@@ -219,6 +221,7 @@ void rlerc_destroy(rlerc_ctx* c)
 		if (c->slot[i].d_warp) cudaFree(c->slot[i].d_warp);
 		if (c->slot[i].d_rgba) cudaFree(c->slot[i].d_rgba);
 		if (c->slot[i].done) cudaEventDestroy(c->slot[i].done);
+		if (c->slot[i].stream) cudaStreamDestroy(c->slot[i].stream);
 	}
 	for (int i = 0; i < 4; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
 	if (c->stream && c->own_stream) cudaStreamDestroy(c->stream);
@@ -312,7 +315,7 @@ int rlerc_set_dda_producer(rlerc_ctx* c, int on)
 
 int rlerc_set_dda_mode(rlerc_ctx* c, int mode)
 {
-	if (!c || (mode != 0 && mode != 2)) { set_error("dda mode must be 0 (serial) or 2 (merge path)"); return RLERC_ERR_ARG; }
+	if (!c || (mode != 0 && mode != 2 && mode != 3)) { set_error("dda mode must be 0 (serial), 2 (merge path) or 3 (closed form)"); return RLERC_ERR_ARG; }
 	c->dda_mode = mode;
 	return RLERC_OK;
 }
@@ -539,10 +542,20 @@ int rlerc_frame_submit(rlerc_ctx* c, const float pos[3], const float rot[3], con
 	rlerc_raymap rm;
 	memset(&rm, 0, sizeof(rm));
 	if ((rc = rlerc_frame_setup(pos, rot, cfg, &rm))) return rc;
-	if ((rc = render_impl(c, &rm, cfg, 0, -1, s.d_warp, nullptr, false))) return rc;
-	if ((rc = unwarp_impl(c, &rm, cfg, s.d_warp, s.d_rgba, 0, -1, 0, -1))) return rc;
+	// a caller-provided stream (rlerc_set_stream) is respected; otherwise every slot has its own
+	cudaStream_t const main_stream = c->stream;
+	if (c->own_stream)
+	{
+		if (!s.stream) CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+		c->stream = s.stream;
+	}
+	cudaStream_t const fs = c->stream;
+	rc = render_impl(c, &rm, cfg, 0, -1, s.d_warp, nullptr, false);
+	if (!rc) rc = unwarp_impl(c, &rm, cfg, s.d_warp, s.d_rgba, 0, -1, 0, -1);
+	c->stream = main_stream;
+	if (rc) return rc;
 	// hand the finished frame to the copy stream so the next frame's traversal overlaps the D2H
-	CK(cudaEventRecord(s.done, c->stream));
+	CK(cudaEventRecord(s.done, fs));
 	CK(cudaStreamWaitEvent(c->copy_stream, s.done, 0));
 	CK(cudaMemcpyAsync(host_rgba, s.d_rgba, (size_t)cfg->width * cfg->height * 4, cudaMemcpyDeviceToHost, c->copy_stream));
 	CK(cudaEventRecord(s.done, c->copy_stream));

@@ -37,12 +37,6 @@
 
 namespace rlerc {
 
-// out-of-line copy for the rare NaN fallback of the merge-path build
-__device__ __noinline__ int dda_serial_batch(DdaState& S, float4* rec, int last_map, int zfar_i)
-{
-	return dda_serial_batch_inl(S, rec, last_map, zfar_i);
-}
-
 // Merge-path batch.  The two tracks of the DDA (x-crossings and z-crossings) are independent recurrences
 // state += gradient; the serial loop only MERGES them (fire the z-track when d1 < d0, else the x-track).
 // So: lanes 0-15 generate the next 33 states of the x-track, lanes 16-31 those of the z-track (33 x 3 adds in
@@ -202,9 +196,12 @@ __device__ __noinline__ void dda_producer(const TraverseParams& P, int rays)
 	}
 }
 
-// MODE: how the DDA advances — 0 serial in every warp (default), 1 producer blocks + ring, 2 merge path
+// MODE: how the DDA advances — 0 serial in every warp, 1 producer blocks + ring, 2 merge path, 3 closed form (lane-parallel)
+#ifndef RLERC_MIN_CTAS
+#define RLERC_MIN_CTAS 4
+#endif
 template <bool IDS, int MODE>
-__global__ void __launch_bounds__(RLERC_BLOCK, 4)
+__global__ void __launch_bounds__(RLERC_BLOCK, RLERC_MIN_CTAS)
 k_traverse_w(const __grid_constant__ TraverseParams P, int rays, int producer_blocks)
 {
 	extern __shared__ __align__(16) uint32_t smem[];
@@ -272,7 +269,20 @@ k_traverse_w(const __grid_constant__ TraverseParams P, int rays, int producer_bl
 	for (float yms = mountain; yms > 512.0f; yms = yms * 0.5f) dda_lod_switch(S, last_map);
 	// merge path needs sorted tracks: a NaN distance (ray exactly along a grid axis through a lattice point)
 	// falls back to the serial recurrence
-	const bool merge_ok = (MODE == 2) && !(S.d0 != S.d0) && !(S.d1 != S.d1) && !(S.gd0 != S.gd0) && !(S.gd1 != S.gd1);
+	const bool sorted_tracks = !(S.d0 != S.d0) && !(S.d1 != S.d1) && !(S.gd0 != S.gd0) && !(S.gd1 != S.gd1);
+	const bool merge_ok = (MODE == 2) && sorted_tracks;
+	// closed-form DDA (MODE 3): lanes 0..5 own one variable each, the rest of the state is uniform
+	const bool closed_ok = (MODE == 3) && sorted_tracks;
+	DdaVar var;
+	var.b = var.gb = var.F = var.D = var.L = 0;
+	DdaUni U;
+	U.mip = S.mip; U.zi = S.zi; U.dzi = S.dzi; U.mapswitch = S.mapswitch; U.csd = 0.0f; U.cpx = 0.0f; U.cpy = 0.0f;
+	if (MODE == 3 && gl < 6)
+	{
+		const float v = gl == 0 ? S.d0 : gl == 1 ? S.i0x : gl == 2 ? S.i0y : gl == 3 ? S.d1 : gl == 4 ? S.i1x : S.i1y;
+		const float g = gl == 0 ? S.gd0 : gl == 1 ? S.g0x : gl == 2 ? S.g0y : gl == 3 ? S.gd1 : gl == 4 ? S.g1x : S.g1y;
+		dda_var_init(var, v, g);
+	}
 
 	// per-lane statistics (IDS build only)
 	Counters Cn;
@@ -402,6 +412,12 @@ k_traverse_w(const __grid_constant__ TraverseParams P, int rays, int producer_bl
 				if (gl == 0 && consumed > 0) st_volatile(P.dda_tail + ray_i, consumed);
 				consumed++;
 			}
+			else if (MODE == 3)
+			{
+				bool ended = false;
+				nvalid = dda_closed_batch(var, U, reinterpret_cast<int*>(wbase + 136), rec, last_map, zfar_i, gl, closed_ok, pra, prb, ended);
+				if (ended) dda_done = true;
+			}
 			else if (merge_ok)
 			{
 				bool ended = false;
@@ -530,14 +546,14 @@ size_t traverse_ring_bytes(int rays) { return (size_t)rays * RLERC_RING_DEPTH * 
 
 void launch_traverse_warp(const TraverseParams& p, bool ids, cudaStream_t st)
 {
-	const int mode = p.dda_ring != nullptr ? 1 : (p.dda_mode == 0 ? 0 : 2);
+	const int mode = p.dda_ring != nullptr ? 1 : (p.dda_mode == 0 ? 0 : (p.dda_mode == 2 ? 2 : 3));
 	if (ids)
 	{
-		if (mode == 1) launch_w<true, 1>(p, st); else if (mode == 0) launch_w<true, 0>(p, st); else launch_w<true, 2>(p, st);
+		if (mode == 1) launch_w<true, 1>(p, st); else if (mode == 0) launch_w<true, 0>(p, st); else if (mode == 2) launch_w<true, 2>(p, st); else launch_w<true, 3>(p, st);
 	}
 	else
 	{
-		if (mode == 1) launch_w<false, 1>(p, st); else if (mode == 0) launch_w<false, 0>(p, st); else launch_w<false, 2>(p, st);
+		if (mode == 1) launch_w<false, 1>(p, st); else if (mode == 0) launch_w<false, 0>(p, st); else if (mode == 2) launch_w<false, 2>(p, st); else launch_w<false, 3>(p, st);
 	}
 }
 

@@ -1,0 +1,34 @@
+"""The closed form of the DDA recurrences (csrc/dda_closed.cuh, evaluated lane-parallel by k_traverse_w) is
+bit-identical to the serial recurrence of the reference (R/src/Cuda_Render.h:286-300,343-367,398-414): CPU
+harness tests/dda_closed_harness.cpp compiled with the same no-contraction flags as the oracle."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "tests", "dda_closed_harness.cpp")
+INC = os.path.join(ROOT, "rle-based-voxel-raycasting_b200", "csrc")
+
+
+@pytest.fixture(scope="module")
+def harness(tmp_path_factory):
+    exe = str(tmp_path_factory.mktemp("dda") / "dda_closed_harness")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fno-fast-math", "-x", "c++", "-I", INC, SRC, "-o", exe],
+                   check=True)
+    return exe
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_single_variable_recurrence(harness, seed):
+    r = subprocess.run([harness, "var", "4000", str(seed)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_two_track_dda_batches(harness, seed):
+    r = subprocess.run([harness, "dda", "400", str(seed)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout
+    checked, closed, fallback = (int(v) for v in r.stdout.split()[1:4])
+    assert checked > 1_000_000
+    assert fallback < 0.05 * closed      # the serial fallback is for the first crossings and NaN rays only

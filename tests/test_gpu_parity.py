@@ -55,13 +55,14 @@ def test_warp_buffer_bit_exact_camera_grid(R, rb, gpu, scene_mid, lanes):
     gpu.set_lanes_per_ray(0)
 
 
-@pytest.mark.parametrize("variant", ["serial", "merge", "producer"])
+@pytest.mark.parametrize("variant", ["closed", "serial", "merge", "producer"])
 def test_dda_variants_bit_exact(R, rb, gpu, scene_mid, variant):
-    """k_traverse_w can advance the DDA three ways (serial recurrence in every warp, merge path over the two
-    tracks, dedicated producer blocks + ring in global memory): same warped buffer, bit for bit."""
+    """k_traverse_w can advance the DDA four ways (closed form evaluated lane-parallel, serial recurrence in
+    every warp, merge path over the two tracks, dedicated producer blocks + ring in global memory): same warped
+    buffer, bit for bit."""
     gpu.all_to_gpu(scene_mid)
     gpu.set_lanes_per_ray(0)
-    gpu.set_dda_mode(2 if variant == "merge" else 0)
+    gpu.set_dda_mode({"merge": 2, "closed": 3}.get(variant, 0))
     gpu.set_dda_producer(variant == "producer")
     try:
         for wh in ((640, 480), (1920, 1080)):
@@ -69,6 +70,8 @@ def test_dda_variants_bit_exact(R, rb, gpu, scene_mid, variant):
             cams = list(camera_grid(-100.0))[::2] if wh[0] == 640 else few_cameras(-100.0)
             # a camera exactly on a lattice point looking along a grid axis: NaN/inf tracks (merge path falls back)
             cams = cams + [((10000.0, -100.0, 10000.0), (0.3, math.pi / 2, 0.0)), ((10000.0, -100.0, 10000.0), (0.3, 0.0, 0.0))]
+            # negative coordinates: the first intersections have the opposite sign of their gradients
+            cams = cams + [((-3000.25, -100.0, -70.5), (0.3, 0.7, 0.0)), ((-0.5, -60.0, 2000.75), (0.5, 3.9, 0.0))]
             for pos, rot in cams:
                 rm = R.RayMap(cfg).get_ray_map(pos, rot)
                 _, want, _, _ = _oracle(rb, rm, scene_mid, cfg)

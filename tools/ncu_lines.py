@@ -70,7 +70,7 @@ def main():
             srcs[f] = open(pth).read().splitlines() if os.path.exists(pth) else []
         return srcs[f][n - 1].strip() if 0 < n <= len(srcs[f]) else "?"
     print("total warp instructions %d, samples %d" % (tot, ts))
-    for key, a in sorted(per.items(), key=lambda kv: -kv[1][0])[:topn]:
+    for key, a in sorted(per.items(), key=lambda kv: -kv[1][1 if os.environ.get("BY_SAMPLES") else 0])[:topn]:
         loc = "%s:%d" % (key[0][:14], key[1]) if key else "?"
         print("%5.1f%% inst %5.1f%% stall  %-20s (%3d sass) %s" % (100.0 * a[0] / tot, 100.0 * a[1] / ts, loc, a[2], text_of(key)[:95]))
 
