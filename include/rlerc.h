@@ -123,11 +123,14 @@ void rlerc_destroy(rlerc_ctx* c);
 int  rlerc_scene_upload(rlerc_ctx* c, const rlerc_scene* s);
 /* Device-side Map4 table as main.cpp:277-278 copies it into the ray map (all levels). */
 int  rlerc_scene_device_maps(rlerc_ctx* c, rlerc_map4* out16, int* nummaps);
-/* Traversal kernel variant: lanes cooperating on one ray plane (1,2,4,8,16,32; 0 = auto). */
+/* Traversal kernel variant, all bit-identical: 0 = production kernel k_traverse_f (one warp per ray plane, column
+ * filter in front of the occlusion machinery); 64 = k_traverse_w (one warp per ray plane, three-stage pipeline
+ * over all columns); 1,2,4,8,16,32 = k_traverse<lanes> (lane <-> run; 1 is the reference's thread-per-ray scheme). */
 int  rlerc_set_lanes_per_ray(rlerc_ctx* c, int lanes);
-/* k_traverse_w only: run the DDA in dedicated producer blocks (default on) or inside every warp. */
+/* k_traverse_w only: run the DDA in dedicated producer blocks or inside every warp (default). */
 int  rlerc_set_dda_producer(rlerc_ctx* c, int on);
-/* k_traverse_w only: 0 = serial DDA recurrence in every warp (default), 2 = merge-path DDA. Same results. */
+/* k_traverse_w only: 0 = serial DDA recurrence in every warp (default), 2 = merge-path DDA, 3 = closed-form
+ * lane-parallel DDA (csrc/dda_closed.cuh). Same results. */
 int  rlerc_set_dda_mode(rlerc_ctx* c, int mode);
 
 /* ---- frame setup: replaces RayMap::set_border/set_ray_limit/get_ray_map ------------ */

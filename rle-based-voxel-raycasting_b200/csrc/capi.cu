@@ -178,7 +178,7 @@ int fill_unwarp(const rlerc_raymap* rm, const rlerc_frame_config* cfg, const uin
 int pick_lanes(const rlerc_ctx* c, int rays)
 {
 	(void)rays;
-	return c->lanes;   // 0 = warp-per-ray, lane<->column kernel (k_traverse_w)
+	return c->lanes;   // 0 = k_traverse_f (filter + warp per ray plane), 64 = k_traverse_w, else k_traverse<lanes>
 }
 
 } // namespace
@@ -297,9 +297,9 @@ int rlerc_scene_device_maps(rlerc_ctx* c, rlerc_map4* out16, int* nummaps)
 
 int rlerc_set_lanes_per_ray(rlerc_ctx* c, int lanes)
 {
-	if (!c || !(lanes == 0 || lanes == 1 || lanes == 2 || lanes == 4 || lanes == 8 || lanes == 16 || lanes == 32))
+	if (!c || !(lanes == 0 || lanes == 1 || lanes == 2 || lanes == 4 || lanes == 8 || lanes == 16 || lanes == 32 || lanes == 64))
 	{
-		set_error("lanes per ray must be 0,1,2,4,8,16 or 32");
+		set_error("lanes per ray must be 0,1,2,4,8,16,32 or 64");
 		return RLERC_ERR_ARG;
 	}
 	c->lanes = lanes;
@@ -341,7 +341,7 @@ int rlerc_warp_buffer(rlerc_ctx* c, const rlerc_frame_config* cfg, uint32_t** d_
 
 static int render_impl(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_config* cfg,
                        int ray_begin, int ray_end, uint32_t* d_warp, uint32_t* d_ids, bool ids,
-                       int slice_block = 1, int slice_n = 1, int slice_rank = 0)
+                       int slice_block = 1, int slice_n = 1, int slice_rank = 0, uint32_t* prof_out = nullptr)
 {
 	if (!c || !rm) { set_error("rlerc_render: null argument"); return RLERC_ERR_ARG; }
 	int rc = check_cfg(cfg);
@@ -364,7 +364,8 @@ static int render_impl(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_c
 		CK(cudaMemsetAsync(c->d_counters, 0, 32 * sizeof(unsigned long long), c->stream));
 	}
 	P.dda_mode = c->dda_mode;
-	if (c->lanes == 0 && c->producer)
+	if (prof_out) P.ids = prof_out;
+	if (c->lanes == 64 && c->producer)
 	{
 		const int cap = cfg->rays_casted;
 		if ((rc = ensure((void**)&c->d_ring, &c->ring_bytes, traverse_ring_bytes(cap)))) return rc;
@@ -399,6 +400,17 @@ int rlerc_render_counters(rlerc_ctx* c, uint64_t out[10])
 	CK(cudaMemcpy(h, c->d_counters, sizeof(h), cudaMemcpyDeviceToHost));
 	for (int i = 0; i < 10; i++) out[i] = h[i];
 	return RLERC_OK;
+}
+
+/* undocumented (tools/ray_profile.py): k_traverse_f with clock64() phase timers; d_out = unsigned long long[rays_casted][8] */
+int rlerc_debug_profile_rays(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_config* cfg, void* d_out)
+{
+	if (!c || !d_out) return RLERC_ERR_ARG;
+	const int saved_mode = c->dda_mode, saved_lanes = c->lanes;
+	c->dda_mode = 99; c->lanes = 0;
+	const int rc = render_impl(c, rm, cfg, 0, -1, nullptr, nullptr, false, 1, 1, 0, (uint32_t*)d_out);
+	c->dda_mode = saved_mode; c->lanes = saved_lanes;
+	return rc;
 }
 
 /* undocumented: raw copy of all 32 debug counter slots (tools/ only) */

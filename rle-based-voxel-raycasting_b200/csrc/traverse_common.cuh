@@ -41,6 +41,15 @@ __device__ __forceinline__ unsigned run_word(const unsigned (&rw)[4], int r)
 	return (w >> ((r & 1) * 16)) & 0xffffu;
 }
 
+// bits [lo, hi) of one 32-bit word, lo / hi clamped to the word (empty when hi <= 0 or lo >= 32 or hi <= lo)
+__device__ __forceinline__ unsigned bit_range(int lo, int hi)
+{
+	lo = lo < 0 ? 0 : lo;
+	hi = hi > 32 ? 32 : hi;
+	if (hi <= lo) return 0u;
+	return (hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
+}
+
 // Everything the span shader needs that is per ray plane (kept in one place so that the rarely
 // taken paths can live in non-inlined functions and stay out of the instruction cache)
 struct RayCtx {
@@ -108,6 +117,53 @@ __device__ __noinline__ int coop_span(const RayCtx& R, const uint16_t* send, flo
 		__syncwarp();
 	}
 	return written;
+}
+
+// The same span shader for the ownership-resolved path (B1 in consume_batch): pixel y of [y, s2) is written iff its
+// bit is set in the claim words cw (bit (y - wbase) of a 128-bit window); the occlusion mask is neither read nor
+// written here.  All arguments warp-uniform.
+static __device__ __noinline__ void coop_span_claim(const RayCtx& R, const uint16_t* send, float cpz, float cpy,
+                                             int y, int s2, int rtop, int rbot, int rtex, int rtexn,
+                                             unsigned c0w, unsigned c1w, unsigned c2w, unsigned c3w, int wbase)
+{
+	const int gl = R.gl;
+	const float ft = (float)rtop, fb2 = (float)rbot;
+	const float z1r = cpz + R.pz_add * ft, y1r = cpy + R.py_add * ft;
+	const float z2r = cpz + R.pz_add * fb2, y2r = cpy + R.py_add * fb2;
+	const float s2r = R.res_y2 + y1r / z1r;
+	const float s1r = R.res_y2 + y2r / z2r;
+	const float u1z = (float)rtexn / z2r;
+	float u2dz = (float)rtex / z1r - u1z;
+	const float onez1 = 1.0f / z2r;
+	float onedz2 = 1.0f / z1r - onez1;
+	u2dz /= s2r - s1r;
+	onedz2 /= s2r - s1r;
+	const float mult = (float)(y + 1) - s1r;
+	float uz = u1z + u2dz * mult;
+	float onez = onez1 + onedz2 * mult;
+	const int tex_hi = rtexn - 1;                      // int(float(tex-1.0))
+	const int n = s2 - y;
+	for (int c0 = 0; c0 < n; c0 += 32)
+	{
+		const int steps = (n - c0 < 32) ? (n - c0) : 32;
+		float muz = uz, monez = onez;
+		for (int t = 0; t < steps; t++)
+		{
+			if (gl == t) { muz = uz; monez = onez; }
+			uz += u2dz; onez += onedz2;
+		}
+		const int yy = y + c0 + gl;
+		const int b = yy - wbase;                        // 0 <= b < 128 for every claimed pixel
+		const unsigned w = (b < 64) ? ((b < 32) ? c0w : c1w) : ((b < 96) ? c2w : c3w);
+		if (gl < steps && b >= 0 && b < 128 && ((w >> (b & 31)) & 1u))
+		{
+			int ui = f2i(muz / monez);
+			ui = (ui > rtex) ? ui : rtex;
+			ui = (ui < tex_hi) ? ui : tex_hi;
+			const unsigned real_z = (unsigned)f2i(1.0f / monez) & 0xfffeu;
+			R.row[yy] = (unsigned)__ldg(send + ui) + (real_z << 16);
+		}
+	}
 }
 
 // A column with more than RW undecided runs: lane <-> run, 32 runs at a time (the scheme of
@@ -276,7 +332,7 @@ __device__ __forceinline__ int dda_serial_batch_inl(DdaState& S, float4* rec, in
 
 
 // Out-of-line serial batch (rare paths of the closed-form and merge-path builds)
-__device__ __noinline__ int dda_serial_batch(DdaState& S, float4* rec, int last_map, int zfar_i)
+static __device__ __noinline__ int dda_serial_batch(DdaState& S, float4* rec, int last_map, int zfar_i)
 {
 	return dda_serial_batch_inl(S, rec, last_map, zfar_i);
 }
@@ -291,7 +347,7 @@ struct DdaUni { int mip, zi, dzi, mapswitch; float csd, cpx, cpy; };   // csd: s
 
 // Serial fallback of the closed-form build: first crossings of a ray plane (a variable doubles more than once per
 // batch), NaN rays.  Rebuilds the uniform float state from the owner lanes, runs the serial batch, hands it back.
-__device__ __noinline__ int dda_closed_fallback(DdaVar& var, DdaUni& U, float4* rec, int last_map, int zfar_i, int gl)
+static __device__ __noinline__ int dda_closed_fallback(DdaVar& var, DdaUni& U, float4* rec, int last_map, int zfar_i, int gl)
 {
 	const unsigned FULL = 0xffffffffu;
 	DdaState T;
@@ -520,6 +576,150 @@ __device__ __forceinline__ bool consume_batch(const TraverseParams& P, const Ray
 			hiw = hiw > yend ? hiw : yend;
 			todo = 0;
 			__syncwarp();
+		}
+	}
+
+	// ---- B1. ownership-resolved path (production build) ----------------------------------------------------
+	// Every draw is first-come on the occlusion mask, and the reference's break / skip tests only ever discard
+	// spans that lie entirely inside already covered rows.  So for REGULAR columns (sy2 non-increasing over the
+	// visible runs) and as long as y_clip_max does not move, the outcome of the 32 columns is: row y goes to the
+	// first span (column order, then run order) that covers it, y_clip_min is the first open row.  Each lane
+	// builds the row set of its spans inside a 128-row window above y_clip_min, an exclusive prefix OR over the
+	// lanes gives the rows covered before each column (hence the horizon it meets, for the exact top-clip test
+	// of Cuda_Render.h:467) and its own rows.  One failed precondition sends the batch through the event loop.
+	if (!IDS && todo)
+	{
+		const int y0 = ycmin;
+		const int w0 = y0 >> 5, wbase = w0 << 5, wend = wbase + 128;
+		const bool mine = (todo >> gl) & 1u;
+		const bool pass0 = mine && s0.have && !(g0.pz * res_y2 + g0.py <= g0.pz * (float)y0);
+		bool ok = true;
+		if (mine && s0.have && !pass0 && !(g0.pz > 0)) ok = false;               // culled now, may pass later
+		unsigned rg0 = 0, rg1 = 0, rg2 = 0, rg3 = 0;
+		if (pass0)
+		{
+			if (longcol) ok = false;
+			int prev2 = INT_MAX;
+			for (int r = 0; r < nr; r++)
+			{
+				if (!((flags >> r) & 1u)) continue;
+				const int2 sy = proj[r * 32 + gl];
+				if (sy.y > prev2) ok = false;                                     // irregular column
+				prev2 = sy.y;
+				if (sy.y <= y0) break;                                            // Cuda_Render.h:543, now and later
+				if (!((flags >> (8 + r)) & 1u) || sy.x >= ycmax) continue;        // Cuda_Render.h:556,560
+				if (sy.y >= ycmax || sy.y > wend) { ok = false; break; }          // y_clip_max would move / window too small
+				const int lo = (sy.x > y0 ? sy.x : y0) - wbase, hi = sy.y - wbase; // 0 <= lo < hi <= 128
+				rg0 |= bit_range(lo, hi); rg1 |= bit_range(lo - 32, hi - 32);
+				rg2 |= bit_range(lo - 64, hi - 64); rg3 |= bit_range(lo - 96, hi - 96);
+			}
+		}
+		if (__all_sync(FULL, ok))
+		{
+			// rows covered before my column: mask as it is, rows below y_clip_min, spans of the lanes before me
+			unsigned i0 = rg0, i1 = rg1, i2 = rg2, i3 = rg3;
+			#pragma unroll
+			for (int d = 1; d < 32; d <<= 1)
+			{
+				const unsigned t0 = __shfl_up_sync(FULL, i0, d), t1 = __shfl_up_sync(FULL, i1, d);
+				const unsigned t2 = __shfl_up_sync(FULL, i2, d), t3 = __shfl_up_sync(FULL, i3, d);
+				if (gl >= d) { i0 |= t0; i1 |= t1; i2 |= t2; i3 |= t3; }
+			}
+			unsigned c0 = __shfl_up_sync(FULL, i0, 1), c1 = __shfl_up_sync(FULL, i1, 1);
+			unsigned c2 = __shfl_up_sync(FULL, i2, 1), c3 = __shfl_up_sync(FULL, i3, 1);
+			if (gl == 0) { c0 = 0; c1 = 0; c2 = 0; c3 = 0; }
+			const int mw = P.mask_words;
+			c0 |= ymask[w0] | ((1u << (y0 & 31)) - 1u);
+			c1 |= (w0 + 1 < mw) ? ymask[w0 + 1] : 0xffffffffu;
+			c2 |= (w0 + 2 < mw) ? ymask[w0 + 2] : 0xffffffffu;
+			c3 |= (w0 + 3 < mw) ? ymask[w0 + 3] : 0xffffffffu;
+			unsigned m0 = rg0 & ~c0, m1 = rg1 & ~c1, m2 = rg2 & ~c2, m3 = rg3 & ~c3;   // my rows
+			if (m0 | m1 | m2 | m3)
+			{
+				// the horizon this column meets = first open row before it
+				const int yc = wbase + (~c0 ? __ffs(~c0) - 1 : (~c1 ? 31 + __ffs(~c1) : (~c2 ? 63 + __ffs(~c2) : 95 + __ffs(~c3))));
+				if (g0.pz * res_y2 + g0.py <= g0.pz * (float)yc) ok = false;      // Cuda_Render.h:467 under the exact horizon
+			}
+			// split my rows among my runs (run order), note short spans for S and at most one long span
+			int long_r = -1, long_y = 0, long_e = 0;
+			unsigned my_shade = 0;
+			if (ok && (m0 | m1 | m2 | m3))
+			{
+				unsigned q0 = m0, q1 = m1, q2 = m2, q3 = m3;
+				for (int r = 0; r < nr; r++)
+				{
+					if (!((flags >> r) & 1u)) continue;
+					const int2 sy = proj[r * 32 + gl];
+					if (sy.y <= y0) break;
+					if (!((flags >> (8 + r)) & 1u) || sy.x >= ycmax) continue;
+					const int lo = (sy.x > y0 ? sy.x : y0) - wbase, hi = sy.y - wbase;
+					const unsigned a0 = q0 & bit_range(lo, hi), a1 = q1 & bit_range(lo - 32, hi - 32);
+					const unsigned a2 = q2 & bit_range(lo - 64, hi - 64), a3 = q3 & bit_range(lo - 96, hi - 96);
+					if (!(a0 | a1 | a2 | a3)) continue;
+					q0 &= ~a0; q1 &= ~a1; q2 &= ~a2; q3 &= ~a3;
+					const int first = a0 ? __ffs(a0) - 1 : (a1 ? 31 + __ffs(a1) : (a2 ? 63 + __ffs(a2) : 95 + __ffs(a3)));
+					const int last = a3 ? 127 - __clz(a3) : (a2 ? 95 - __clz(a2) : (a1 ? 63 - __clz(a1) : 31 - __clz(a0)));
+					const int n = last - first + 1;
+					if (n <= 12)
+					{
+						// the 12 rows from `first` on, as a bit field
+						const int k = first >> 5, sh = first & 31;
+						const unsigned lo_w = k == 0 ? a0 : (k == 1 ? a1 : (k == 2 ? a2 : a3));
+						const unsigned hi_w = k == 0 ? a1 : (k == 1 ? a2 : (k == 2 ? a3 : 0u));
+						const unsigned bits = (sh ? ((lo_w >> sh) | (hi_w << (32 - sh))) : lo_w) & 0xfffu;
+						shade[r * 32 + gl] = (unsigned)(wbase + first) | ((unsigned)n << 16) | (bits << 20);   // scratch until shade_runs says so
+						my_shade |= 1u << r;
+					}
+					else if (long_r < 0) { long_r = r; long_y = wbase + first; long_e = wbase + last + 1; }
+					else ok = false;                                               // two long spans in one column: rare
+				}
+			}
+			if (__all_sync(FULL, ok))
+			{
+				// ---- commit: nothing was modified before this point ----
+				const unsigned t0 = __shfl_sync(FULL, i0, 31), t1 = __shfl_sync(FULL, i1, 31);
+				const unsigned t2 = __shfl_sync(FULL, i2, 31), t3 = __shfl_sync(FULL, i3, 31);
+				shade_runs |= my_shade;
+				// long spans: whole warp, in any order (the rows are already assigned)
+				unsigned lb = __ballot_sync(FULL, long_r >= 0);
+				while (lb)
+				{
+					const int L = __ffs(lb) - 1;
+					lb &= lb - 1;
+					if (gl == L)
+					{
+						int blen = 0, btex = 0, top = 0, bot = 0, texture = 0, texn = 0;
+						for (int r = 0; r <= long_r; r++)
+						{
+							const unsigned rw = run_word(s0.rw, r);
+							const int skip = (int)(rw & 1023u), solid = (int)(rw >> 10);
+							top = (blen + skip) << g0.cmip; bot = top + (solid << g0.cmip);
+							texture = btex; texn = btex + solid;
+							blen += skip + solid; btex += solid;
+						}
+						job->cpz = g0.pz; job->cpy = g0.py;
+						job->y = long_y; job->s2 = long_e; job->rtop = top; job->rbot = bot;
+						job->rtex = texture; job->rtexn = texn;
+						job->m = g0.cmip; job->colid = g0.cidx; job->e0 = s0.e0; job->slen = (unsigned)slen;
+					}
+					__syncwarp();
+					const DrawJob J = *job;
+					coop_span_claim(R, P.level[J.m].slabs + 2 + (size_t)J.e0 + J.slen, J.cpz, J.cpy, J.y, J.s2, J.rtop, J.rbot, J.rtex, J.rtexn,
+					                __shfl_sync(FULL, m0, L), __shfl_sync(FULL, m1, L), __shfl_sync(FULL, m2, L), __shfl_sync(FULL, m3, L), wbase);
+					__syncwarp();
+				}
+				// occlusion mask, horizon
+				if (gl < 4 && w0 + gl < mw)
+				{
+					const unsigned t = gl == 0 ? t0 : (gl == 1 ? t1 : (gl == 2 ? t2 : t3));
+					if (t) ymask[w0 + gl] |= t;
+				}
+				__syncwarp();
+				const int top_row = (t3 ? 128 - __clz(t3) : (t2 ? 96 - __clz(t2) : (t1 ? 64 - __clz(t1) : (t0 ? 32 - __clz(t0) : 0))));
+				if (t0 | t1 | t2 | t3) { const int h = wbase + top_row; hiw = hiw > h ? hiw : h; }
+				ycmin = first_clear(ymask, y0, ycmax);                              // Cuda_Render.h:573-577
+				todo = 0;
+			}
 		}
 	}
 

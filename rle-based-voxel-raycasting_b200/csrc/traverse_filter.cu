@@ -1,0 +1,448 @@
+// k_traverse_f — the production traversal kernel: one WARP per ray plane, a column FILTER in front of the
+// occlusion machinery.  Replaces cudaRender + Render::render_line (R/src/Cuda_Main.cu:150-181,
+// R/src/Cuda_Render.h:96-737) and gives the same warped ray buffer bit for bit (arithmetic contract: DESIGN.md §3).
+//
+// Measured on B200 (tools/chain_probe.py): a frame's traversal time is the serial chain of its longest ray planes
+// (the ones that see sky and walk all ~7000 cell crossings to z_far), not throughput; and on those ray planes
+// > 90 % of the visited columns are no-ops: their first visible run already projects at or below the floating
+// horizon y_clip_min, so the reference breaks out of the run loop without touching any state
+// (Cuda_Render.h:542-543).  That test needs nothing but the 8-byte pointer-map entry (the first run rides in it)
+// and it is monotone: the horizon only rises, so a column that is dead under today's horizon is dead under
+// every later one.  Hence two loops instead of one pipeline over all columns:
+//
+//   FILTER   per 32 crossings: DDA (uniform serial recurrence) -> per lane column address, projected cell,
+//            conservative top-clip test (Cuda_Render.h:467), pointer-map gather (consumed one step later, the
+//            DDA of the next step hides its latency) -> first-run test -> the LIVE columns are compacted
+//            (ballot + popc) into a small queue in shared memory, in crossing order.
+//   CONSUME  per 32 LIVE columns: run-word loads (issued one round early), projection of up to RW runs,
+//            then consume_batch (traverse_common.cuh): rising-horizon prefix-max fast path, owner-lane event
+//            loop, cooperative long spans, deferred parallel shading — unchanged exact semantics, it re-tests
+//            every column under the exact state.
+//
+// The filter only ever removes columns that are provable no-ops, so the result does not depend on how far it
+// runs ahead.  The instrumented build (IDS) passes every column that survives the top-clip test, because the
+// work counters of the byte model count the no-op columns too.
+#include <stdint.h>
+#include <limits.h>
+#include "kernels.cuh"
+#include "device_common.cuh"
+#include "traverse_common.cuh"
+
+namespace rlerc {
+
+#define RLERC_QCAP 64                       // queue capacity in columns (ring, power of two): < 32 left + <= 32 new
+#define RLERC_F_REC 136                     // words: 33 crossing records (float4), padded
+#define RLERC_F_QUEUE (8 * RLERC_QCAP)      // words: 8 fields x QCAP, field-major
+
+// The DDA state as two register quads, one per track, laid out like the crossing record a lane consumes:
+// {distance, pos.x, pos.y, mip}.  The z-track keeps its distance NEGATED (the record marks the track that fired
+// by the sign of its distance, and -(a + b) == (-a) + (-b) exactly), so a crossing is: compare, store the quad of
+// the track that fires, three adds.
+struct DdaQ {
+	float d0, x0, y0;        // x-track: dds_dist0, isect0           (Cuda_Render.h:286-300)
+	float nd1, x1, y1;       // z-track: -dds_dist1, isect1
+	float gd0, gx0, gy0;     // grad_dist0, grad0
+	float ngd1, gx1, gy1;    // -grad_dist1, grad1
+	int mip, zi, dzi, mapswitch;   // z and dz are integer valued
+};
+
+__device__ __forceinline__ void ddaq_lod_switch(DdaQ& Q, int last_map)          // Cuda_Render.h:343-365
+{
+	if (Q.mip < last_map) Q.mip++;
+	Q.gx0 *= 2; Q.gy0 *= 2; Q.gx1 *= 2; Q.gy1 *= 2;
+	Q.gd0 *= 2; Q.ngd1 *= 2;
+	Q.mapswitch *= 2;
+	Q.dzi *= 2;
+}
+
+// Up to 32 crossings, all lanes in lockstep: rec[s+1] = record of crossing s; rec[0] = the last record of the
+// previous batch (rec[prev_n], or zeros before the first).  LOD / z_far budgets by shifts (dz is a power of two).
+// Returns the number of crossings made (< 32 only when z_far was reached, Cuda_Render.h:366-367).
+__device__ __forceinline__ int ddaq_batch(DdaQ& Q, float4* rec, int prev_n, int last_map, int zfar_i)
+{
+	int nvalid = 32;
+	{
+		const float4 carry = rec[prev_n];
+		__syncwarp();
+		rec[0] = make_float4(carry.x, carry.y, carry.z, 0.0f);
+	}
+	for (int s = 0; s < 32;)
+	{
+		while (Q.zi > Q.mapswitch) ddaq_lod_switch(Q, last_map);
+		const int sh = 31 - __clz(Q.dzi);
+		const int lod_free = ((Q.mapswitch - Q.zi) >> sh) + 1;        // crossings before z > mapswitch
+		const int far_free = (zfar_i - Q.zi) >> sh;                   // crossings with z + dz <= z_far (<= 0: none)
+		if (far_free <= 0) { nvalid = s; break; }
+		int n = 32 - s;
+		n = n < lod_free ? n : lod_free;
+		n = n < far_free ? n : far_free;
+		const float mipf = __int_as_float(Q.mip);
+		float4* out = rec + s + 1;
+		#pragma unroll 4
+		for (int j = 0; j < n; j++)
+		{
+			if (-Q.nd1 < Q.d0)                                        // Cuda_Render.h:398-414
+			{
+				out[j] = make_float4(Q.nd1, Q.x1, Q.y1, mipf);
+				Q.nd1 += Q.ngd1; Q.x1 += Q.gx1; Q.y1 += Q.gy1;
+			}
+			else
+			{
+				out[j] = make_float4(Q.d0, Q.x0, Q.y0, mipf);
+				Q.d0 += Q.gd0; Q.x0 += Q.gx0; Q.y0 += Q.gy0;
+			}
+		}
+		Q.zi += n << sh;
+		s += n;
+	}
+	return nvalid;
+}
+
+// PROF (tools/ray_profile.py only): per ray plane, clock64() cycles spent in each phase, written as
+// unsigned long long[8] {total, dda, filter test + queue, geometry + gather, C1, C2, consume, steps | batches << 32}
+// to the buffer passed in P.ids.
+#define RLERC_TICK(slot) do { if (PROF) { const long long now_ = clock64(); prof[slot] += now_ - tick; tick = now_; } } while (0)
+
+template <bool IDS, bool PROF>
+__global__ void __launch_bounds__(RLERC_BLOCK, 4)
+k_traverse_f(const __grid_constant__ TraverseParams P, int rays)
+{
+	long long prof[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+	long long tick = PROF ? clock64() : 0;
+	const long long t_begin = tick;
+	extern __shared__ __align__(16) uint32_t smem[];
+	constexpr int G = 32;
+	constexpr int WPB = RLERC_BLOCK / 32;
+	const int gl = threadIdx.x & 31;
+	const int wid = threadIdx.x >> 5;
+	const unsigned FULL = 0xffffffffu;
+	const unsigned lt_mask = (1u << gl) - 1u;
+
+	const int ray_i = (int)blockIdx.x * WPB + wid;                  // launch-local ray index
+	const int x = owned_ray(P, ray_i);
+	if (ray_i >= rays || x >= P.ray_end) return;
+
+	// shared per warp: crossing records | live-column queue | DrawJob | RW x 32 projected runs (int2) |
+	//                  RW x 32 deferred short spans | occlusion bits
+	const int per_warp = (RLERC_F_REC + RLERC_F_QUEUE + 16 + RLERC_RW * 96 + P.mask_words + 3) & ~3;
+	uint32_t* wbase = smem + (size_t)wid * per_warp;
+	float4* rec = reinterpret_cast<float4*>(wbase);
+	uint32_t* queue = wbase + RLERC_F_REC;                           // [8][QCAP]
+	DrawJob* job = reinterpret_cast<DrawJob*>(wbase + RLERC_F_REC + RLERC_F_QUEUE);
+	int2* proj = reinterpret_cast<int2*>(wbase + RLERC_F_REC + RLERC_F_QUEUE + 16);
+	uint32_t* shade = wbase + RLERC_F_REC + RLERC_F_QUEUE + 16 + RLERC_RW * 64;
+	uint32_t* ymask = wbase + RLERC_F_REC + RLERC_F_QUEUE + 16 + RLERC_RW * 96;
+
+	const int res_y = P.res_y;
+	const float res_y2 = (float)(res_y / 2);             // Cuda_Render.h:108 (integer division)
+	uint32_t* row = P.warp + (size_t)x * res_y;
+
+	RayInit ri;
+	ray_init(P, x, ri);
+	clear_outside<G>(row, res_y, ri, gl);
+	if (ri.skip) return;
+	const float ray_x = ri.ray_x, ray_z = ri.ray_z, rx2mr = ri.rx2mr;
+	const bool vertical = ri.vertical;
+	const float sin_x = P.sin_x, cos_x = P.cos_x;
+	HorizonState Hs;
+	Hs.ycmin = ri.ycmin; Hs.ycmax = ri.ycmax; Hs.hiw = 0;
+	const int ymin0 = Hs.ycmin, ymax0 = Hs.ycmax;
+
+	// occlusion mask clear; the sky sentinel is written at the end to the pixels that stayed
+	// open (same final row as clear-then-overwrite, Cuda_Render.h:255-264)
+	for (int w = gl; w < P.mask_words; w += G) ymask[w] = 0;
+	__syncwarp();
+
+	const float vpx = P.viewpos[0], mountain = P.viewpos[1], vpz = P.viewpos[2];
+	int fixx, fixz;
+	DdaQ Q;
+	{
+		Dda dd;
+		dda_init(P, ray_x, ray_z, dd);
+		fixx = dd.fixx; fixz = dd.fixz;
+		Q.d0 = dd.d0; Q.x0 = dd.i0x; Q.y0 = dd.i0y; Q.nd1 = -dd.d1; Q.x1 = dd.i1x; Q.y1 = dd.i1y;
+		Q.gd0 = dd.gd0; Q.gx0 = dd.g0x; Q.gy0 = dd.g0y; Q.ngd1 = -dd.gd1; Q.gx1 = dd.g1x; Q.gy1 = dd.g1y;
+	}
+	Q.mip = 0;
+	Q.zi = 0; Q.dzi = 1;                                         // z and dz (Cuda_Render.h:181,325), integer valued
+	Q.mapswitch = P.mapswitch0;
+	if (gl == 0) rec[0] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);   // no crossing yet: distance 0, x-track (Cuda_Render.h:302-305)
+	int prev_n = 0;
+	__syncwarp();
+	const float pz_add = sin_x;                                  // pos3d_z_add (Cuda_Render.h:313)
+	const float py_add = (vertical ? cos_x : 0.0f) * rx2mr;      // pos3d_y_add (Cuda_Render.h:314-315)
+	const int zfar_i = P.z_far;
+	const int last_map = P.nummaps - 1;
+	// The y_map_switch half of the LOD loop condition (Cuda_Render.h:343) can only be true on
+	// the first crossing (it halves until <= 512 and never grows), where z = 0 < mapswitch.
+	for (float yms = mountain; yms > 512.0f; yms = yms * 0.5f) ddaq_lod_switch(Q, last_map);
+
+	Counters Cn;
+	memset(&Cn, 0, sizeof(Cn));
+
+	RayCtx R;
+	R.row = row; R.ymask = ymask; R.ids = (IDS && !PROF) ? P.ids + (size_t)x * res_y * 2 : nullptr;
+	R.res_y2 = res_y2; R.pz_add = pz_add; R.py_add = py_add; R.mountain = mountain; R.gl = gl;
+
+	// filter: the batch whose pointer-map gather is in flight
+	Geo fg;
+	fg.pz = fg.py = fg.czz = fg.cyy = 0; fg.cmip = 0; fg.cidx = 0;
+	unsigned fe0 = 0, fe1 = 0;
+	bool fhave = false;
+	int fn = 0;                        // crossings in that batch (0: none in flight)
+	bool dda_done = false;
+	int qhead = 0, qcount = 0;         // live-column queue (uniform)
+	// consume: the batch whose run words are in flight
+	Stage s0;
+	Geo g0 = fg;
+	s0.nvalid = 0; s0.have = false; s0.e0 = s0.e1 = 0;
+	#pragma unroll
+	for (int k = 0; k < 4; k++) s0.rw[k] = 0;
+
+	while (true)
+	{
+		if (Hs.ycmin >= Hs.ycmax) break;                         // Cuda_Render.h:370
+
+		// ---- FILTER: until a full batch of live columns is queued (or the ray plane has reached z_far) -------------
+		while (qcount < 32 && (!dda_done || fn > 0))
+		{
+			// F1. DDA for the next 32 crossings; the gather of the batch in flight lands meanwhile
+			int nvalid = 0;
+			RLERC_TICK(0);
+			if (PROF) prof[7] += 1;
+			if (!dda_done)
+			{
+				nvalid = ddaq_batch(Q, rec, prev_n, last_map, zfar_i);
+				prev_n = nvalid;
+				if (nvalid < G) dda_done = true;
+				if (IDS && gl == 0) Cn.c_steps += nvalid;
+			}
+			__syncwarp();
+			RLERC_TICK(1);
+			// F2. first-run test of the batch in flight, live columns -> queue
+			if (fn > 0)
+			{
+				const int ycmin = Hs.ycmin;
+				bool live = false;
+				if (gl < fn && fhave)
+				{
+					const int slen = (int)(fe1 & 0xffffu);
+					const unsigned first = fe1 >> 16;
+					const int solid = (int)(first >> 10), skip = (int)(first & 1023u);
+					if (IDS) live = true;                                // the byte model counts no-op columns too
+					else if (slen == 0) live = false;                    // empty column: the run loop does not execute
+					else if (solid == 0) live = true;                    // pure skip run: undecided, let the machinery look
+					else
+					{
+						const float ft = (float)(skip << fg.cmip);         // Cuda_Render.h:529-543 for run 0
+						float zz1 = fg.pz, yy1 = fg.py;
+						if (mountain + ft >= 0) { zz1 += fg.czz; yy1 += fg.cyy; }
+						const float z1 = zz1 + pz_add * ft;
+						if (z1 <= 0) live = true;                          // `continue`: a later run may be the first visible one
+						else
+						{
+							const float y1 = yy1 + py_add * ft;
+							live = f2i(res_y2 + y1 / z1) > ycmin;          // else: break, now and under every later horizon
+						}
+					}
+				}
+				const unsigned lb = __ballot_sync(FULL, live);
+				if (live)
+				{
+					uint32_t* q = queue + ((qhead + qcount + __popc(lb & lt_mask)) & (RLERC_QCAP - 1));
+					q[0 * RLERC_QCAP] = __float_as_uint(fg.pz); q[1 * RLERC_QCAP] = __float_as_uint(fg.py);
+					q[2 * RLERC_QCAP] = __float_as_uint(fg.czz); q[3 * RLERC_QCAP] = __float_as_uint(fg.cyy);
+					q[4 * RLERC_QCAP] = (uint32_t)fg.cmip; q[5 * RLERC_QCAP] = (uint32_t)fg.cidx;
+					q[6 * RLERC_QCAP] = fe0; q[7 * RLERC_QCAP] = fe1;
+				}
+				qcount += __popc(lb);
+			}
+			RLERC_TICK(2);
+			// F3. geometry of the new crossings, conservative top clip, pointer-map gather (into the registers F2 freed)
+			fn = nvalid;
+			fhave = false;
+			if (gl < nvalid)
+			{
+				const float4 ra = rec[gl], rb = rec[gl + 1];           // state before / after crossing gl
+				const float db = fabsf(ra.x), dn = fabsf(rb.x);
+				const int ib = __float_as_int(ra.x) < 0 ? 1 : 0;        // index_before: sign bit of the record
+				fg.cmip = __float_as_int(rb.w);
+				const int fix_x = (1 - ib) * fixx, fix_z = ib * fixz;    // Cuda_Render.h:418-419
+				const float ddelta = dn - db;
+				const float vsx = ray_x * db, vsz = ray_z * db;
+				const int voxel_x = f2i(vpx + ra.y) + fix_x;             // Cuda_Render.h:429-430
+				const int voxel_z = f2i(vpz + ra.z) + fix_z;
+				const int gx = P.level[fg.cmip].sx, gz = P.level[fg.cmip].sz;
+				const int vx = (voxel_x >> fg.cmip) & (gx - 1);          // Cuda_Render.h:441-442
+				const int vz = (voxel_z >> fg.cmip) & (gz - 1);
+				fg.cidx = vx + vz * gx;
+				const float corx = ray_x * ddelta, corz = ray_z * ddelta;
+				fg.pz = cos_x * vsz + sin_x * mountain;                  // Cuda_Render.h:459-464
+				fg.py = vertical ? (cos_x * mountain - sin_x * vsz) : vsx;
+				fg.py *= rx2mr;
+				fg.czz = cos_x * corz;                                   // Cuda_Render.h:483-486
+				fg.cyy = vertical ? (-sin_x * corz) : corx;
+				fg.cyy *= rx2mr;
+				// The horizon only rises.  For pz > 0 a column culled now stays culled; for pz <= 0 (or NaN)
+				// the test can flip, so keep those.
+				fhave = !(fg.pz * res_y2 + fg.py <= fg.pz * (float)Hs.ycmin) || !(fg.pz > 0);   // Cuda_Render.h:467
+				if (fhave)
+				{
+					const uint2 ent = __ldg(P.level[fg.cmip].map + fg.cidx);         // Cuda_Render.h:474-478
+					fe0 = ent.x; fe1 = ent.y;
+				}
+			}
+			__syncwarp();
+			RLERC_TICK(3);
+		}
+		RLERC_TICK(0);
+
+		// ---- C1. take the next batch of live columns off the queue, request their run words ---------------------
+		Stage s1;
+		Geo g1;
+		{
+			const int n1 = qcount < 32 ? qcount : 32;
+			s1.nvalid = n1; s1.have = gl < n1;
+			s1.e0 = s1.e1 = 0;
+			#pragma unroll
+			for (int k = 0; k < 4; k++) s1.rw[k] = 0;
+			g1.pz = g1.py = g1.czz = g1.cyy = 0; g1.cmip = 0; g1.cidx = 0;
+			if (s1.have)
+			{
+				const uint32_t* q = queue + ((qhead + gl) & (RLERC_QCAP - 1));
+				g1.pz = __uint_as_float(q[0 * RLERC_QCAP]); g1.py = __uint_as_float(q[1 * RLERC_QCAP]);
+				g1.czz = __uint_as_float(q[2 * RLERC_QCAP]); g1.cyy = __uint_as_float(q[3 * RLERC_QCAP]);
+				g1.cmip = (int)q[4 * RLERC_QCAP]; g1.cidx = (int)q[5 * RLERC_QCAP];
+				s1.e0 = q[6 * RLERC_QCAP]; s1.e1 = q[7 * RLERC_QCAP];
+				const int sl = (int)(s1.e1 & 0xffffu);
+				// element i0 of the slab stream is run 0; runs 0..7 are fetched as aligned 32-bit words
+				const unsigned i0 = 2u + s1.e0;
+				const uint32_t* w32 = reinterpret_cast<const uint32_t*>(P.level[g1.cmip].slabs);
+				const uint32_t* p = w32 + ((i0 + (i0 & 1u)) >> 1);
+				const int odd = (int)(i0 & 1u);                            // odd: words hold runs (1,2) (3,4) (5,6) (7,8)
+				s1.rw[0] = (sl > 1) ? __ldg(p) : 0u;
+				s1.rw[1] = (sl > 2 + odd) ? __ldg(p + 1) : 0u;
+				s1.rw[2] = (sl > 4 + odd) ? __ldg(p + 2) : 0u;
+				s1.rw[3] = (sl > 6 + odd) ? __ldg(p + 3) : 0u;
+			}
+			qhead = (qhead + n1) & (RLERC_QCAP - 1);
+			qcount -= n1;
+		}
+		__syncwarp();
+		RLERC_TICK(4);
+
+		// ---- C2. project the runs of batch s0 (their words were requested one round ago) -------------------------
+		if (s0.nvalid > 0)
+		{
+			const int ycmin = Hs.ycmin;
+			int slen = 0, nr = 0;
+			bool longcol = false;
+			unsigned flags = 0;               // bit r: run r can be seen (z1 > 0); bit 8+r: its bottom too (z2 > 0)
+			if (s0.have)
+			{
+				{	// run words as loaded in C1 -> runs 0..7, two per register (run 0 rides in the map entry)
+					const unsigned first = s0.e1 >> 16;
+					const unsigned a = s0.rw[0], b = s0.rw[1], c = s0.rw[2], d = s0.rw[3];
+					if (!((2u + s0.e0) & 1u)) s0.rw[0] = first | (a & 0xffff0000u);
+					else
+					{
+						s0.rw[0] = first | (a << 16);
+						s0.rw[1] = __funnelshift_r(a, b, 16);
+						s0.rw[2] = __funnelshift_r(b, c, 16);
+						s0.rw[3] = __funnelshift_r(c, d, 16);
+					}
+				}
+				slen = (int)(s0.e1 & 0xffffu);
+				nr = slen < RLERC_RW ? slen : RLERC_RW;
+				longcol = slen > RLERC_RW;
+				int blen = 0;
+				for (int r = 0; r < nr; r++)
+				{
+					const unsigned rw = run_word(s0.rw, r);
+					const int skip = (int)(rw & 1023u), solid = (int)(rw >> 10);
+					const int top = (blen + skip) << g0.cmip;                // sti_general_sti_skip
+					const int bot = top + (solid << g0.cmip);                // sti_general
+					blen += skip + solid;
+					if (solid == 0) continue;
+					const float ft = (float)top, fb = (float)bot;           // Cuda_Render.h:529-560
+					float zz1 = g0.pz, yy1 = g0.py;
+					if (mountain + ft >= 0) { zz1 += g0.czz; yy1 += g0.cyy; }
+					const float z1 = zz1 + pz_add * ft;
+					if (z1 <= 0) continue;
+					flags |= 1u << r;
+					const float y1 = yy1 + py_add * ft;
+					const int sy2 = f2i(res_y2 + y1 / z1);
+					int sy1 = 0;
+					if (sy2 > ycmin)
+					{
+						float zz2 = g0.pz, yy2 = g0.py;
+						if (mountain + fb < 0) { zz2 += g0.czz; yy2 += g0.cyy; }
+						const float z2 = zz2 + pz_add * fb;
+						if (!(z2 <= 0))
+						{
+							flags |= 1u << (8 + r);
+							const float y2 = yy2 + py_add * fb;
+							sy1 = f2i(res_y2 + y2 / z2 - 1);
+						}
+					}
+					proj[r * 32 + gl] = make_int2(sy1, sy2);
+					if (sy2 <= ycmin)
+					{
+						// breaks now, hence under every later (higher) horizon: later runs are dead
+						nr = r + 1; longcol = false;
+						break;
+					}
+				}
+			}
+
+			RLERC_TICK(5);
+			if (PROF) prof[7] += 1ll << 32;
+			// ---- B / B0 / S. consume batch s0 (traverse_common.cuh) ----------------------------------------------
+			const bool finished = consume_batch<IDS>(P, R, Hs, Cn, s0, g0, slen, nr, longcol, flags, proj, shade, job);
+			RLERC_TICK(6);
+			if (finished) break;
+		}
+		else if (s1.nvalid == 0 && dda_done && fn == 0 && qcount == 0) break;   // drained (z > z_far, Cuda_Render.h:367)
+
+		s0 = s1; g0 = g1;
+	}
+	__syncwarp();
+
+	// sky sentinel on every pixel of the clip range that no run covered
+	for (int y = ymin0 + gl; y <= ymax0; y += G)
+		if (!((ymask[y >> 5] >> (y & 31)) & 1u)) row[y] = RLERC_SKY;
+
+	if (IDS) flush_counters(P, Cn, gl, ymax0 - ymin0 + 1);
+	if (PROF && gl == 0)
+	{
+		prof[0] = clock64() - t_begin;
+		unsigned long long* out = reinterpret_cast<unsigned long long*>(P.ids) + (size_t)x * 8;
+		for (int k = 0; k < 8; k++) out[k] = (unsigned long long)prof[k];
+	}
+}
+
+template <bool IDS, bool PROF>
+static void launch_f(const TraverseParams& p, cudaStream_t st)
+{
+	const int wpb = RLERC_BLOCK / 32;
+	const int rays = (p.slice_n > 1) ? owned_count(p.ray_end, p.slice_block, p.slice_n, p.slice_rank) : p.ray_end - p.ray_begin;
+	if (rays <= 0) return;
+	const int blocks = (rays + wpb - 1) / wpb;
+	const size_t smem = (size_t)wpb * ((RLERC_F_REC + RLERC_F_QUEUE + 16 + RLERC_RW * 96 + p.mask_words + 3) & ~3) * sizeof(uint32_t);
+	static size_t configured = 0;
+	if (smem > configured)
+	{
+		cudaFuncSetAttribute(k_traverse_f<IDS, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		configured = smem;
+	}
+	k_traverse_f<IDS, PROF><<<blocks, RLERC_BLOCK, smem, st>>>(p, rays);
+}
+
+void launch_traverse_filter(const TraverseParams& p, bool ids, cudaStream_t st)
+{
+	if (p.dda_mode == 99) launch_f<false, true>(p, st);          // tools/ray_profile.py
+	else if (ids) launch_f<true, false>(p, st);
+	else launch_f<false, false>(p, st);
+}
+
+} // namespace rlerc

@@ -37,13 +37,13 @@ def _oracle(rb, rm, scene, cfg, ids=False):
     return orm, warp, oid, cnt
 
 
-@pytest.mark.parametrize("lanes", [0, 32, 8, 1])
+@pytest.mark.parametrize("lanes", [0, 64, 32, 8, 1])
 def test_warp_buffer_bit_exact_camera_grid(R, rb, gpu, scene_mid, lanes):
     gpu.all_to_gpu(scene_mid)
     gpu.set_lanes_per_ray(lanes)
     cfg = R.FrameConfig.default(640, 480)
     cams = list(camera_grid(-100.0))
-    if lanes not in (0, 32):
+    if lanes not in (0, 64, 32):
         cams = cams[::3]
     for pos, rot in cams:
         rm = R.RayMap(cfg).get_ray_map(pos, rot)
@@ -61,7 +61,7 @@ def test_dda_variants_bit_exact(R, rb, gpu, scene_mid, variant):
     every warp, merge path over the two tracks, dedicated producer blocks + ring in global memory): same warped
     buffer, bit for bit."""
     gpu.all_to_gpu(scene_mid)
-    gpu.set_lanes_per_ray(0)
+    gpu.set_lanes_per_ray(64)
     gpu.set_dda_mode({"merge": 2, "closed": 3}.get(variant, 0))
     gpu.set_dda_producer(variant == "producer")
     try:
@@ -80,6 +80,7 @@ def test_dda_variants_bit_exact(R, rb, gpu, scene_mid, variant):
                 got = gpu.read_warp(cfg)
                 assert np.array_equal(got, want), (variant, wh, rot, int((got != want).sum()))
     finally:
+        gpu.set_lanes_per_ray(0)
         gpu.set_dda_mode(0)
         gpu.set_dda_producer(False)
 
