@@ -58,6 +58,7 @@ struct RayCtx {
 	uint32_t* ids;           // IDS build: id words of this ray plane's row, else null
 	float res_y2, pz_add, py_add, mountain;
 	int gl;
+	long long* stat;         // STATS build: [0] batches [1] B0 taken [2] B1 taken [3] event-loop iterations [4..11] B1 fail reasons
 };
 
 // A pixel span [y, s2) of one run, shaded by the whole warp 32 pixels at a time, stores coalesced
@@ -462,7 +463,7 @@ struct Counters {                                  // instrumented build: per-la
 };
 
 // Returns true when the ray plane is finished (y_clip_min >= y_clip_max, Cuda_Render.h:370).
-template <bool IDS>
+template <bool IDS, bool STATS = false>
 __device__ __forceinline__ bool consume_batch(const TraverseParams& P, const RayCtx& R, HorizonState& H, Counters& C,
                                               const Stage& s0, const Geo& g0, int slen, int nr, bool longcol, unsigned flags,
                                               const int2* proj, uint32_t* shade, DrawJob* job)
@@ -491,6 +492,7 @@ __device__ __forceinline__ bool consume_batch(const TraverseParams& P, const Ray
 	// is of that kind under ANY horizon it can meet in this batch; one failed proof sends the
 	// whole batch through the general event loop below.
 	if (IDS && gl == 0 && todo) dbg[0]++;
+	if (STATS && todo) R.stat[0]++;
 	if (todo && hiw <= ycmin)
 	{
 		if (IDS && gl == 0) dbg[1]++;
@@ -545,6 +547,7 @@ __device__ __forceinline__ bool consume_batch(const TraverseParams& P, const Ray
 		if (__all_sync(FULL, ok))
 		{
 			if (IDS && gl == 0) dbg[2]++;
+			if (STATS) R.stat[1]++;
 			int yend = __shfl_sync(FULL, inc, 31);
 			yend = yend > y0 ? yend : y0;
 			if (draws)
@@ -594,21 +597,22 @@ __device__ __forceinline__ bool consume_batch(const TraverseParams& P, const Ray
 		const bool mine = (todo >> gl) & 1u;
 		const bool pass0 = mine && s0.have && !(g0.pz * res_y2 + g0.py <= g0.pz * (float)y0);
 		bool ok = true;
-		if (mine && s0.have && !pass0 && !(g0.pz > 0)) ok = false;               // culled now, may pass later
+		unsigned why = 0;
+		if (mine && s0.have && !pass0 && !(g0.pz > 0)) { ok = false; why |= 1; }  // culled now, may pass later
 		unsigned rg0 = 0, rg1 = 0, rg2 = 0, rg3 = 0;
 		if (pass0)
 		{
-			if (longcol) ok = false;
+			if (longcol) { ok = false; why |= 2; }
 			int prev2 = INT_MAX;
 			for (int r = 0; r < nr; r++)
 			{
 				if (!((flags >> r) & 1u)) continue;
 				const int2 sy = proj[r * 32 + gl];
-				if (sy.y > prev2) ok = false;                                     // irregular column
+				if (sy.y > prev2) { ok = false; why |= 4; }                       // irregular column
 				prev2 = sy.y;
 				if (sy.y <= y0) break;                                            // Cuda_Render.h:543, now and later
 				if (!((flags >> (8 + r)) & 1u) || sy.x >= ycmax) continue;        // Cuda_Render.h:556,560
-				if (sy.y >= ycmax || sy.y > wend) { ok = false; break; }          // y_clip_max would move / window too small
+				if (sy.y >= ycmax || sy.y > wend) { ok = false; why |= (sy.y >= ycmax) ? 8 : 16; break; }   // y_clip_max would move / window too small
 				const int lo = (sy.x > y0 ? sy.x : y0) - wbase, hi = sy.y - wbase; // 0 <= lo < hi <= 128
 				rg0 |= bit_range(lo, hi); rg1 |= bit_range(lo - 32, hi - 32);
 				rg2 |= bit_range(lo - 64, hi - 64); rg3 |= bit_range(lo - 96, hi - 96);
@@ -638,7 +642,7 @@ __device__ __forceinline__ bool consume_batch(const TraverseParams& P, const Ray
 			{
 				// the horizon this column meets = first open row before it
 				const int yc = wbase + (~c0 ? __ffs(~c0) - 1 : (~c1 ? 31 + __ffs(~c1) : (~c2 ? 63 + __ffs(~c2) : 95 + __ffs(~c3))));
-				if (g0.pz * res_y2 + g0.py <= g0.pz * (float)yc) ok = false;      // Cuda_Render.h:467 under the exact horizon
+				if (g0.pz * res_y2 + g0.py <= g0.pz * (float)yc) { ok = false; why |= 32; }   // Cuda_Render.h:467 under the exact horizon
 			}
 			// split my rows among my runs (run order), note short spans for S and at most one long span
 			int long_r = -1, long_y = 0, long_e = 0;
@@ -671,7 +675,7 @@ __device__ __forceinline__ bool consume_batch(const TraverseParams& P, const Ray
 						my_shade |= 1u << r;
 					}
 					else if (long_r < 0) { long_r = r; long_y = wbase + first; long_e = wbase + last + 1; }
-					else ok = false;                                               // two long spans in one column: rare
+					else { ok = false; why |= 64; }                                // two long spans in one column: rare
 				}
 			}
 			if (__all_sync(FULL, ok))
@@ -719,12 +723,19 @@ __device__ __forceinline__ bool consume_batch(const TraverseParams& P, const Ray
 				if (t0 | t1 | t2 | t3) { const int h = wbase + top_row; hiw = hiw > h ? hiw : h; }
 				ycmin = first_clear(ymask, y0, ycmax);                              // Cuda_Render.h:573-577
 				todo = 0;
+				if (STATS) R.stat[2]++;
 			}
+		}
+		if (STATS && todo)
+		{
+			const unsigned allwhy = __reduce_or_sync(FULL, why);
+			for (int k = 0; k < 7; k++) if ((allwhy >> k) & 1u) R.stat[4 + k]++;
 		}
 	}
 
 	while (todo)
 	{
+		if (STATS) R.stat[3]++;
 		if (ycmin >= ycmax) { finished = true; break; }
 		const bool mine = (todo >> gl) & 1u;
 		const bool pass = mine && s0.have && !(g0.pz * res_y2 + g0.py <= g0.pz * (float)ycmin);   // Cuda_Render.h:467

@@ -55,16 +55,17 @@ __device__ __forceinline__ void ddaq_lod_switch(DdaQ& Q, int last_map)          
 	Q.dzi *= 2;
 }
 
-// Up to 32 crossings, all lanes in lockstep: rec[s+1] = record of crossing s; rec[0] = the last record of the
+// Up to 32 crossings, all lanes in lockstep (one lane writes: 32 lanes storing the same 16 bytes cost four
+// shared-memory passes per crossing, which made the DDA store-bound); rec[s+1] = record of crossing s; rec[0] = the last record of the
 // previous batch (rec[prev_n], or zeros before the first).  LOD / z_far budgets by shifts (dz is a power of two).
 // Returns the number of crossings made (< 32 only when z_far was reached, Cuda_Render.h:366-367).
-__device__ __forceinline__ int ddaq_batch(DdaQ& Q, float4* rec, int prev_n, int last_map, int zfar_i)
+__device__ __forceinline__ int ddaq_batch(DdaQ& Q, float4* rec, int prev_n, int last_map, int zfar_i, bool writer)
 {
 	int nvalid = 32;
 	{
 		const float4 carry = rec[prev_n];
 		__syncwarp();
-		rec[0] = make_float4(carry.x, carry.y, carry.z, 0.0f);
+		if (writer) rec[0] = make_float4(carry.x, carry.y, carry.z, 0.0f);
 	}
 	for (int s = 0; s < 32;)
 	{
@@ -81,16 +82,11 @@ __device__ __forceinline__ int ddaq_batch(DdaQ& Q, float4* rec, int prev_n, int 
 		#pragma unroll 4
 		for (int j = 0; j < n; j++)
 		{
-			if (-Q.nd1 < Q.d0)                                        // Cuda_Render.h:398-414
-			{
-				out[j] = make_float4(Q.nd1, Q.x1, Q.y1, mipf);
-				Q.nd1 += Q.ngd1; Q.x1 += Q.gx1; Q.y1 += Q.gy1;
-			}
-			else
-			{
-				out[j] = make_float4(Q.d0, Q.x0, Q.y0, mipf);
-				Q.d0 += Q.gd0; Q.x0 += Q.gx0; Q.y0 += Q.gy0;
-			}
+			const bool t1 = -Q.nd1 < Q.d0;                            // Cuda_Render.h:398-414
+			const float4 cur = make_float4(t1 ? Q.nd1 : Q.d0, t1 ? Q.x1 : Q.x0, t1 ? Q.y1 : Q.y0, mipf);
+			if (writer) out[j] = cur;
+			if (t1) { Q.nd1 += Q.ngd1; Q.x1 += Q.gx1; Q.y1 += Q.gy1; }
+			else    { Q.d0 += Q.gd0; Q.x0 += Q.gx0; Q.y0 += Q.gy0; }
 		}
 		Q.zi += n << sh;
 		s += n;
@@ -99,7 +95,7 @@ __device__ __forceinline__ int ddaq_batch(DdaQ& Q, float4* rec, int prev_n, int 
 }
 
 // PROF (tools/ray_profile.py only): per ray plane, clock64() cycles spent in each phase, written as
-// unsigned long long[8] {total, dda, filter test + queue, geometry + gather, C1, C2, consume, steps | batches << 32}
+// unsigned long long[20] {total, dda, filter test + queue, geometry + gather, C1, C2, consume, steps | batches << 32}
 // to the buffer passed in P.ids.
 #define RLERC_TICK(slot) do { if (PROF) { const long long now_ = clock64(); prof[slot] += now_ - tick; tick = now_; } } while (0)
 
@@ -108,6 +104,7 @@ __global__ void __launch_bounds__(RLERC_BLOCK, 4)
 k_traverse_f(const __grid_constant__ TraverseParams P, int rays)
 {
 	long long prof[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+	long long stat[12] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
 	long long tick = PROF ? clock64() : 0;
 	const long long t_begin = tick;
 	extern __shared__ __align__(16) uint32_t smem[];
@@ -183,6 +180,7 @@ k_traverse_f(const __grid_constant__ TraverseParams P, int rays)
 	RayCtx R;
 	R.row = row; R.ymask = ymask; R.ids = (IDS && !PROF) ? P.ids + (size_t)x * res_y * 2 : nullptr;
 	R.res_y2 = res_y2; R.pz_add = pz_add; R.py_add = py_add; R.mountain = mountain; R.gl = gl;
+	R.stat = PROF ? stat : nullptr;
 
 	// filter: the batch whose pointer-map gather is in flight
 	Geo fg;
@@ -212,7 +210,7 @@ k_traverse_f(const __grid_constant__ TraverseParams P, int rays)
 			if (PROF) prof[7] += 1;
 			if (!dda_done)
 			{
-				nvalid = ddaq_batch(Q, rec, prev_n, last_map, zfar_i);
+				nvalid = ddaq_batch(Q, rec, prev_n, last_map, zfar_i, gl == 0);
 				prev_n = nvalid;
 				if (nvalid < G) dda_done = true;
 				if (IDS && gl == 0) Cn.c_steps += nvalid;
@@ -398,7 +396,7 @@ k_traverse_f(const __grid_constant__ TraverseParams P, int rays)
 			RLERC_TICK(5);
 			if (PROF) prof[7] += 1ll << 32;
 			// ---- B / B0 / S. consume batch s0 (traverse_common.cuh) ----------------------------------------------
-			const bool finished = consume_batch<IDS>(P, R, Hs, Cn, s0, g0, slen, nr, longcol, flags, proj, shade, job);
+			const bool finished = consume_batch<IDS, PROF>(P, R, Hs, Cn, s0, g0, slen, nr, longcol, flags, proj, shade, job);
 			RLERC_TICK(6);
 			if (finished) break;
 		}
@@ -416,8 +414,9 @@ k_traverse_f(const __grid_constant__ TraverseParams P, int rays)
 	if (PROF && gl == 0)
 	{
 		prof[0] = clock64() - t_begin;
-		unsigned long long* out = reinterpret_cast<unsigned long long*>(P.ids) + (size_t)x * 8;
+		unsigned long long* out = reinterpret_cast<unsigned long long*>(P.ids) + (size_t)x * 20;
 		for (int k = 0; k < 8; k++) out[k] = (unsigned long long)prof[k];
+		for (int k = 0; k < 12; k++) out[8 + k] = (unsigned long long)stat[k];
 	}
 }
 
