@@ -402,7 +402,7 @@ int rlerc_render_counters(rlerc_ctx* c, uint64_t out[10])
 	return RLERC_OK;
 }
 
-/* undocumented (tools/ray_profile.py): k_traverse_f with clock64() phase timers; d_out = unsigned long long[rays_casted][20] */
+/* undocumented (tools/ray_profile.py): k_traverse_f with clock64() phase timers; d_out = unsigned long long[rays_casted][24] */
 int rlerc_debug_profile_rays(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_config* cfg, void* d_out)
 {
 	if (!c || !d_out) return RLERC_ERR_ARG;

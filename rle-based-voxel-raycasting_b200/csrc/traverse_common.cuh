@@ -58,7 +58,7 @@ struct RayCtx {
 	uint32_t* ids;           // IDS build: id words of this ray plane's row, else null
 	float res_y2, pz_add, py_add, mountain;
 	int gl;
-	long long* stat;         // STATS build: [0] batches [1] B0 taken [2] B1 taken [3] event-loop iterations [4..11] B1 fail reasons
+	long long* stat;         // STATS build: [0] batches [1] B0 taken [2] B1 taken [3] event-loop iterations [4..10] B1 fail reasons [12..15] cycles in B0, B1, event loop, S
 };
 
 // A pixel span [y, s2) of one run, shaded by the whole warp 32 pixels at a time, stores coalesced
@@ -493,6 +493,7 @@ __device__ __forceinline__ bool consume_batch(const TraverseParams& P, const Ray
 	// whole batch through the general event loop below.
 	if (IDS && gl == 0 && todo) dbg[0]++;
 	if (STATS && todo) R.stat[0]++;
+	long long stick = STATS ? clock64() : 0;
 	if (todo && hiw <= ycmin)
 	{
 		if (IDS && gl == 0) dbg[1]++;
@@ -582,6 +583,7 @@ __device__ __forceinline__ bool consume_batch(const TraverseParams& P, const Ray
 		}
 	}
 
+	if (STATS) { const long long now_ = clock64(); R.stat[12] += now_ - stick; stick = now_; }
 	// ---- B1. ownership-resolved path (production build) ----------------------------------------------------
 	// Every draw is first-come on the occlusion mask, and the reference's break / skip tests only ever discard
 	// spans that lie entirely inside already covered rows.  So for REGULAR columns (sy2 non-increasing over the
@@ -733,6 +735,7 @@ __device__ __forceinline__ bool consume_batch(const TraverseParams& P, const Ray
 		}
 	}
 
+	if (STATS) { const long long now_ = clock64(); R.stat[13] += now_ - stick; stick = now_; }
 	while (todo)
 	{
 		if (STATS) R.stat[3]++;
@@ -855,6 +858,7 @@ __device__ __forceinline__ bool consume_batch(const TraverseParams& P, const Ray
 		}
 	}
 
+	if (STATS) { const long long now_ = clock64(); R.stat[14] += now_ - stick; stick = now_; }
 	// ---- S. shade the short spans of this batch: every lane its own column, side by side -------
 	if (shade_runs)
 	{
@@ -924,6 +928,7 @@ __device__ __forceinline__ bool consume_batch(const TraverseParams& P, const Ray
 			}
 		}
 	}
+	if (STATS) { const long long now_ = clock64(); R.stat[15] += now_ - stick; stick = now_; }
 	H.ycmin = ycmin; H.ycmax = ycmax; H.hiw = hiw;
 	return finished;
 }

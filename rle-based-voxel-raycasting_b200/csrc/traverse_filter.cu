@@ -95,7 +95,7 @@ __device__ __forceinline__ int ddaq_batch(DdaQ& Q, float4* rec, int prev_n, int 
 }
 
 // PROF (tools/ray_profile.py only): per ray plane, clock64() cycles spent in each phase, written as
-// unsigned long long[20] {total, dda, filter test + queue, geometry + gather, C1, C2, consume, steps | batches << 32}
+// unsigned long long[24] {total, dda, filter test + queue, geometry + gather, C1, C2, consume, steps | batches << 32}
 // to the buffer passed in P.ids.
 #define RLERC_TICK(slot) do { if (PROF) { const long long now_ = clock64(); prof[slot] += now_ - tick; tick = now_; } } while (0)
 
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(RLERC_BLOCK, 4)
 k_traverse_f(const __grid_constant__ TraverseParams P, int rays)
 {
 	long long prof[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
-	long long stat[12] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+	long long stat[16] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
 	long long tick = PROF ? clock64() : 0;
 	const long long t_begin = tick;
 	extern __shared__ __align__(16) uint32_t smem[];
@@ -414,9 +414,9 @@ k_traverse_f(const __grid_constant__ TraverseParams P, int rays)
 	if (PROF && gl == 0)
 	{
 		prof[0] = clock64() - t_begin;
-		unsigned long long* out = reinterpret_cast<unsigned long long*>(P.ids) + (size_t)x * 20;
+		unsigned long long* out = reinterpret_cast<unsigned long long*>(P.ids) + (size_t)x * 24;
 		for (int k = 0; k < 8; k++) out[k] = (unsigned long long)prof[k];
-		for (int k = 0; k < 12; k++) out[8 + k] = (unsigned long long)stat[k];
+		for (int k = 0; k < 16; k++) out[8 + k] = (unsigned long long)stat[k];
 	}
 }
 

@@ -45,6 +45,11 @@ def test_warp_buffer_bit_exact_camera_grid(R, rb, gpu, scene_mid, lanes):
     cams = list(camera_grid(-100.0))
     if lanes not in (0, 64, 32):
         cams = cams[::3]
+    else:
+        # exactly on a lattice point looking along a grid axis (NaN / inf DDA tracks: merge path -> serial
+        # fallback), and negative coordinates (first intersections opposite in sign to their gradients)
+        cams = cams + [((10000.0, -100.0, 10000.0), (0.3, math.pi / 2, 0.0)), ((10000.0, -100.0, 10000.0), (0.3, 0.0, 0.0)),
+                       ((-3000.25, -100.0, -70.5), (0.3, 0.7, 0.0)), ((-0.5, -60.0, 2000.75), (0.5, 3.9, 0.0))]
     for pos, rot in cams:
         rm = R.RayMap(cfg).get_ray_map(pos, rot)
         _, want, _, _ = _oracle(rb, rm, scene_mid, cfg)

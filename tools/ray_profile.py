@@ -20,7 +20,7 @@ names = ["total", "dda", "test+queue", "geom+gather", "C1", "C2", "consume"]
 for t in frames:
     pos, rot = bench.path_pose(R, t, 1000, sy, False)
     rm = R.RayMap(cfg).get_ray_map(pos, rot)
-    buf = torch.zeros((cfg.rays_casted, 20), dtype=torch.int64, device="cuda")
+    buf = torch.zeros((cfg.rays_casted, 24), dtype=torch.int64, device="cuda")
     for _ in range(2):
         rc = lib.rlerc_debug_profile_rays(r._c, C.byref(rm), C.byref(cfg), C.c_void_p(buf.data_ptr()))
         assert rc == 0, rc
@@ -38,4 +38,6 @@ for t in frames:
     st = a[:, 8:].sum(axis=0)
     print("  consume batches %d: B0 %d, B1 %d, event loop %d (%d iterations); B1 refused for [flip,longcol,irregular,topattach,window,clipflip,2long] = %s"
           % (st[0], st[1], st[2], st[0] - st[1] - st[2], st[3], list(st[4:11])))
+    i = order[0]
+    print("  slowest ray plane, cycles per consume batch: B0 %.0f, B1 %.0f, event loop %.0f, S %.0f" % tuple(a[i, 20 + k] / max(1, batches[i]) for k in range(4)))
     print("  all rays: %s | %d, %d" % (" ".join("%5.1f%%" % (100.0 * a[:, k].sum() / tot) for k in range(1, 7)), steps.sum(), batches.sum()))
