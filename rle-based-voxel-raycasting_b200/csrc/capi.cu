@@ -297,9 +297,9 @@ int rlerc_scene_device_maps(rlerc_ctx* c, rlerc_map4* out16, int* nummaps)
 
 int rlerc_set_lanes_per_ray(rlerc_ctx* c, int lanes)
 {
-	if (!c || !(lanes == 0 || lanes == 1 || lanes == 2 || lanes == 4 || lanes == 8 || lanes == 16 || lanes == 32 || lanes == 64))
+	if (!c || !(lanes == 0 || lanes == 1 || lanes == 2 || lanes == 4 || lanes == 8 || lanes == 16 || lanes == 32 || (lanes >= 64 && lanes <= 67)))
 	{
-		set_error("lanes per ray must be 0,1,2,4,8,16,32 or 64");
+		set_error("lanes per ray must be 0,1,2,4,8,16,32 or a kernel code 64..67");
 		return RLERC_ERR_ARG;
 	}
 	c->lanes = lanes;
