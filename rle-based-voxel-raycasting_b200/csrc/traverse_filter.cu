@@ -99,8 +99,13 @@ __device__ __forceinline__ int ddaq_batch(DdaQ& Q, float4* rec, int prev_n, int 
 // to the buffer passed in P.ids.
 #define RLERC_TICK(slot) do { if (PROF) { const long long now_ = clock64(); prof[slot] += now_ - tick; tick = now_; } } while (0)
 
+#ifndef RLERC_F_WPB
+#define RLERC_F_WPB 8                       // ray planes (warps) per block (16 warps per SM at 128 registers); adjacent ray
+                                            // planes share pointer-map lines in L1, 8 per block measured best at 4K
+#endif
+
 template <bool IDS, bool PROF>
-__global__ void __launch_bounds__(RLERC_BLOCK, 4)
+__global__ void __launch_bounds__(RLERC_F_WPB * 32, 16 / RLERC_F_WPB)
 k_traverse_f(const __grid_constant__ TraverseParams P, int rays)
 {
 	long long prof[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
@@ -109,7 +114,7 @@ k_traverse_f(const __grid_constant__ TraverseParams P, int rays)
 	const long long t_begin = tick;
 	extern __shared__ __align__(16) uint32_t smem[];
 	constexpr int G = 32;
-	constexpr int WPB = RLERC_BLOCK / 32;
+	constexpr int WPB = RLERC_F_WPB;
 	const int gl = threadIdx.x & 31;
 	const int wid = threadIdx.x >> 5;
 	const unsigned FULL = 0xffffffffu;
@@ -423,7 +428,7 @@ k_traverse_f(const __grid_constant__ TraverseParams P, int rays)
 template <bool IDS, bool PROF>
 static void launch_f(const TraverseParams& p, cudaStream_t st)
 {
-	const int wpb = RLERC_BLOCK / 32;
+	const int wpb = RLERC_F_WPB;
 	const int rays = (p.slice_n > 1) ? owned_count(p.ray_end, p.slice_block, p.slice_n, p.slice_rank) : p.ray_end - p.ray_begin;
 	if (rays <= 0) return;
 	const int blocks = (rays + wpb - 1) / wpb;
@@ -434,7 +439,7 @@ static void launch_f(const TraverseParams& p, cudaStream_t st)
 		cudaFuncSetAttribute(k_traverse_f<IDS, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		configured = smem;
 	}
-	k_traverse_f<IDS, PROF><<<blocks, RLERC_BLOCK, smem, st>>>(p, rays);
+	k_traverse_f<IDS, PROF><<<blocks, wpb * 32, smem, st>>>(p, rays);
 }
 
 void launch_traverse_filter(const TraverseParams& p, bool ids, cudaStream_t st)
