@@ -105,6 +105,22 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
+KERNEL_NAMES = {0: "k_traverse_f", 65: "k_traverse_f", 64: "k_traverse_w", 66: "k_traverse_c<3>", 67: "k_traverse_c<7>"}
+
+
+def measured_traffic(workload, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the traversal kernel, from the committed
+    `ncu --set full` capture (profiles/traffic.json; null when there is none for this workload / kernel)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        e = t.get(workload)
+        if e and e.get("kernel") == kernel:
+            return e["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    return None
+
+
 def traversal_bytes(c):
     """Algorithmic bytes of one traversal launch from its work counters."""
     C_, E, C1, P, K = c["cols_fetched"], c["run_iters"], c["cols_nonempty"], c["pixels"], c["cleared"]
@@ -135,13 +151,20 @@ def cpu_frames(R, rb, scene, cfg, poses, threads):
 
 
 def main():
+    # The contract is ONE JSON line on stdout.  Native libraries write there too (NCCL prints its version banner to
+    # fd 1 on communicator creation), so everything but the final line goes to stderr at the file-descriptor level.
+    json_out = os.fdopen(os.dup(1), "w")
+    sys.stdout.flush()
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default="imrodh1080p", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="rlerc", choices=["rlerc", "reference"])
-    ap.add_argument("--lanes", type=int, default=0, help="traversal kernel variant (0 = warp per ray plane)")
+    ap.add_argument("--lanes", type=int, default=0,
+                    help="traversal kernel variant (rlerc_set_lanes_per_ray): 0 = k_traverse_f (production), 64 = k_traverse_w, "
+                         "66/67 = k_traverse_c, 1..32 = k_traverse<lanes>")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--slice-block", type=int, default=32)
@@ -185,7 +208,7 @@ def main():
                                  "sample": "%d fly-through frames: reference render_line (OpenMP over ray planes, %.1f ms/frame) + oracle unwarp (%.1f ms/frame)"
                                            % (K, 1e3 * sum(t[0] for t in times) / K, 1e3 * sum(t[1] for t in times) / K)},
                 "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=json_out, flush=True)
         return 0
 
     # ------------------------------------------------------------------ our arm (B200)
@@ -327,13 +350,28 @@ def main():
         per_launch_bytes = bytes_per_frame / (world if sliced else 1)
         achieved = per_launch_bytes / (trav_ms_max / max(kernels_timed, 1) / 1e3) / 1e9
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "k_traverse_w" if args.lanes == 0 else "k_traverse<%d>" % args.lanes,
+                "traffic": measured_traffic(args.workload, KERNEL_NAMES.get(args.lanes, "k_traverse<%d>" % args.lanes)),
+                "kernel": KERNEL_NAMES.get(args.lanes, "k_traverse<%d>" % args.lanes),
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                 "algorithmic_bytes_per_launch": per_launch_bytes,
                 "traverse_ms_per_launch": trav_ms_max / max(kernels_timed, 1), "unwarp_ms_per_launch": unwarp_ms_max / max(kernels_timed, 1),
                 "unwarp_achieved_gbs": 8.0 * WW * HH / (max(unwarp_ms_max, 1e-9) / max(kernels_timed, 1) / 1e3) / 1e9,
                 "counters_per_frame": {k_: v / len(sample_idx) for k_, v in agg.items()},
                 "plane_rays_per_frame": tot_rays / len(sample_idx)}
+
+    # ---- same-GPU comparator: the reference's own scheme (one THREAD per ray plane, k_traverse<1>) on a few frames
+    if rank == 0 and world == 1 and roof is not None and args.lanes == 0:
+        r.set_lanes_per_ray(1)
+        r.set_timing(True)
+        ms = []
+        for j in ([int(j * K / 3) for j in range(3)] if K >= 3 else list(range(K))):
+            r.render(raymaps[j], cfg)
+            r.sync()
+            ms.append(r.last_kernel_ms()[0])
+        r.set_timing(False)
+        r.set_lanes_per_ray(args.lanes)
+        roof["reference_scheme_on_this_gpu"] = {"kernel": "k_traverse<1>: one thread per ray plane, as cudaRender (R/src/Cuda_Main.cu:150-181)",
+                                                "traverse_ms_per_launch": sum(ms) / len(ms), "frames": len(ms)}
 
     # ---- e2e through the C ABI with host buffers (pinned), D2H inside the timed region
     barrier()
@@ -439,7 +477,7 @@ def main():
                 "clocks": clocks, "e2e": e2e, "gpu_launches": 2 * K, "roofline": roof}
         if cpu:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=json_out, flush=True)
     barrier()
     if dist.is_initialized():
         dist.destroy_process_group()
