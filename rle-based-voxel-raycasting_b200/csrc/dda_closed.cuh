@@ -168,4 +168,38 @@ RLERC_HD int dda_merge_search(const int* T0, const int* T1, int s)
 	return lo;
 }
 
+// ---- single-regime fast path (k_traverse_f) ------------------------------------------------------------------
+// While none of a track's three variables leaves its binade, firing i of the track has the bit patterns
+// b + i*D.  Lane j takes firing j of BOTH tracks and finds its position in the merged order directly:
+//     rank(x-track firing i) = i + #{k : d1[k] <  d0[i]}        (the serial loop fires the z-track iff d1 < d0,
+//     rank(z-track firing j) = j + #{k : d0[k] <= d1[j]}         Cuda_Render.h:398: ties go to the x-track)
+// The count is estimated from the real-valued crossing (A - head) / gradient and fixed up with exact integer
+// compares of the bit patterns (non-negative floats order like their bits).  Values past the regime's exact
+// range are linear extrapolations; they stay monotone and above every exact value, so a comparison against them
+// still answers correctly for every firing that belongs to the batch as long as the batch consumes no more than
+// L exact firings of either track (checked after the fact: n0 <= L0, n1 <= L1).
+
+// #{k in [0, 34] : (b + k*D) < A}, or <= A with le.  ok = false when the fix-up did not converge.
+RLERC_HD int dda_count_below(int b, int D, float head, float inv_g, int A, bool le, bool& ok)
+{
+	const float t = (dda_b2f(A) - head) * inv_g;
+	int c = !(t > -1.0f) ? 0 : (t >= 33.0f ? 34 : (int)t + 1);
+	const int adj = le ? 1 : 0;                                      // (x <= A) == (x < A + 1) on integers
+	#pragma unroll
+	for (int it = 0; it < 3; it++) if (c < 34 && (b + c * D) < A + adj) c++;
+	#pragma unroll
+	for (int it = 0; it < 3; it++) if (c > 0 && !((b + (c - 1) * D) < A + adj)) c--;
+	if ((c < 34 && (b + c * D) < A + adj) || (c > 0 && !((b + (c - 1) * D) < A + adj))) ok = false;
+	return c;
+}
+
+// regime of one variable for the fast path: D, and L = exact firings available (0: take the serial recurrence)
+RLERC_HD void dda_fast_regime(int b, int gb, int& D, int& L)
+{
+	int F;
+	dda_regime(b, gb, F, D, L);
+	if (F != D || D > (1 << 22) || D < 0) L = 0;                     // odd start of a tie regime / huge increment
+	if (((unsigned)b & 0x7fffffffu) > 0x70000000u) L = 0;            // b + 34*D must stay a positive integer
+}
+
 } // namespace rlerc

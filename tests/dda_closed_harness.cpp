@@ -3,6 +3,8 @@
  * (R/src/Cuda_Render.h:286-300,343-367,398-414) on the CPU.  Built and run by tests/test_dda_closed.py.
  *
  *   var  N seed   : single-variable recurrences v <- fl(v + g), random magnitudes, LOD doublings, random advances
+ *   fast N seed   : the single-regime fast path of k_traverse_f (rank of every firing by count estimate + exact fix-up,
+ *                   validity check after the fact, serial fallback), compared crossing by crossing with the serial loop.
  *   dda  N seed   : whole two-track DDA, batch by batch, exactly as the kernel organises it (6 owner "lanes", plan
  *                   table, merge-path search per lane, validity prefix, serial fallback), compared crossing by
  *                   crossing with the serial loop.
@@ -247,6 +249,130 @@ static int test_dda(long N)
 	return 0;
 }
 
+
+/* ---- the single-regime fast path of k_traverse_f, batch by batch -------------------------------------------- */
+static int test_fast(long N)
+{
+	long checked = 0, fastb = 0, fallback = 0;
+	for (long t = 0; t < N; t++)
+	{
+		const double ang = urand() * 6.283185307179586;
+		float drx = (float)cos(ang), dry = (float)sin(ang);
+		if (rnd() % 16 == 0) dry = (float)ldexp(urand(), -(int)(rnd() % 30));
+		if (rnd() % 16 == 0) drx = (float)ldexp(urand(), -(int)(rnd() % 30));
+		if (rnd() % 64 == 0) dry = 0.0f;
+		float vpx = (float)(urand() * 20000.0 - (rnd() % 4 == 0 ? 10000.0 : 0.0)), vpz = (float)(urand() * 20000.0);
+		if (rnd() % 32 == 0) vpx = floorf(vpx);
+		float fx = vpx - (float)(int)vpx, fy = vpz - (float)(int)vpz;
+		float sgx = -1, sgy = -1;
+		if (drx >= 0) { sgx = 1; fx = 1 - fx; }
+		if (dry >= 0) { sgy = 1; fy = 1 - fy; }
+		Serial S;
+		S.g0y = dry / fabsf(drx); S.g0x = sgx;
+		S.g1x = drx / fabsf(dry); S.g1y = sgy;
+		S.i0x = S.g0x * fx; S.i0y = S.g0y * fx;
+		S.i1x = S.g1x * fy; S.i1y = S.g1y * fy;
+		S.gd0 = sqrtf(S.g0x * S.g0x + S.g0y * S.g0y);
+		S.gd1 = sqrtf(S.g1x * S.g1x + S.g1y * S.g1y);
+		S.d0 = sqrtf(S.i0x * S.i0x + S.i0y * S.i0y);
+		S.d1 = sqrtf(S.i1x * S.i1x + S.i1y * S.i1y);
+		S.posx = S.posy = S.dist_now = 0; S.index = 0; S.mip = 0; S.zi = 0; S.dzi = 1;
+		S.mapswitch = 100 + (int)(rnd() % 2000);
+		const int last_map = 9, zfar = 80000;
+		for (int k = (int)(rnd() % 3); k > 0; k--) lod_switch(S, last_map);
+		Serial Q = S;                                                                   /* the serial truth */
+		const bool sorted = !(S.d0 != S.d0) && !(S.d1 != S.d1) && !(S.gd0 != S.gd0) && !(S.gd1 != S.gd1);
+		/* kernel-side state: float heads + gradients (uniform), D / L per variable (owner lanes) */
+		float* const hv[6] = { &S.d0, &S.i0x, &S.i0y, &S.d1, &S.i1x, &S.i1y };
+		float* const gv[6] = { &S.gd0, &S.g0x, &S.g0y, &S.gd1, &S.g1x, &S.g1y };
+		int D[6], L[6];
+		for (int k = 0; k < 6; k++) dda_fast_regime(dda_f2b(*hv[k]), dda_f2b(*gv[k]), D[k], L[k]);
+		int guard = 0;
+		while (guard++ < 4000)
+		{
+			Rec out[32]; int n = 0;
+			bool lod = false;
+			while (S.zi > S.mapswitch) { lod_switch(S, last_map); lod = true; }
+			if (lod) for (int k = 0; k < 6; k++) dda_fast_regime(dda_f2b(*hv[k]), dda_f2b(*gv[k]), D[k], L[k]);
+			const int lod_free = (S.mapswitch - S.zi) / S.dzi + 1;
+			const int far_free = (zfar - S.zi) / S.dzi;
+			if (far_free <= 0) break;
+			int want = 32; if (lod_free < want) want = lod_free; if (far_free < want) want = far_free;
+			int L0 = L[0], L1 = L[3];
+			for (int k = 1; k < 3; k++) { if (L[k] < L0) L0 = L[k]; if (L[3 + k] < L1) L1 = L[3 + k]; }
+			bool done_fast = false;
+			if (sorted && L0 >= 1 && L1 >= 1)
+			{
+				bool ok = true;
+				int slot_tr[33], slot_ix[33], filled[33];
+				memset(filled, 0, sizeof(filled));
+				const int b0 = dda_f2b(S.d0), b1 = dda_f2b(S.d1);
+				const float inv0 = 1.0f / S.gd0, inv1 = 1.0f / S.gd1;
+				int n0 = 0;
+				for (int j = 0; j < 32; j++)
+				{
+					const int A0 = b0 + j * D[0], A1 = b1 + j * D[3];
+					const int r0 = j + dda_count_below(b1, D[3], S.d1, inv1, A0, false, ok);
+					const int r1 = j + dda_count_below(b0, D[0], S.d0, inv0, A1, true, ok);
+					if (r0 < want) { n0++; filled[r0]++; slot_tr[r0] = 0; slot_ix[r0] = j; }
+					if (r1 < want) { filled[r1]++; slot_tr[r1] = 1; slot_ix[r1] = j; }
+				}
+				const int n1 = want - n0;
+				if (ok && n0 <= L0 && n1 <= L1)
+				{
+					for (int s = 0; s < want; s++) if (filled[s] != 1) { printf("slot %d filled %d times (t %ld batch %d)\n", s, filled[s], t, guard); return 1; }
+					for (int s = 0; s < want; s++)
+					{
+						const int tr = slot_tr[s], ix = slot_ix[s];
+						const float d = dda_b2f(dda_f2b(*hv[tr * 3]) + ix * D[tr * 3]);
+						out[s].sd = tr ? -d : d;
+						out[s].px = dda_b2f(dda_f2b(*hv[tr * 3 + 1]) + ix * D[tr * 3 + 1]);
+						out[s].py = dda_b2f(dda_f2b(*hv[tr * 3 + 2]) + ix * D[tr * 3 + 2]);
+						out[s].mip = S.mip;
+					}
+					for (int k = 0; k < 3; k++)
+					{
+						*hv[k] = dda_b2f(dda_f2b(*hv[k]) + n0 * D[k]); if (L[k] < RLERC_DDA_LBIG) L[k] -= n0;
+						*hv[3 + k] = dda_b2f(dda_f2b(*hv[3 + k]) + n1 * D[3 + k]); if (L[3 + k] < RLERC_DDA_LBIG) L[3 + k] -= n1;
+					}
+					S.zi += want * S.dzi;
+					n = want;
+					done_fast = true;
+					fastb++;
+				}
+			}
+			if (!done_fast)
+			{
+				for (; n < want; n++) if (!serial_step(S, last_map, zfar, out[n])) break;
+				for (int k = 0; k < 6; k++) dda_fast_regime(dda_f2b(*hv[k]), dda_f2b(*gv[k]), D[k], L[k]);
+				fallback++;
+			}
+			for (int s = 0; s < n; s++)
+			{
+				Rec r;
+				if (!serial_step(Q, last_map, zfar, r)) { printf("serial ended early t %ld\n", t); return 1; }
+				if (!same(r.sd, out[s].sd) || !same(r.px, out[s].px) || !same(r.py, out[s].py) || r.mip != out[s].mip)
+				{
+					printf("fast mismatch t %ld batch %d s %d: want (%a %a %a %d) got (%a %a %a %d) fast %d\n",
+					       t, guard, s, r.sd, r.px, r.py, r.mip, out[s].sd, out[s].px, out[s].py, out[s].mip, (int)done_fast);
+					return 1;
+				}
+				checked++;
+			}
+			if (S.zi != Q.zi) { printf("zi mismatch t %ld\n", t); return 1; }
+			for (int k = 0; k < 6; k++)
+			{
+				float* const qv[6] = { &Q.d0, &Q.i0x, &Q.i0y, &Q.d1, &Q.i1x, &Q.i1y };
+				if (!same(*hv[k], *qv[k])) { printf("head %d mismatch t %ld batch %d fast %d\n", k, t, guard, (int)done_fast); return 1; }
+			}
+		}
+		Rec r;
+		if (serial_step(Q, last_map, zfar, r)) { printf("fast path ended early t %ld (zi %d)\n", t, S.zi); return 1; }
+	}
+	printf("ok %ld %ld %ld\n", checked, fastb, fallback);
+	return 0;
+}
+
 int main(int argc, char** argv)
 {
 	if (argc < 3) { fprintf(stderr, "usage: %s var|dda N [seed]\n", argv[0]); return 2; }
@@ -255,5 +381,6 @@ int main(int argc, char** argv)
 	for (int i = 0; i < 8; i++) rnd();
 	if (!strcmp(argv[1], "var")) return test_var(N);
 	if (!strcmp(argv[1], "dda")) return test_dda(N);
+	if (!strcmp(argv[1], "fast")) return test_fast(N);
 	return 2;
 }

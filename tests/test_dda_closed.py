@@ -32,3 +32,14 @@ def test_two_track_dda_batches(harness, seed):
     checked, closed, fallback = (int(v) for v in r.stdout.split()[1:4])
     assert checked > 1_000_000
     assert fallback < 0.05 * closed      # the serial fallback is for the first crossings and NaN rays only
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_single_regime_fast_path(harness, seed):
+    """Rank-by-count formulation (every lane takes firing j of both tracks, count estimate + exact integer fix-up,
+    validity checked after the fact): bit-identical records and heads.  Measured slower than the serial recurrence
+    on B200, so the kernel does not use it; the scheme stays pinned here."""
+    r = subprocess.run([harness, "fast", "300", str(seed)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout
+    checked, fast, fallback = (int(v) for v in r.stdout.split()[1:4])
+    assert checked > 500_000 and fast > fallback
