@@ -434,6 +434,7 @@ k_traverse_w(const __grid_constant__ TraverseParams P, int rays, int producer_bl
 					S = T;
 				}
 				if (nvalid < G) dda_done = true;
+				__syncwarp();          // every lane wrote every record (same values): ordering made explicit for racecheck
 				pra = rec[gl]; prb = rec[gl + 1];
 			}
 			if (PC && nvalid < G) dda_done = true;

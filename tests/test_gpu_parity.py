@@ -392,4 +392,41 @@ def test_error_paths_on_device(R, gpu, scene_small):
     m4.map, m4.slabs = mp.ctypes.data, sl.ctypes.data
     with pytest.raises(R.RlercError):
         r2.all_to_gpu(R.RLE4.from_maps([m4]))
-    r2.close()
+    r2.close()@pytest.mark.gpu
+def test_production_build_equals_instrumented_build_up_to_8k(R, rb, gpu):
+    """BASELINE config 2-5 sizes (1080p, 4K, 8K): the production build (column filter, B0 / B1 batch paths) and the
+    instrumented build of the same kernel (every column through, owner-lane event loop) give the same warped buffer;
+    a slice of the ray planes is also checked against the oracle directly."""
+    import torch
+    scenes = ((R.RLE4.synth(0, 256, 256, 256, seed=1), 0.25), (R.RLE4.synth(1, 128, 64, 128, seed=42), 0.03))
+    for scene, hscale in scenes:
+        gpu.all_to_gpu(scene)
+        for wh in ((1920, 1080), (3840, 2160), (7680, 4320)):
+            cfg = R.FrameConfig.default(*wh)
+            for t in ((0, 600) if wh[0] < 7680 else (250,)):
+                pos, rot = R.flythrough_pose(t)
+                pos = (pos[0], pos[1] * hscale, pos[2])
+                rm = R.RayMap(cfg).get_ray_map(pos, rot)
+                gpu.set_lanes_per_ray(0)
+                _fresh_warp(gpu, cfg)
+                gpu.render(rm, cfg)
+                gpu.sync()
+                prod = gpu.read_warp(cfg)
+                ids = torch.empty((cfg.rays_casted, cfg.render_size, 2), dtype=torch.int32, device="cuda")
+                _fresh_warp(gpu, cfg)
+                gpu.render_ids(rm, cfg, ids.data_ptr())
+                gpu.sync()
+                inst = gpu.read_warp(cfg)
+                del ids
+                assert np.array_equal(prod, inst), (wh, t, int((prod != inst).sum()))
+                # oracle on 192 ray planes around the middle of the frame
+                r0 = max(0, rm.map_line_count // 2 - 96)
+                r1 = min(rm.map_line_count, r0 + 192)
+                orm = oracle_raymap(rb, rm, scene)
+                want, _, _ = rb.orc_render(orm, cfg.render_size, cfg.rays_casted, cfg.mip_distance, cfg.z_far, ray_begin=r0, ray_end=r1)
+                assert np.array_equal(prod[r0:r1], want[r0:r1]), (wh, t)
+                del prod, inst, want
+    gpu.set_lanes_per_ray(0)
+
+
+
