@@ -392,7 +392,9 @@ def test_error_paths_on_device(R, gpu, scene_small):
     m4.map, m4.slabs = mp.ctypes.data, sl.ctypes.data
     with pytest.raises(R.RlercError):
         r2.all_to_gpu(R.RLE4.from_maps([m4]))
-    r2.close()@pytest.mark.gpu
+    r2.close()
+
+
 def test_production_build_equals_instrumented_build_up_to_8k(R, rb, gpu):
     """BASELINE config 2-5 sizes (1080p, 4K, 8K): the production build (column filter, B0 / B1 batch paths) and the
     instrumented build of the same kernel (every column through, owner-lane event loop) give the same warped buffer;
@@ -427,6 +429,3 @@ def test_production_build_equals_instrumented_build_up_to_8k(R, rb, gpu):
                 assert np.array_equal(prod[r0:r1], want[r0:r1]), (wh, t)
                 del prod, inst, want
     gpu.set_lanes_per_ray(0)
-
-
-
