@@ -37,6 +37,7 @@ WORKLOADS = {
     "imrodh768": (0, (1024, 1024, 1024), 1, (1024, 768), "BASELINE config 1 window: 1024x768"),
     "tiled4k": (0, (512, 512, 512), 16, (3840, 2160), "BASELINE config 3: 16x16 physical tiling (multi-GB RLE) at 3840x2160"),
     "shortrun4k": (1, (2048, 1024, 2048), 1, (3840, 2160), "BASELINE config 4 (reduced footprint): worst-case short-run band at 3840x2160"),
+    "view8k": (0, (512, 512, 512), 16, (7680, 4320), "BASELINE config 5: 7680x4320 views of the tiled scene (N > 1, --mp frames: one camera per GPU, NVLink gather to rank 0)"),
     "small": (0, (256, 256, 256), 1, (1024, 768), "quick functional run"),
 }
 
@@ -380,21 +381,22 @@ def main():
         r2 = R.Renderer(local)
         r2.all_to_gpu(scene)
         r2.set_lanes_per_ray(args.lanes)
-        pins = [R.PinnedBuffer((HH, WW, 4)) for _ in range(3)]
+        DEPTH = int(os.environ.get("RLERC_E2E_DEPTH", "4"))          # frames in flight (rlerc_frame_submit pipelines up to RLERC_FRAME_SLOTS)
+        pins = [R.PinnedBuffer((HH, WW, 4)) for _ in range(DEPTH)]
         for i in range(W):
-            r2.frame_wait(r2.frame_submit(poses[i % K][0], poses[i % K][1], cfg, pins[i % 3].array))
+            r2.frame_wait(r2.frame_submit(poses[i % K][0], poses[i % K][1], cfg, pins[i % DEPTH].array))
         r2.sync()
         t0 = time.perf_counter()
         tickets = []
         for i in range(K):
-            if len(tickets) >= 3:
+            if len(tickets) >= DEPTH:
                 r2.frame_wait(tickets.pop(0))
-            tickets.append(r2.frame_submit(poses[i][0], poses[i][1], cfg, pins[i % 3].array))
+            tickets.append(r2.frame_submit(poses[i][0], poses[i][1], cfg, pins[i % DEPTH].array))
         for tk in tickets:
             r2.frame_wait(tk)
         r2.sync()
         e2e_wall = time.perf_counter() - t0
-        checksum = int(pins[(K - 1) % 3].array[::16, ::16].astype(np.uint32).sum())
+        checksum = int(pins[(K - 1) % DEPTH].array[::16, ::16].astype(np.uint32).sum())
         for p in pins:
             p.free()
         r2.close()
@@ -435,7 +437,7 @@ def main():
     e2e_fps = K / e2e_wall
     e2e = {"value": WW * HH * e2e_fps / 1e6, "unit": "Mrays/s", "frames_per_s": e2e_fps,
            "h2d_bytes_per_step": 1024 * world, "d2h_bytes_per_step": WW * HH * 4,
-           "how": "pinned host RGBA out, camera pose in; %s" % ("rlerc_frame_submit/wait, 3 frames in flight" if world == 1
+           "how": "pinned host RGBA out, camera pose in; %s" % ("rlerc_frame_submit/wait, %s frames in flight, one stream per frame slot" % os.environ.get("RLERC_E2E_DEPTH", "4") if world == 1
                                                                  else ("per-rank slices + NCCL reduce + D2H on rank 0" if farm is None
                                                                        else "whole frames per rank + NCCL gather + D2H of every frame on rank 0")),
            "checksum": checksum}
