@@ -131,13 +131,13 @@ k_traverse_c(const __grid_constant__ TraverseParams P, int rays)
 	volatile int* tail = stop + 2 * WPB;                             // chunks released by the ray-plane warp
 	uint32_t* warps0 = after_ring + WPB * RLERC_C_STATE + 8 * WPB;
 	const bool dda_warp = wid == WPB;
-	const int per_warp = (RLERC_C_QUEUE + 16 + RLERC_RW * 96 + P.mask_words + 3) & ~3;
+	const int per_warp = (RLERC_C_QUEUE + 16 + RLERC_PS_WORDS + P.mask_words + 3) & ~3;
 	uint32_t* wbase = warps0 + (size_t)(dda_warp ? 0 : wid) * per_warp;
 	uint32_t* queue = wbase;                                         // [8][QCAP]
 	DrawJob* job = reinterpret_cast<DrawJob*>(wbase + RLERC_C_QUEUE);
 	int2* proj = reinterpret_cast<int2*>(wbase + RLERC_C_QUEUE + 16);
 	uint32_t* shade = wbase + RLERC_C_QUEUE + 16 + RLERC_RW * 64;
-	uint32_t* ymask = wbase + RLERC_C_QUEUE + 16 + RLERC_RW * 96;
+	uint32_t* ymask = wbase + RLERC_C_QUEUE + 16 + RLERC_PS_WORDS;
 
 	const int ray_i = (int)blockIdx.x * WPB + wid;                  // launch-local ray index
 	const int x = owned_ray(P, ray_i);
@@ -504,7 +504,7 @@ static void launch_c(const TraverseParams& p, cudaStream_t st)
 	const int rays = (p.slice_n > 1) ? owned_count(p.ray_end, p.slice_block, p.slice_n, p.slice_rank) : p.ray_end - p.ray_begin;
 	if (rays <= 0) return;
 	const int blocks = (rays + WPB - 1) / WPB;                        // + one DDA warp per block
-	const size_t per_warp = (RLERC_C_QUEUE + 16 + RLERC_RW * 96 + p.mask_words + 3) & ~3;
+	const size_t per_warp = (RLERC_C_QUEUE + 16 + RLERC_PS_WORDS + p.mask_words + 3) & ~3;
 	const size_t words = (size_t)2 * WPB * (RLERC_CH + 1) * 4 + (size_t)WPB * RLERC_C_STATE + 8 * WPB + (size_t)WPB * per_warp;
 	const size_t smem = words * sizeof(uint32_t);
 	static size_t configured = 0;

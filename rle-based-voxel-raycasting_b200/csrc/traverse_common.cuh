@@ -11,7 +11,10 @@ namespace rlerc {
 
 #define RLERC_RW 8          // runs pre-projected per column (first 8 run words)
 #define RLERC_DDA_WORDS (66 * 4 + 72)   // shared words per warp for the DDA hand-over (merge path: 66 float4 + 72 float)
-#define RLERC_COOP_MIN 12   // pixel spans at least this long are shaded by the whole warp
+#ifndef RLERC_COOP_MIN
+#define RLERC_COOP_MIN 33   // pixel spans at least this long are shaded by the whole warp (a deferred span record holds <= 32 rows)
+#endif
+#define RLERC_PS_WORDS (RLERC_RW * 128)   // shared words per warp: RW x 32 projected runs (int2) + RW x 32 deferred span records (uint2)
 
 struct DrawJob {            // owner lane -> warp hand-off for a long pixel span (shared memory)
 	float cpz, cpy;
@@ -40,6 +43,9 @@ __device__ __forceinline__ unsigned run_word(const unsigned (&rw)[4], int r)
 	const unsigned w = (r < 4) ? ((r < 2) ? rw[0] : rw[1]) : ((r < 6) ? rw[2] : rw[3]);
 	return (w >> ((r & 1) * 16)) & 0xffffu;
 }
+
+// the n lowest bits (0 <= n <= 32)
+__device__ __forceinline__ unsigned row_bits(int n) { return n >= 32 ? 0xffffffffu : ((1u << n) - 1u); }
 
 // bits [lo, hi) of one 32-bit word, lo / hi clamped to the word (empty when hi <= 0 or lo >= 32 or hi <= lo)
 __device__ __forceinline__ unsigned bit_range(int lo, int hi)
@@ -553,7 +559,7 @@ __device__ __forceinline__ bool consume_batch(const TraverseParams& P, const Ray
 			yend = yend > y0 ? yend : y0;
 			if (draws)
 			{
-				shade[ra * 32 + gl] = (unsigned)yc | ((unsigned)(T - yc) << 16) | (0xfffu << 20);
+				reinterpret_cast<uint2*>(shade)[ra * 32 + gl] = make_uint2((unsigned)yc | ((unsigned)(T - yc) << 16), row_bits(T - yc));
 				shade_runs |= 1u << ra;
 			}
 			for (int w = (y0 >> 5) + gl; w <= ((yend - 1) >> 5) && yend > y0; w += 32)
@@ -666,14 +672,14 @@ __device__ __forceinline__ bool consume_batch(const TraverseParams& P, const Ray
 					const int first = a0 ? __ffs(a0) - 1 : (a1 ? 31 + __ffs(a1) : (a2 ? 63 + __ffs(a2) : 95 + __ffs(a3)));
 					const int last = a3 ? 127 - __clz(a3) : (a2 ? 95 - __clz(a2) : (a1 ? 63 - __clz(a1) : 31 - __clz(a0)));
 					const int n = last - first + 1;
-					if (n <= 12)
+					if (n < RLERC_COOP_MIN)
 					{
-						// the 12 rows from `first` on, as a bit field
+						// the 32 rows from `first` on, as a bit field
 						const int k = first >> 5, sh = first & 31;
 						const unsigned lo_w = k == 0 ? a0 : (k == 1 ? a1 : (k == 2 ? a2 : a3));
 						const unsigned hi_w = k == 0 ? a1 : (k == 1 ? a2 : (k == 2 ? a3 : 0u));
-						const unsigned bits = (sh ? ((lo_w >> sh) | (hi_w << (32 - sh))) : lo_w) & 0xfffu;
-						shade[r * 32 + gl] = (unsigned)(wbase + first) | ((unsigned)n << 16) | (bits << 20);   // scratch until shade_runs says so
+						const unsigned bits = sh ? ((lo_w >> sh) | (hi_w << (32 - sh))) : lo_w;
+						reinterpret_cast<uint2*>(shade)[r * 32 + gl] = make_uint2((unsigned)(wbase + first) | ((unsigned)n << 16), bits);   // scratch until shade_runs says so
 						my_shade |= 1u << r;
 					}
 					else if (long_r < 0) { long_r = r; long_y = wbase + first; long_e = wbase + last + 1; }
@@ -827,10 +833,10 @@ __device__ __forceinline__ bool consume_batch(const TraverseParams& P, const Ray
 						const int w = y >> 5, sh = y & 31;
 						unsigned bits = ymask[w] >> sh;
 						if (sh) bits |= ymask[w + 1] << (32 - sh);
-						const unsigned clear = ~bits & ((1u << n) - 1u);
+						const unsigned clear = ~bits & row_bits(n);
 						ymask[w] |= clear << sh;
 						if (sh && (clear >> (32 - sh))) ymask[w + 1] |= clear >> (32 - sh);
-						shade[r * 32 + gl] = (unsigned)y | ((unsigned)n << 16) | (clear << 20);
+						reinterpret_cast<uint2*>(shade)[r * 32 + gl] = make_uint2((unsigned)y | ((unsigned)n << 16), clear);
 						shade_runs |= 1u << r;
 					}
 				}
@@ -873,10 +879,10 @@ __device__ __forceinline__ bool consume_batch(const TraverseParams& P, const Ray
 			const int texture = btex, texn = btex + solid;
 			blen += skip + solid; btex += solid;
 			if (!((shade_runs >> r) & 1u)) continue;
-			const unsigned jw = shade[r * 32 + gl];
-			int y = (int)(jw & 0xffffu);
-			const int n = (int)((jw >> 16) & 15u);
-			unsigned clear = jw >> 20;
+			const uint2 jw = reinterpret_cast<const uint2*>(shade)[r * 32 + gl];
+			int y = (int)(jw.x & 0xffffu);
+			const int n = (int)(jw.x >> 16);
+			unsigned clear = jw.y;
 			// interpolants (Cuda_Render.h:645-680)
 			const float ft = (float)top, fb2 = (float)bot;
 			const float z1r = g0.pz + pz_add * ft, y1r = g0.py + py_add * ft;

@@ -126,14 +126,14 @@ k_traverse_f(const __grid_constant__ TraverseParams P, int rays)
 
 	// shared per warp: crossing records | live-column queue | DrawJob | RW x 32 projected runs (int2) |
 	//                  RW x 32 deferred short spans | occlusion bits
-	const int per_warp = (RLERC_F_REC + RLERC_F_QUEUE + 16 + RLERC_RW * 96 + P.mask_words + 3) & ~3;
+	const int per_warp = (RLERC_F_REC + RLERC_F_QUEUE + 16 + RLERC_PS_WORDS + P.mask_words + 3) & ~3;
 	uint32_t* wbase = smem + (size_t)wid * per_warp;
 	float4* rec = reinterpret_cast<float4*>(wbase);
 	uint32_t* queue = wbase + RLERC_F_REC;                           // [8][QCAP]
 	DrawJob* job = reinterpret_cast<DrawJob*>(wbase + RLERC_F_REC + RLERC_F_QUEUE);
 	int2* proj = reinterpret_cast<int2*>(wbase + RLERC_F_REC + RLERC_F_QUEUE + 16);
 	uint32_t* shade = wbase + RLERC_F_REC + RLERC_F_QUEUE + 16 + RLERC_RW * 64;
-	uint32_t* ymask = wbase + RLERC_F_REC + RLERC_F_QUEUE + 16 + RLERC_RW * 96;
+	uint32_t* ymask = wbase + RLERC_F_REC + RLERC_F_QUEUE + 16 + RLERC_PS_WORDS;
 
 	const int res_y = P.res_y;
 	const float res_y2 = (float)(res_y / 2);             // Cuda_Render.h:108 (integer division)
@@ -432,7 +432,7 @@ static void launch_f(const TraverseParams& p, cudaStream_t st)
 	const int rays = (p.slice_n > 1) ? owned_count(p.ray_end, p.slice_block, p.slice_n, p.slice_rank) : p.ray_end - p.ray_begin;
 	if (rays <= 0) return;
 	const int blocks = (rays + wpb - 1) / wpb;
-	const size_t smem = (size_t)wpb * ((RLERC_F_REC + RLERC_F_QUEUE + 16 + RLERC_RW * 96 + p.mask_words + 3) & ~3) * sizeof(uint32_t);
+	const size_t smem = (size_t)wpb * ((RLERC_F_REC + RLERC_F_QUEUE + 16 + RLERC_PS_WORDS + p.mask_words + 3) & ~3) * sizeof(uint32_t);
 	static size_t configured = 0;
 	if (smem > configured)
 	{

@@ -219,7 +219,7 @@ k_traverse_w(const __grid_constant__ TraverseParams P, int rays, int producer_bl
 
 	// shared per warp: 33 crossing records (float4) | DrawJob (16 words) | RW x 32 projected runs (int2) |
 	//                  RW x 32 deferred short spans | geometry of 3 batches | occlusion bits
-	const int per_warp = (RLERC_DDA_WORDS + 16 + RLERC_RW * 96 + 3 * 6 * 32 + P.mask_words + 3) & ~3;
+	const int per_warp = (RLERC_DDA_WORDS + 16 + RLERC_PS_WORDS + 3 * 6 * 32 + P.mask_words + 3) & ~3;
 	uint32_t* wbase = smem + (size_t)wid * per_warp;
 	float4* rec = reinterpret_cast<float4*>(wbase);                 // serial DDA: 33 crossing records
 	float4* trk = reinterpret_cast<float4*>(wbase);                 // merge-path DDA: 2 x 33 track states (same space)
@@ -227,8 +227,8 @@ k_traverse_w(const __grid_constant__ TraverseParams P, int rays, int producer_bl
 	DrawJob* job = reinterpret_cast<DrawJob*>(wbase + RLERC_DDA_WORDS);
 	int2* proj = reinterpret_cast<int2*>(wbase + RLERC_DDA_WORDS + 16);     // [r][lane] = {scr_y1, scr_y2}
 	uint32_t* shade = wbase + RLERC_DDA_WORDS + 16 + RLERC_RW * 64;         // [r][lane] deferred short spans
-	uint32_t* geo = wbase + RLERC_DDA_WORDS + 16 + RLERC_RW * 96;            // [3 batches][6 fields][lane]
-	uint32_t* ymask = wbase + RLERC_DDA_WORDS + 16 + RLERC_RW * 96 + 3 * 6 * 32;
+	uint32_t* geo = wbase + RLERC_DDA_WORDS + 16 + RLERC_PS_WORDS;            // [3 batches][6 fields][lane]
+	uint32_t* ymask = wbase + RLERC_DDA_WORDS + 16 + RLERC_PS_WORDS + 3 * 6 * 32;
 
 	const int res_y = P.res_y;
 	const float res_y2 = (float)(res_y / 2);             // Cuda_Render.h:108 (integer division)
@@ -533,7 +533,7 @@ static void launch_w(const TraverseParams& p, cudaStream_t st)
 	if (rays <= 0) return;
 	const int producers = (MODE == 1) ? (rays + RLERC_BLOCK - 1) / RLERC_BLOCK : 0;
 	const int blocks = producers + (rays + wpb - 1) / wpb;
-	const size_t smem = (size_t)wpb * ((RLERC_DDA_WORDS + 16 + RLERC_RW * 96 + 3 * 6 * 32 + p.mask_words + 3) & ~3) * sizeof(uint32_t);
+	const size_t smem = (size_t)wpb * ((RLERC_DDA_WORDS + 16 + RLERC_PS_WORDS + 3 * 6 * 32 + p.mask_words + 3) & ~3) * sizeof(uint32_t);
 	static size_t configured = 0;
 	if (smem > configured)
 	{
