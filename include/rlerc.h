@@ -75,7 +75,15 @@ typedef struct rlerc_frame_config {
 	int32_t z_far;              /* RAYS_DISTANCE                                         */
 	int32_t mip_distance;       /* MIP_DISTANCE                                          */
 	float   border;             /* RayMap::set_border, R/src/main.cpp:774                */
+	int32_t flags;              /* RLERC_FLAG_*: compile-time options of R/src/core.h as run-time switches (0 = shipped config) */
 } rlerc_frame_config;
+
+/* R/src/core.h:18 CLIPREGION: the scene is finite, columns outside the level-0 grid are skipped
+ * (R/src/Cuda_Render.h:432-437) instead of wrapping (infinite tiling). */
+#define RLERC_FLAG_CLIPREGION   1
+/* R/src/core.h:22 HEIGHT_COLOR: the low attribute byte is scaled by the camera height (R/src/Cuda_Render.h:674-676,716-722). */
+#define RLERC_FLAG_HEIGHT_COLOR 2
+/* Both are implemented by the production traversal kernel (lanes_per_ray = 0) only. */
 
 /* Defaults exactly as R/src/core.h for a W x H window: render_size=W, rays=4W,
  * z_far=80000, mip_distance=W, border=(1-H/W)/2 (=0.125 for 1024x768, main.cpp:774-776). */

@@ -95,8 +95,10 @@ def ref_host():
     return lib
 
 
-def ref_render(bench=False):
-    lib = _load("libref_render_bench.so" if bench else "libref_render.so")
+def ref_render(bench=False, flags=0):
+    """flags: 1 = built with -DCLIPREGION, 2 = -DHEIGHT_COLOR (R/src/core.h:18,22), 3 = both."""
+    name = {0: "libref_render.so", 1: "libref_render_clip.so", 2: "libref_render_hc.so", 3: "libref_render_cliphc.so"}[flags]
+    lib = _load("libref_render_bench.so" if bench else name)
     if not getattr(lib, "_typed", False):
         lib.ref_render_frame.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                          C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong)]
@@ -157,9 +159,9 @@ def ref_get_ray_map(pos, rot, border, rays_res):
     return rm
 
 
-def ref_render_frame(rm, res, mip_distance=None, z_far=80000, rays=None, threads=0, bench=False, fill=0):
+def ref_render_frame(rm, res, mip_distance=None, z_far=80000, rays=None, threads=0, bench=False, fill=0, flags=0):
     """Run the reference render_line over all rays; returns (warp uint32[rays,res], perf or None)."""
-    lib = ref_render(bench)
+    lib = ref_render(bench, flags)
     nrays = rm.map_line_count if rays is None else rays
     warp = np.full((max(nrays, 1), res), fill, dtype=np.uint32)
     perf = (C.c_longlong * 5)()
@@ -178,6 +180,7 @@ def port():
         lib.orc_build_map.argtypes = [C.c_void_p, C.c_ulonglong, C.c_int, C.c_int, C.c_void_p]
         lib.orc_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                    C.POINTER(C.c_longlong), C.c_int, C.c_int, C.c_int]
+        lib.orc_render_flags.argtypes = lib.orc_render.argtypes + [C.c_int]
         lib.orc_unwarp.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                    C.c_int, C.c_int]
         lib.orc_get_ray_map.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float, C.c_int, C.c_void_p]
@@ -208,13 +211,13 @@ def orc_build_map(slabs, sx, sz):
     return mp
 
 
-def orc_render(rm, res, rays_casted, mip_distance=None, z_far=80000, want_ids=False, threads=0, ray_begin=0, ray_end=-1):
+def orc_render(rm, res, rays_casted, mip_distance=None, z_far=80000, want_ids=False, threads=0, ray_begin=0, ray_end=-1, flags=0):
     """Returns (warp uint32[rays_casted,res], ids uint32[rays_casted,res,2] or None, counters dict)."""
     warp = np.zeros((rays_casted, res), np.uint32)
     ids = np.full((rays_casted, res, 2), 0xffffffff, np.uint32) if want_ids else None
     cnt = (C.c_longlong * 10)()
-    rc = port().orc_render(C.byref(rm), res, mip_distance or res, z_far, warp.ctypes.data,
-                           ids.ctypes.data if want_ids else None, cnt, ray_begin, ray_end, threads)
+    rc = port().orc_render_flags(C.byref(rm), res, mip_distance or res, z_far, warp.ctypes.data,
+                                 ids.ctypes.data if want_ids else None, cnt, ray_begin, ray_end, threads, flags)
     if rc:
         raise RuntimeError("orc_render rc=%d" % rc)
     return warp, ids, dict(zip(COUNTER_NAMES, list(cnt)))

@@ -95,7 +95,7 @@ struct Counters {   /* R/src/Cuda_Render.h:14-22 + byte-model terms (DESIGN.md Â
  * without DETAIL_BENCH, i.e. with the early return at :370).  y_cache: private occlusion
  * bitmask of >= res_y bits, zeroed in full by the caller.  ids: optional uint32[res_y][2]. */
 void render_line(const ORayMap& rm, int x, uint32_t* y_cache, int res_x, int res_y, int MIP_DISTANCE, int RAYS_DISTANCE,
-                 uint32_t* ofs_rgb_start, uint32_t* ids, Counters& cnt)
+                 uint32_t* ofs_rgb_start, uint32_t* ids, Counters& cnt, int flags)
 {
 	const V3 viewpos = rm.position, viewrot = rm.rotation;
 	const float res_x2 = res_x / 2;                      /* :107-108 integer division */
@@ -249,6 +249,13 @@ void render_line(const ORayMap& rm, int x, uint32_t* y_cache, int res_x, int res
 		const float view_space_x = ray_x * dds_dist_before, view_space_z = ray_z * dds_dist_before;
 		const int voxel_x = f2i(viewpos.x + pos_before_x) + fix_x;                       /* :429-430 */
 		const int voxel_z = f2i(viewpos.z + pos_before_y) + fix_z;
+		if (flags & 1)                                                                   /* CLIPREGION :432-437 */
+		{
+			if (voxel_x < 0) continue;
+			if (voxel_z < 0) continue;
+			if ((voxel_x >> mip_lvl) > rle4_gridx - 1) continue;
+			if ((voxel_z >> mip_lvl) > rle4_gridz - 1) continue;
+		}
 		const int vx = (voxel_x >> mip_lvl) & (rle4_gridx - 1);                          /* :441-442 */
 		const int vz = (voxel_z >> mip_lvl) & (rle4_gridz - 1);
 		const float mountain = viewpos.y;
@@ -324,6 +331,7 @@ void render_line(const ORayMap& rm, int x, uint32_t* y_cache, int res_x, int res
 			onedz2 /= scr_y2r - scr_y1r;
 			cnt.elems_rendered++;
 
+			const int height_color = f2i(4095 - mountain + viewpos.y);                    /* HEIGHT_COLOR :675 (float arithmetic, int target) */
 			const float mult = y + 1 - scr_y1r;                                            /* :678-680 */
 			float uz = u1z + u2dz * mult;
 			float onez = onez1 + onedz2 * mult;
@@ -339,7 +347,15 @@ void render_line(const ORayMap& rm, int x, uint32_t* y_cache, int res_x, int res
 				ui = ui < hi ? ui : hi;
 				const uint32_t u = ui;
 				const uint32_t real_z = f2i(float(1 / onez)) & 0xfffe;
-				const uint32_t color16 = send[u];
+				uint32_t color16 = send[u];
+				if (flags & 2)                                                               /* HEIGHT_COLOR :716-722 */
+				{
+					const uint16_t colorpal = color16 & 0xff00;
+					int v = (int)(((color16 & 0xff) * (uint32_t)height_color) >> 12);       /* uint * int is unsigned */
+					v = v > 0 ? v : 0;                                                       /* int max / min of R/inc/cutil_math.h:48-56 */
+					v = v < 255 ? v : 255;
+					color16 = (uint32_t)v | colorpal;
+				}
 				ofs_rgb_start[y] = color16 + (real_z << 16);
 				if (ids) { ids[y * 2] = (uint32_t)(vx + vz * rle4_gridx); ids[y * 2 + 1] = ((uint32_t)mip_lvl << 16) | u; }
 				cnt.pixels++;
@@ -385,8 +401,18 @@ int orc_build_map(const uint16_t* slabs, unsigned long long slabs_size, int sx, 
 /* All ray planes [ray_begin, ray_end) of one frame, as cudaRender does (R/src/Cuda_Main.cu:150-181).
  * raymap: RayMap_GPU bytes with HOST pointers in map4_gpu.  warp: uint32[rays][res]; ids: optional
  * uint32[rays][res][2]; counters: optional long long[10]. */
+int orc_render_flags(const void* raymap, int res, int mip_distance, int z_far, uint32_t* warp, uint32_t* ids,
+                     long long* counters, int ray_begin, int ray_end, int threads, int flags);
+
 int orc_render(const void* raymap, int res, int mip_distance, int z_far, uint32_t* warp, uint32_t* ids,
                long long* counters, int ray_begin, int ray_end, int threads)
+{
+	return orc_render_flags(raymap, res, mip_distance, z_far, warp, ids, counters, ray_begin, ray_end, threads, 0);
+}
+
+/* flags: 1 = CLIPREGION, 2 = HEIGHT_COLOR (R/src/core.h:18,22) */
+int orc_render_flags(const void* raymap, int res, int mip_distance, int z_far, uint32_t* warp, uint32_t* ids,
+                     long long* counters, int ray_begin, int ray_end, int threads, int flags)
 {
 	const ORayMap& rm = *(const ORayMap*)raymap;
 	if (ray_end < 0 || ray_end > rm.map_line_count) ray_end = rm.map_line_count;
@@ -407,7 +433,7 @@ int orc_render(const void* raymap, int res, int mip_distance, int z_far, uint32_
 		{
 			memset(mask, 0, words * sizeof(uint32_t));
 			render_line(rm, x, mask, res, res, mip_distance, z_far, warp + (size_t)x * res,
-			            ids ? ids + (size_t)x * res * 2 : 0, c);
+			            ids ? ids + (size_t)x * res * 2 : 0, c, flags);
 		}
 		#pragma omp critical
 		{

@@ -58,7 +58,8 @@ class FrameConfig(C.Structure):
     """The compile-time constants of R/src/core.h:3-10 as run-time fields."""
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("render_size", C.c_int32),
                 ("rays_casted", C.c_int32), ("rays_casted_res", C.c_int32), ("z_far", C.c_int32),
-                ("mip_distance", C.c_int32), ("border", C.c_float)]
+                ("mip_distance", C.c_int32), ("border", C.c_float), ("flags", C.c_int32)]
+    CLIPREGION, HEIGHT_COLOR = 1, 2      # R/src/core.h:18,22 as run-time switches
 
     @classmethod
     def default(cls, width, height):

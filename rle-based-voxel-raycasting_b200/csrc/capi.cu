@@ -102,7 +102,8 @@ int check_cfg(const rlerc_frame_config* cfg)
 {
 	if (!cfg) { set_error("null frame config"); return RLERC_ERR_ARG; }
 	if (cfg->width < 4 || cfg->height < 1 || cfg->render_size < 32 || cfg->render_size > 16384 ||
-	    cfg->rays_casted < 4 || cfg->rays_casted_res < 4 || cfg->z_far < 1 || cfg->mip_distance < 1)
+	    cfg->rays_casted < 4 || cfg->rays_casted_res < 4 || cfg->z_far < 1 || cfg->mip_distance < 1 ||
+	    (cfg->flags & ~(RLERC_FLAG_CLIPREGION | RLERC_FLAG_HEIGHT_COLOR)) != 0)
 	{
 		set_error("frame config out of range");
 		return RLERC_ERR_ARG;
@@ -145,6 +146,7 @@ int fill_traverse(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_config
 	if (ray_begin < 0) ray_begin = 0;
 	P.ray_begin = ray_begin; P.ray_end = ray_end;
 	P.mask_words = (cfg->render_size + 31) / 32 + 1;
+	P.flags = cfg->flags;
 	P.warp = d_warp;
 	P.slice_block = 1; P.slice_n = 1; P.slice_rank = 0;
 	return RLERC_OK;
@@ -355,6 +357,11 @@ static int render_impl(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_c
 	}
 	TraverseParams P;
 	if ((rc = fill_traverse(c, rm, cfg, ray_begin, ray_end, d_warp, P))) return rc;
+	if (cfg->flags != 0 && !(c->lanes == 0 || c->lanes == 65))
+	{
+		set_error("frame config flags (CLIPREGION / HEIGHT_COLOR) are implemented by the production traversal kernel only (lanes_per_ray = 0)");
+		return RLERC_ERR_ARG;
+	}
 	if (slice_n > 1) { P.slice_block = slice_block; P.slice_n = slice_n; P.slice_rank = slice_rank; P.ray_begin = 0; }
 	if (ids)
 	{

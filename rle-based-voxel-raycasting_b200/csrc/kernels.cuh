@@ -34,6 +34,7 @@ struct TraverseParams {
 	// interleaved multi-GPU slices: ray r belongs to this launch iff (r / slice_block) % slice_n == slice_rank
 	int slice_block, slice_n, slice_rank;
 	int mask_words;          // per-ray occlusion bitmask size in 32-bit words
+	int flags;               // RLERC_FLAG_CLIPREGION | RLERC_FLAG_HEIGHT_COLOR (include/rlerc.h; k_traverse_f only)
 	uint32_t* warp;          // [rays_casted][res_y]
 	uint32_t* ids;           // optional [rays_casted][res_y][2]
 	unsigned long long* counters; // optional [10]

@@ -536,6 +536,7 @@ void rlerc_frame_config_default(int width, int height, rlerc_frame_config* out)
 	out->z_far = 80000;
 	out->mip_distance = width;
 	out->border = (1.0f - (float)height / (float)width) * 0.5f;
+	out->flags = 0;
 }
 
 int rlerc_frame_setup(const float pos[3], const float rot[3], const rlerc_frame_config* cfg, rlerc_raymap* out)

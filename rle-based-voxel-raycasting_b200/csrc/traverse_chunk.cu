@@ -206,7 +206,7 @@ k_traverse_c(const __grid_constant__ TraverseParams P, int rays)
 	RayCtx R;
 	R.row = row; R.ymask = ymask; R.ids = (IDS && has_row) ? P.ids + (size_t)x * res_y * 2 : nullptr;
 	R.res_y2 = res_y2; R.pz_add = pz_add; R.py_add = py_add; R.mountain = mountain; R.gl = gl;
-	R.stat = nullptr;
+	R.stat = nullptr; R.hc_on = 0; R.hc = 0;
 
 	FilterSet fa, fb;                  // two filter batches in flight
 	fa.g.pz = fa.g.py = fa.g.czz = fa.g.cyy = 0; fa.g.cmip = 0; fa.g.cidx = 0;

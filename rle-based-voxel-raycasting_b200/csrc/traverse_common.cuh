@@ -47,6 +47,17 @@ __device__ __forceinline__ unsigned run_word(const unsigned (&rw)[4], int r)
 // the n lowest bits (0 <= n <= 32)
 __device__ __forceinline__ unsigned row_bits(int n) { return n >= 32 ? 0xffffffffu : ((1u << n) - 1u); }
 
+// HEIGHT_COLOR (Cuda_Render.h:716-722): the low attribute byte scaled by height_color >> 12, clamped to a byte, the
+// high byte kept.  The product is unsigned as in the reference (uint * int), the clamp is the int min/max.
+__device__ __forceinline__ unsigned height_color16(unsigned color16, int hc)
+{
+	const unsigned pal = color16 & 0xff00u;
+	int v = (int)(((color16 & 0xffu) * (unsigned)hc) >> 12);
+	v = v > 0 ? v : 0;
+	v = v < 255 ? v : 255;
+	return (unsigned)v | pal;
+}
+
 // bits [lo, hi) of one 32-bit word, lo / hi clamped to the word (empty when hi <= 0 or lo >= 32 or hi <= lo)
 __device__ __forceinline__ unsigned bit_range(int lo, int hi)
 {
@@ -64,6 +75,7 @@ struct RayCtx {
 	uint32_t* ids;           // IDS build: id words of this ray plane's row, else null
 	float res_y2, pz_add, py_add, mountain;
 	int gl;
+	int hc_on, hc;           // HEIGHT_COLOR (R/src/core.h:22): on/off, height_color (Cuda_Render.h:675)
 	long long* stat;         // STATS build: [0] batches [1] B0 taken [2] B1 taken [3] event-loop iterations [4..10] B1 fail reasons [12..15] cycles in B0, B1, event loop, S
 };
 
@@ -110,7 +122,9 @@ __device__ __noinline__ int coop_span(const RayCtx& R, const uint16_t* send, flo
 			ui = (ui > rtex) ? ui : rtex;
 			ui = (ui < tex_hi) ? ui : tex_hi;
 			const unsigned real_z = (unsigned)f2i(1.0f / monez) & 0xfffeu;
-			R.row[yy] = (unsigned)__ldg(send + ui) + (real_z << 16);
+			unsigned c16 = (unsigned)__ldg(send + ui);
+			if (R.hc_on) c16 = height_color16(c16, R.hc);
+			R.row[yy] = c16 + (real_z << 16);
 			if (IDS) { R.ids[yy * 2] = (uint32_t)colid; R.ids[yy * 2 + 1] = ((uint32_t)m << 16) | (uint32_t)ui; }
 		}
 		const unsigned wb = __ballot_sync(FULL, wr);
@@ -168,7 +182,9 @@ static __device__ __noinline__ void coop_span_claim(const RayCtx& R, const uint1
 			ui = (ui > rtex) ? ui : rtex;
 			ui = (ui < tex_hi) ? ui : tex_hi;
 			const unsigned real_z = (unsigned)f2i(1.0f / monez) & 0xfffeu;
-			R.row[yy] = (unsigned)__ldg(send + ui) + (real_z << 16);
+			unsigned c16 = (unsigned)__ldg(send + ui);
+			if (R.hc_on) c16 = height_color16(c16, R.hc);
+			R.row[yy] = c16 + (real_z << 16);
 		}
 	}
 }
@@ -929,7 +945,7 @@ __device__ __forceinline__ bool consume_batch(const TraverseParams& P, const Ray
 				}
 				#pragma unroll
 				for (int k = 0; k < 4; k++)
-					if (k0 + k < n && ((clear >> k) & 1u)) row[y + k] = colr[k] + (zz[k] << 16);
+					if (k0 + k < n && ((clear >> k) & 1u)) row[y + k] = (R.hc_on ? height_color16(colr[k], R.hc) : colr[k]) + (zz[k] << 16);
 				y += 4; clear >>= 4;
 			}
 		}

@@ -186,6 +186,8 @@ k_traverse_f(const __grid_constant__ TraverseParams P, int rays)
 	R.row = row; R.ymask = ymask; R.ids = (IDS && !PROF) ? P.ids + (size_t)x * res_y * 2 : nullptr;
 	R.res_y2 = res_y2; R.pz_add = pz_add; R.py_add = py_add; R.mountain = mountain; R.gl = gl;
 	R.stat = PROF ? stat : nullptr;
+	R.hc_on = (P.flags & 2) ? 1 : 0;
+	R.hc = f2i((4095.0f - mountain) + P.viewpos[1]);              // int height_color = 4095-mountain+viewpos.y (Cuda_Render.h:675)
 
 	// filter: the batch whose pointer-map gather is in flight
 	Geo fg;
@@ -276,6 +278,8 @@ k_traverse_f(const __grid_constant__ TraverseParams P, int rays)
 				const int voxel_x = f2i(vpx + ra.y) + fix_x;             // Cuda_Render.h:429-430
 				const int voxel_z = f2i(vpz + ra.z) + fix_z;
 				const int gx = P.level[fg.cmip].sx, gz = P.level[fg.cmip].sz;
+				// CLIPREGION (Cuda_Render.h:432-437): finite scene, columns outside the grid are skipped
+				const bool outside = (P.flags & 1) && (voxel_x < 0 || voxel_z < 0 || (voxel_x >> fg.cmip) > gx - 1 || (voxel_z >> fg.cmip) > gz - 1);
 				const int vx = (voxel_x >> fg.cmip) & (gx - 1);          // Cuda_Render.h:441-442
 				const int vz = (voxel_z >> fg.cmip) & (gz - 1);
 				fg.cidx = vx + vz * gx;
@@ -288,7 +292,7 @@ k_traverse_f(const __grid_constant__ TraverseParams P, int rays)
 				fg.cyy *= rx2mr;
 				// The horizon only rises.  For pz > 0 a column culled now stays culled; for pz <= 0 (or NaN)
 				// the test can flip, so keep those.
-				fhave = !(fg.pz * res_y2 + fg.py <= fg.pz * (float)Hs.ycmin) || !(fg.pz > 0);   // Cuda_Render.h:467
+				fhave = !outside && (!(fg.pz * res_y2 + fg.py <= fg.pz * (float)Hs.ycmin) || !(fg.pz > 0));   // Cuda_Render.h:467
 				if (fhave)
 				{
 					const uint2 ent = __ldg(P.level[fg.cmip].map + fg.cidx);         // Cuda_Render.h:474-478

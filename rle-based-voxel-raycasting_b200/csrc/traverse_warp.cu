@@ -304,7 +304,7 @@ k_traverse_w(const __grid_constant__ TraverseParams P, int rays, int producer_bl
 
 	RayCtx R;
 	R.row = row; R.ymask = ymask; R.ids = IDS ? P.ids + (size_t)x * res_y * 2 : nullptr;
-	R.res_y2 = res_y2; R.pz_add = pz_add; R.py_add = py_add; R.mountain = mountain; R.gl = gl; R.stat = nullptr;
+	R.res_y2 = res_y2; R.pz_add = pz_add; R.py_add = py_add; R.mountain = mountain; R.gl = gl; R.stat = nullptr; R.hc_on = 0; R.hc = 0;
 
 	while (true)
 	{

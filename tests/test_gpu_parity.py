@@ -429,3 +429,32 @@ def test_production_build_equals_instrumented_build_up_to_8k(R, rb, gpu):
                 assert np.array_equal(prod[r0:r1], want[r0:r1]), (wh, t)
                 del prod, inst, want
     gpu.set_lanes_per_ray(0)
+
+
+@pytest.mark.parametrize("flags", [1, 2, 3])
+def test_core_h_options_clipregion_height_color(R, rb, gpu, scene_small, scene_mid, flags):
+    """The reference's CLIPREGION / HEIGHT_COLOR compile-time options (R/src/core.h:18,22) as run-time flags of the
+    frame config: production kernel == oracle, bit for bit; other kernel variants refuse them."""
+    cams = [((64.5, -60.0, 64.5), (0.5, 0.8, 0.0)), ((3.25, -40.0, 120.5), (0.3, 2.4, 0.0)),
+            ((-50.0, -80.0, -50.0), (0.45, 0.785 + 1.5708, 0.0)), ((300.0, -120.0, 64.0), (0.4, 4.71, 0.0)),
+            ((10000.0, -100.0, 10000.0), (0.4, 1.9, 0.0))]
+    gpu.set_lanes_per_ray(0)
+    for scene in (scene_small, scene_mid):
+        gpu.all_to_gpu(scene)
+        for wh in ((512, 384), (1920, 1080)):
+            cfg = R.FrameConfig.default(*wh)
+            cfg.flags = flags
+            for pos, rot in cams:
+                rm = R.RayMap(cfg).get_ray_map(pos, rot)
+                orm = oracle_raymap(rb, rm, scene)
+                want, _, _ = rb.orc_render(orm, cfg.render_size, cfg.rays_casted, cfg.mip_distance, cfg.z_far, flags=flags)
+                _fresh_warp(gpu, cfg)
+                gpu.render(rm, cfg)
+                got = gpu.read_warp(cfg)
+                assert np.array_equal(got, want), (flags, wh, pos, int((got != want).sum()))
+    cfg = R.FrameConfig.default(512, 384)
+    cfg.flags = flags
+    gpu.set_lanes_per_ray(64)
+    with pytest.raises(R.RlercError):
+        gpu.render(R.RayMap(cfg).get_ray_map(*cams[0]), cfg)
+    gpu.set_lanes_per_ray(0)

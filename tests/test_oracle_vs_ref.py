@@ -112,3 +112,26 @@ def test_loader_equals_reference(R, rb, need_ref, scene_mid, tmp_path):
     g = str(tmp_path / "r.rle4")
     ref.save(g)
     assert open(f, "rb").read() == open(g, "rb").read()
+
+
+# cameras for the finite-scene option: inside the grid, at its edge, outside looking in, far outside
+CLIP_CAMERAS = [((64.5, -60.0, 64.5), (0.5, 0.8, 0.0)), ((3.25, -40.0, 120.5), (0.3, 2.4, 0.0)),
+                ((-50.0, -80.0, -50.0), (0.45, 0.785 + 1.5708, 0.0)), ((300.0, -120.0, 64.0), (0.4, 4.71, 0.0)),
+                ((10000.0, -100.0, 10000.0), (0.4, 1.9, 0.0))]
+
+
+@pytest.mark.parametrize("flags", [1, 2, 3])
+def test_render_line_port_equals_reference_with_core_h_options(R, rb, need_ref, scene_small, flags):
+    """R/src/core.h:18,22: CLIPREGION (finite scene) and HEIGHT_COLOR, compiled into the reference with -D and
+    switched at run time in the port (flags bit 0 / bit 1)."""
+    cfg = R.FrameConfig.default(512, 384)
+    drew = 0
+    for pos, rot in CLIP_CAMERAS + few_cameras(-40.0)[:2]:
+        rm = R.RayMap(cfg).get_ray_map(pos, rot)
+        orm = oracle_raymap(rb, rm, scene_small)
+        ref, _ = rb.ref_render_frame(orm, cfg.render_size, mip_distance=cfg.mip_distance, z_far=cfg.z_far, rays=cfg.rays_casted, flags=flags)
+        port, _, cnt = rb.orc_render(orm, cfg.render_size, cfg.rays_casted, cfg.mip_distance, cfg.z_far, flags=flags)
+        assert np.array_equal(ref, port), (flags, pos, rot)
+        plain, _, _ = rb.orc_render(orm, cfg.render_size, cfg.rays_casted, cfg.mip_distance, cfg.z_far)
+        drew += int(cnt["pixels"] > 0 and not np.array_equal(plain, port))
+    assert drew >= 3          # the options change the picture on most of these cameras
