@@ -95,6 +95,7 @@ class ClockSampler(threading.Thread):
 
     def summary(self):
         self.stop_flag = True
+        self.join(timeout=6.0)          # a query that overlapped a very short timed region still counts
         sm = sorted(int(r[1]) for r in self.rows if r[1].isdigit())
         mx = [int(r[2]) for r in self.rows if r[2].isdigit()]
         reasons = set()
@@ -383,7 +384,7 @@ def main():
         r2.set_lanes_per_ray(args.lanes)
         DEPTH = int(os.environ.get("RLERC_E2E_DEPTH", "4"))          # frames in flight (rlerc_frame_submit pipelines up to RLERC_FRAME_SLOTS)
         pins = [R.PinnedBuffer((HH, WW, 4)) for _ in range(DEPTH)]
-        for i in range(W):
+        for i in range(max(W, 8)):      # every frame slot (stream, warped buffer, RGBA buffer) exists before the timed region
             r2.frame_wait(r2.frame_submit(poses[i % K][0], poses[i % K][1], cfg, pins[i % DEPTH].array))
         r2.sync()
         t0 = time.perf_counter()
