@@ -37,6 +37,7 @@ WORKLOADS = {
     "imrodh768": (0, (1024, 1024, 1024), 1, (1024, 768), "BASELINE config 1 window: 1024x768"),
     "tiled4k": (0, (512, 512, 512), 16, (3840, 2160), "BASELINE config 3: 16x16 physical tiling (multi-GB RLE) at 3840x2160"),
     "shortrun4k": (1, (2048, 1024, 2048), 1, (3840, 2160), "BASELINE config 4 (reduced footprint): worst-case short-run band at 3840x2160"),
+    "shortrun16k": (2, (16384, 1024, 16384), 1, (3840, 2160), "BASELINE config 4 at full size: 16384 x 1024 x 16384 heightfield + cave floors + worst-case short-run band (rlerc_synth_rle, ~5.5 GB of RLE incl. mips) at 3840x2160"),
     "view8k": (0, (512, 512, 512), 16, (7680, 4320), "BASELINE config 5: 7680x4320 views of the tiled scene (N > 1, --mp frames: one camera per GPU, NVLink gather to rank 0)"),
     "small": (0, (256, 256, 256), 1, (1024, 768), "quick functional run"),
 }
@@ -64,8 +65,11 @@ def build_scene(R, workload, log):
         scene, name = R.RLE4.load(path), "Imrodh.rle4"
         sy = scene.level(0)[1]
     else:
-        scene = R.RLE4.synth(kind, sx, sy, sz, seed=1 if kind == 0 else 42)
-        name = "synth_%s_%dx%dx%d" % ("imrodh" if kind == 0 else "shortrun", sx, sy, sz)
+        if kind == 2:
+            scene = R.RLE4.synth_rle(sx, sy, sz, seed=42, band_every=48)
+        else:
+            scene = R.RLE4.synth(kind, sx, sy, sz, seed=1 if kind == 0 else 42)
+        name = "synth_%s_%dx%dx%d" % ({0: "imrodh", 1: "shortrun", 2: "rle_shortrun"}[kind], sx, sy, sz)
         if tiling > 1:
             scene = scene.tile(tiling, tiling)
             name += "_tiled%dx%d" % (tiling, tiling)

@@ -122,6 +122,10 @@ int  rlerc_scene_tile(const rlerc_scene* s, int nx, int nz, rlerc_scene** out);
  * kind 0: terrain + boulders + caves ("synth_imrodh"); kind 1: worst-case short-run band. */
 int  rlerc_synth_volume(int kind, int sx, int sy, int sz, uint32_t seed,
                         uint8_t* voxel, uint8_t* col1, uint8_t* col2);
+/* Heightfield + cave floors + worst-case short-run band (one column in band_every, 32 runs of one voxel) written
+ * straight into the .rle4 layout, all mip levels: BASELINE config 4 at its full size (16384 x 1024 x 16384) without
+ * a 32 GiB bit volume.  Sizes: powers of two, sy <= 1024. */
+int  rlerc_synth_rle(int sx, int sy, int sz, uint32_t seed, int band_every, rlerc_scene** out);
 
 /* ---- context / device scene: replaces gpu_malloc + RLE4::all_to_gpu ----------------- */
 

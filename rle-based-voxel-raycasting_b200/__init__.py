@@ -88,6 +88,7 @@ _SIGS = {
     "rlerc_scene_compress": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
     "rlerc_scene_tile": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_P)]),
     "rlerc_synth_volume": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, _P, _P, _P]),
+    "rlerc_synth_rle": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_int, C.POINTER(_P)]),
     "rlerc_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
     "rlerc_destroy": (None, [_P]),
     "rlerc_scene_upload": (C.c_int, [_P, _P]),
@@ -205,6 +206,13 @@ class RLE4:
         _check(lib().rlerc_synth_volume(kind, sx, sy, sz, seed, v.ctypes.data,
                                         c1.ctypes.data if color else None, c2.ctypes.data if color else None))
         return cls.compress_all(v, sx, sy, sz, c1, c2)
+
+    @classmethod
+    def synth_rle(cls, sx, sy, sz, seed=42, band_every=32):
+        """Heightfield + short-run band written straight into RLE (BASELINE config 4 at full size)."""
+        s = cls()
+        _check(lib().rlerc_synth_rle(sx, sy, sz, seed, band_every, C.byref(s._h)))
+        return s
 
     def tile(self, nx, nz):
         s = RLE4()

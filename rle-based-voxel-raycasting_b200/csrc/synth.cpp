@@ -116,3 +116,128 @@ extern "C" int rlerc_synth_volume(int kind, int sx, int sy, int sz, uint32_t see
 	}
 	return RLERC_OK;
 }
+
+
+// ---- direct-to-RLE scene: BASELINE config 4 at its full size ---------------------------------------------------------
+// A 16384 x 1024 x 16384 bit volume would be 32 GiB, so this scene is written column by column straight into the
+// .rle4 layout ([n_runs][n_vox][runs][attr16 x n_vox], run = solid << 10 | skip, split as R/src/Rle4.cpp:166-182),
+// every mip level from the same functions of the level-0 coordinates:
+//   * periodic 4-octave heightfield in [sy/4, 3*sy/4], a crust of 2 surface voxels;
+//   * one column in `band_every`: the worst-case short-run band, 32 runs of one solid voxel / one air voxel under
+//     the crust (halved per mip level) — as many runs per column as the per-level ushort budget of the format allows
+//     on average (slabs_size is an int32 count of ushorts, R/src/Rle4.cpp:237);
+//   * a cave floor two voxels thick under a noise threshold;
+//   * attribute = hash(x, y, z) & 0x3ff.
+namespace {
+
+inline int height_at(int X, int Z, int sx, int sy, uint32_t seed)
+{
+	const int cell0 = sx / 4 > 8 ? sx / 4 : 8;
+	uint64_t acc = 0, wsum = 0;
+	for (int o = 0; o < 4; o++)
+	{
+		const int cell = (cell0 >> (2 * o)) > 2 ? (cell0 >> (2 * o)) : 2;
+		const int period = sx / cell > 1 ? sx / cell : 1;
+		const uint32_t w = 8u >> o;
+		acc += (uint64_t)vnoise2(X, Z, cell, period, seed + 17 * o) * w;
+		wsum += 65535ull * w;
+	}
+	return sy / 4 + (int)(acc * (uint64_t)(sy / 2) / wsum);
+}
+
+inline void push_run(std::vector<uint16_t>& runs, int& skip, int solid)
+{
+	while (skip > 1023) { runs.push_back(1023); skip -= 1023; }                        // Rle4.cpp:168-172
+	while (solid > 63) { runs.push_back((uint16_t)(63 * 1024 + (skip & 1023))); solid -= 63; skip = 0; }
+	runs.push_back((uint16_t)((solid & 63) * 1024 + (skip & 1023)));
+	skip = 0;
+}
+
+// one column of level m at level coordinates (x, z), appended to `out`
+void gen_column(int m, int x, int z, int sx0, int sy0, uint32_t seed, int band_every, std::vector<uint16_t>& out,
+                std::vector<uint16_t>& runs, std::vector<uint16_t>& attrs)
+{
+	const int X = x << m, Z = z << m, sym = sy0 >> m;
+	const int hm = height_at(X, Z, sx0, sy0, seed) >> m;
+	runs.clear(); attrs.clear();
+	int y = 0, skip = 0;                       // y: next voxel not yet encoded
+	auto solid_span = [&](int a, int b)       // [a, b) solid, a >= y
+	{
+		if (b > sym) b = sym;
+		if (a < y) a = y;
+		if (b <= a) return;
+		skip += a - y;
+		push_run(runs, skip, b - a);
+		for (int v = a; v < b; v++) attrs.push_back((uint16_t)(hash3((uint32_t)X, (uint32_t)(v << m), (uint32_t)Z, seed) & 0x3ffu));
+		y = b;
+	};
+	solid_span(hm, hm + 2);
+	if (band_every > 0 && (hash3((uint32_t)X, 3u, (uint32_t)Z, seed ^ 0x5bd1u) % (uint32_t)band_every) == 0)
+	{
+		const int nb = 32 >> m;
+		for (int k = 0; k < nb; k++) solid_span(hm + 3 + 2 * k, hm + 4 + 2 * k);
+	}
+	if (vnoise2(X, Z, 64, sx0 / 64 > 1 ? sx0 / 64 : 1, seed + 99) > 40000u)
+	{
+		const int cf = hm + (96 >> m) + 4;
+		solid_span(cf, cf + 2);
+	}
+	out.push_back((uint16_t)runs.size());
+	out.push_back((uint16_t)attrs.size());
+	out.insert(out.end(), runs.begin(), runs.end());
+	out.insert(out.end(), attrs.begin(), attrs.end());
+}
+
+} // namespace
+
+extern "C" int rlerc_synth_rle(int sx, int sy, int sz, uint32_t seed, int band_every, rlerc_scene** out)
+{
+	auto pow2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
+	if (!out || !pow2(sx) || !pow2(sz) || !pow2(sy) || sx < 64 || sz < 64 || sy < 64 || sy > 1024 || band_every < 0)
+	{
+		rlerc::set_error("rlerc_synth_rle: sizes must be powers of two, sx, sz >= 64, 64 <= sy <= 1024");
+		return RLERC_ERR_ARG;
+	}
+	*out = nullptr;
+	rlerc_scene* sc = new rlerc_scene();
+	for (int m = 0; m < 16 && (sx >> m) >= 8 && (sz >> m) >= 8 && (sy >> m) >= 8; m++)
+	{
+		const int lx = sx >> m, ly = sy >> m, lz = sz >> m;
+		std::vector<std::vector<uint16_t>> rows((size_t)lz);
+		#pragma omp parallel
+		{
+			std::vector<uint16_t> runs, attrs;
+			#pragma omp for schedule(dynamic, 8)
+			for (int z = 0; z < lz; z++)
+			{
+				std::vector<uint16_t>& r = rows[(size_t)z];
+				r.reserve((size_t)lx * 8);
+				for (int x = 0; x < lx; x++) gen_column(m, x, z, sx, sy, seed, band_every, r, runs, attrs);
+			}
+		}
+		uint64_t total = 0;
+		for (const auto& r : rows) total += r.size();
+		if (total >= 0x7fffffffull)
+		{
+			delete sc;
+			rlerc::set_error("rlerc_synth_rle: level %d needs %llu ushorts, the format holds 2^31-1 per level (R/src/Rle4.cpp:237)", m, (unsigned long long)total);
+			return RLERC_ERR_ARG;
+		}
+		sc->levels.emplace_back();
+		rlerc::Level& lv = sc->levels.back();
+		lv.sx = lx; lv.sy = ly; lv.sz = lz;
+		lv.slabs.resize((size_t)total);
+		std::vector<uint64_t> base((size_t)lz + 1, 0);
+		for (int z = 0; z < lz; z++) base[(size_t)z + 1] = base[(size_t)z] + rows[(size_t)z].size();
+		#pragma omp parallel for schedule(dynamic, 8)
+		for (int z = 0; z < lz; z++)
+		{
+			memcpy(lv.slabs.data() + base[(size_t)z], rows[(size_t)z].data(), rows[(size_t)z].size() * sizeof(uint16_t));
+			std::vector<uint16_t>().swap(rows[(size_t)z]);
+		}
+		const int rc = rlerc::build_pointer_map(lv);
+		if (rc) { delete sc; return rc; }
+	}
+	*out = sc;
+	return RLERC_OK;
+}

@@ -53,3 +53,11 @@ def scene_mid(R):
 def scene_runs(R):
     """128^3 worst-case short-run band: columns with up to ~64 runs (exercises the long-column path)."""
     return R.RLE4.synth(1, 128, 128, 128, seed=42)
+
+
+@pytest.fixture(scope="session")
+def scene_rle(R):
+    """256^3 heightfield written straight into RLE (rlerc_synth_rle): crust, cave floors, one column in 8 with the
+    32-run short-run band; the small sibling of BASELINE config 4's 16384 x 1024 x 16384 scene."""
+    return R.RLE4.synth_rle(256, 256, 256, seed=42, band_every=8)
+

@@ -91,17 +91,19 @@ def test_dda_variants_bit_exact(R, rb, gpu, scene_mid, variant):
 
 
 @pytest.mark.parametrize("lanes", [0, 32])
-def test_warp_buffer_bit_exact_short_run_scene(R, rb, gpu, scene_runs, lanes):
-    """Columns with dozens of runs: the lane<->run path."""
-    gpu.all_to_gpu(scene_runs)
+def test_warp_buffer_bit_exact_short_run_scene(R, rb, gpu, scene_runs, scene_rle, lanes):
+    """Columns with dozens of runs: the lane<->run path.  Both worst-case scenes: the compressed bit volume and the
+    one written straight into RLE (the small sibling of BASELINE config 4's full-size scene)."""
     gpu.set_lanes_per_ray(lanes)
     cfg = R.FrameConfig.default(512, 384)
-    for pos, rot in few_cameras(-90.0):
-        rm = R.RayMap(cfg).get_ray_map(pos, rot)
-        _, want, _, _ = _oracle(rb, rm, scene_runs, cfg)
-        _fresh_warp(gpu, cfg)
-        gpu.render(rm, cfg)
-        assert np.array_equal(gpu.read_warp(cfg), want), (lanes, rot)
+    for scene, h in ((scene_runs, -90.0), (scene_rle, -30.0)):
+        gpu.all_to_gpu(scene)
+        for pos, rot in few_cameras(h):
+            rm = R.RayMap(cfg).get_ray_map(pos, rot)
+            _, want, _, _ = _oracle(rb, rm, scene, cfg)
+            _fresh_warp(gpu, cfg)
+            gpu.render(rm, cfg)
+            assert np.array_equal(gpu.read_warp(cfg), want), (lanes, h, rot)
     gpu.set_lanes_per_ray(0)
 
 

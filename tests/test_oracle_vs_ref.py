@@ -34,8 +34,8 @@ def test_render_line_port_equals_reference_on_camera_grid(R, rb, need_ref, scene
         assert np.all(has_id[(port != 0) & (port != 0xff8844)])
 
 
-def test_render_line_port_equals_reference_other_scenes(R, rb, need_ref, scene_small, scene_runs):
-    for scene, h in ((scene_small, -40.0), (scene_runs, -90.0)):
+def test_render_line_port_equals_reference_other_scenes(R, rb, need_ref, scene_small, scene_runs, scene_rle):
+    for scene, h in ((scene_small, -40.0), (scene_runs, -90.0), (scene_rle, -30.0)):
         cfg = R.FrameConfig.default(512, 384)
         for pos, rot in few_cameras(h):
             ref, port, ids, cnt = _both(R, rb, scene, cfg, pos, rot)

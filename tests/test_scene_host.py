@@ -156,3 +156,38 @@ def test_synth_scene_shape(scene_mid):
     sx, sy, sz, mp, sl = scene_mid.level(0)
     cnt = mp[1::2] & 0xffff
     assert cnt.min() >= 1                      # the terrain covers every column
+
+
+def test_direct_rle_scene(R, rb, scene_rle, tmp_path):
+    """rlerc_synth_rle writes columns straight into the .rle4 layout (BASELINE config 4 without a 32 GiB volume):
+    valid format (decodes column by column, run-splitting rules of Rle4.cpp:166-182), halved mip chain, the
+    short-run band is there, the file round-trips through the reference's own loader layout, and the budget of the
+    full-size scene fits the format's int32 slab count."""
+    assert scene_rle.nummaps == 6
+    for m in range(scene_rle.nummaps):
+        sx, sy, sz, mp, sl = scene_rle.level(m)
+        assert (sx, sy, sz) == (256 >> m,) * 3
+        assert np.array_equal(rb.orc_build_map(sl, sx, sz), mp)
+        # walk every column: header, runs, attributes; heights stay inside the volume
+        ofs = 0
+        for _ in range(sx * sz):
+            n_runs, n_vox = int(sl[ofs]), int(sl[ofs + 1])
+            runs = sl[ofs + 2: ofs + 2 + n_runs].astype(np.int64)
+            assert int((runs >> 10).sum()) == n_vox
+            assert int(((runs & 1023) + (runs >> 10)).sum()) <= sy
+            ofs += 2 + n_runs + n_vox
+        assert ofs == len(sl)
+    cnt = scene_rle.level(0)[3][1::2] & 0xffff
+    assert cnt.max() >= 33 and 1.0 < cnt.mean() < 8.0           # band columns have 1 + 32 runs, most have one or two
+    f = str(tmp_path / "rle.rle4")
+    scene_rle.save(f)
+    back = R.RLE4.load(f)
+    for m in range(back.nummaps):
+        a, b = scene_rle.level(m), back.level(m)
+        assert a[:3] == b[:3] and np.array_equal(a[3], b[3]) and np.array_equal(a[4], b[4])
+    # same statistics at 1024^2 columns: ushorts per column x 16384^2 must stay below 2^31 (Rle4.cpp:237)
+    big = R.RLE4.synth_rle(1024, 1024, 1024, seed=42, band_every=48)
+    per_col = len(big.level(0)[4]) / float(1024 * 1024)
+    assert per_col * 16384.0 * 16384.0 < 2.0 ** 31
+    with pytest.raises(R.RlercError):
+        R.RLE4.synth_rle(100, 256, 256)
