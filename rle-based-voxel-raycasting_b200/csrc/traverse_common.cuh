@@ -614,11 +614,18 @@ __device__ __forceinline__ bool consume_batch(const TraverseParams& P, const Ray
 	// builds the row set of its spans inside a 128-row window above y_clip_min, an exclusive prefix OR over the
 	// lanes gives the rows covered before each column (hence the horizon it meets, for the exact top-clip test
 	// of Cuda_Render.h:467) and its own rows.  One failed precondition sends the batch through the event loop.
-	if (!IDS && todo)
+	// B1 works on the longest PREFIX of the open columns that meets the per-column preconditions; a column that does
+	// not (more than RW undecided runs, a span reaching y_clip_max, a span beyond the window) is left to one iteration
+	// of the event loop below, after which B1 takes the rest of the batch (at most three attempts per batch).
+	int b1_attempts = 0;
+	while (todo)
+	{
+	bool b1_done = false;
+	if (!IDS && b1_attempts++ < 3)
 	{
 		const int y0 = ycmin;
 		const int w0 = y0 >> 5, wbase = w0 << 5, wend = wbase + 128;
-		const bool mine = (todo >> gl) & 1u;
+		bool mine = (todo >> gl) & 1u;
 		const bool pass0 = mine && s0.have && !(g0.pz * res_y2 + g0.py <= g0.pz * (float)y0);
 		bool ok = true;
 		unsigned why = 0;
@@ -642,7 +649,12 @@ __device__ __forceinline__ bool consume_batch(const TraverseParams& P, const Ray
 				rg2 |= bit_range(lo - 64, hi - 64); rg3 |= bit_range(lo - 96, hi - 96);
 			}
 		}
-		if (__all_sync(FULL, ok))
+		const unsigned badmask = __ballot_sync(FULL, !ok) & todo;
+		const int first_bad = badmask ? (__ffs(badmask) - 1) : 32;
+		const unsigned sub = todo & (first_bad >= 32 ? 0xffffffffu : ((1u << first_bad) - 1u));   // the columns B1 takes
+		if (gl >= first_bad) { rg0 = 0; rg1 = 0; rg2 = 0; rg3 = 0; mine = false; }
+		ok = true;
+		if (sub != 0)
 		{
 			// rows covered before my column: mask as it is, rows below y_clip_min, spans of the lanes before me
 			unsigned i0 = rg0, i1 = rg1, i2 = rg2, i3 = rg3;
@@ -746,19 +758,21 @@ __device__ __forceinline__ bool consume_batch(const TraverseParams& P, const Ray
 				const int top_row = (t3 ? 128 - __clz(t3) : (t2 ? 96 - __clz(t2) : (t1 ? 64 - __clz(t1) : (t0 ? 32 - __clz(t0) : 0))));
 				if (t0 | t1 | t2 | t3) { const int h = wbase + top_row; hiw = hiw > h ? hiw : h; }
 				ycmin = first_clear(ymask, y0, ycmax);                              // Cuda_Render.h:573-577
-				todo = 0;
+				todo &= ~sub;
+				b1_done = true;
 				if (STATS) R.stat[2]++;
 			}
 		}
-		if (STATS && todo)
+		if (!b1_done && sub != 0) b1_attempts = 3;                                // refused as a whole: the event loop takes the batch
+		if (STATS && !b1_done)
 		{
 			const unsigned allwhy = __reduce_or_sync(FULL, why);
 			for (int k = 0; k < 7; k++) if ((allwhy >> k) & 1u) R.stat[4 + k]++;
 		}
 	}
+	if (b1_done) continue;
 
 	if (STATS) { const long long now_ = clock64(); R.stat[13] += now_ - stick; stick = now_; }
-	while (todo)
 	{
 		if (STATS) R.stat[3]++;
 		if (ycmin >= ycmax) { finished = true; break; }
@@ -879,6 +893,7 @@ __device__ __forceinline__ bool consume_batch(const TraverseParams& P, const Ray
 			                 m, __shfl_sync(FULL, g0.cidx, L), ycmin, ycmax, hiw, lstats);
 		}
 	}
+	}   // while (todo)
 
 	if (STATS) { const long long now_ = clock64(); R.stat[14] += now_ - stick; stick = now_; }
 	// ---- S. shade the short spans of this batch: every lane its own column, side by side -------
