@@ -76,7 +76,7 @@ struct RayCtx {
 	float res_y2, pz_add, py_add, mountain;
 	int gl;
 	int hc_on, hc;           // HEIGHT_COLOR (R/src/core.h:22): on/off, height_color (Cuda_Render.h:675)
-	long long* stat;         // STATS build: [0] batches [1] B0 taken [2] B1 taken [3] event-loop iterations [4..10] B1 fail reasons [12..15] cycles in B0, B1, event loop, S
+	long long* stat;         // STATS build: [0] batches [1] B0 taken [2] B1 taken [3] event-loop iterations [4..10] B1 fail reasons [11] batches that needed the event loop [12..15] cycles in B0, B1, event loop, S
 };
 
 // A pixel span [y, s2) of one run, shaded by the whole warp 32 pixels at a time, stores coalesced
@@ -618,6 +618,7 @@ __device__ __forceinline__ bool consume_batch(const TraverseParams& P, const Ray
 	// not (more than RW undecided runs, a span reaching y_clip_max, a span beyond the window) is left to one iteration
 	// of the event loop below, after which B1 takes the rest of the batch (at most three attempts per batch).
 	int b1_attempts = 0;
+	bool ev_batch = false;            // STATS: this batch needed the event loop
 	while (todo)
 	{
 	bool b1_done = false;
@@ -770,9 +771,11 @@ __device__ __forceinline__ bool consume_batch(const TraverseParams& P, const Ray
 			for (int k = 0; k < 7; k++) if ((allwhy >> k) & 1u) R.stat[4 + k]++;
 		}
 	}
-	if (b1_done) continue;
-
 	if (STATS) { const long long now_ = clock64(); R.stat[13] += now_ - stick; stick = now_; }
+	if (b1_done) continue;
+	if (STATS && !ev_batch) { ev_batch = true; R.stat[11]++; }
+
+	if (STATS) { const long long now_ = clock64(); R.stat[13] += now_ - stick; stick = now_; }   // ---- E. one event-loop iteration
 	{
 		if (STATS) R.stat[3]++;
 		if (ycmin >= ycmax) { finished = true; break; }
@@ -893,6 +896,7 @@ __device__ __forceinline__ bool consume_batch(const TraverseParams& P, const Ray
 			                 m, __shfl_sync(FULL, g0.cidx, L), ycmin, ycmax, hiw, lstats);
 		}
 	}
+	if (STATS) { const long long now_ = clock64(); R.stat[14] += now_ - stick; stick = now_; }
 	}   // while (todo)
 
 	if (STATS) { const long long now_ = clock64(); R.stat[14] += now_ - stick; stick = now_; }

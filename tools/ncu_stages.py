@@ -24,7 +24,7 @@ M = {
     "traverse_commo": marks("traverse_common.cuh", [
         ("__device__ __noinline__ int coop_span(", "cooperative span shaders"), ("void long_column(", "long_column (lane <-> run)"),
         ("struct DdaState {", "helpers"), ("// ---- B0. rising-horizon", "B0 rising-horizon path"),
-        ("// ---- B1. ownership-resolved", "B1 ownership-resolved path"), ("\twhile (todo)", "event loop (owner lane)"),
+        ("// ---- B1. ownership-resolved", "B1 ownership-resolved path"), ("// ---- E. one event-loop iteration", "event loop (owner lane)"),
         ("// ---- S. shade the short spans", "S deferred shading")]),
 }
 acc, T, C = {}, 0, 0

@@ -36,8 +36,8 @@ for t in frames:
         print("  %-8d %8.3f | %s | %d, %d" % (i, tot / 1.965e6, " ".join("%5.1f%% %5.0f" % (100.0 * a[i, k] / tot, a[i, k] / max(1, steps[i] if k <= 3 else batches[i])) for k in range(1, 7)), steps[i], batches[i]))
     tot = a[:, 0].sum()
     st = a[:, 8:].sum(axis=0)
-    print("  consume batches %d: B0 %d, B1 %d, event loop %d (%d iterations); B1 refused for [flip,longcol,irregular,topattach,window,clipflip,2long] = %s"
-          % (st[0], st[1], st[2], st[0] - st[1] - st[2], st[3], [int(v) for v in st[4:11]]))
+    print("  consume batches %d: B0 took %d, B1 took (all or a prefix of) %d, %d needed the event loop (%d iterations); B1 blocked by [flip,longcol,irregular,topattach,window,clipflip,2long] = %s"
+          % (st[0], st[1], st[2], st[11], st[3], [int(v) for v in st[4:11]]))
     i = order[0]
     print("  slowest ray plane, cycles per consume batch: B0 %.0f, B1 %.0f, event loop %.0f, S %.0f" % tuple(a[i, 20 + k] / max(1, batches[i]) for k in range(4)))
     print("  all rays: %s | %d, %d" % (" ".join("%5.1f%%" % (100.0 * a[:, k].sum() / tot) for k in range(1, 7)), steps.sum(), batches.sum()))
