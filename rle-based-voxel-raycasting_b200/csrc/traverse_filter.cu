@@ -104,8 +104,12 @@ __device__ __forceinline__ int ddaq_batch(DdaQ& Q, float4* rec, int prev_n, int 
                                             // planes share pointer-map lines in L1, 8 per block measured best at 4K
 #endif
 
+#ifndef RLERC_F_MINB
+#define RLERC_F_MINB (16 / RLERC_F_WPB)       // resident blocks per SM the register allocation is capped for (128 registers)
+#endif
+
 template <bool IDS, bool PROF>
-__global__ void __launch_bounds__(RLERC_F_WPB * 32, 16 / RLERC_F_WPB)
+__global__ void __launch_bounds__(RLERC_F_WPB * 32, RLERC_F_MINB)
 k_traverse_f(const __grid_constant__ TraverseParams P, int rays)
 {
 	long long prof[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
