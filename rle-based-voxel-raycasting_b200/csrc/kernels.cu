@@ -398,7 +398,11 @@ static void launch_traverse_t(const TraverseParams& p, cudaStream_t st)
 	if (rays <= 0) return;
 	const int blocks = (rays + gpb - 1) / gpb;
 	const size_t smem = ((size_t)gpb * G * 8 + (size_t)gpb * p.mask_words) * sizeof(uint32_t);
-	static size_t configured = 0;
+	// dynamic shared memory above 48 KB is an opt-in per kernel AND per device
+	static size_t configured_on[64] = { 0 };
+	int dev = 0;
+	cudaGetDevice(&dev);
+	size_t& configured = configured_on[dev & 63];
 	if (smem > configured)
 	{
 		cudaFuncSetAttribute(k_traverse<G, IDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -507,7 +507,11 @@ static void launch_c(const TraverseParams& p, cudaStream_t st)
 	const size_t per_warp = (RLERC_C_QUEUE + 16 + RLERC_PS_WORDS + p.mask_words + 3) & ~3;
 	const size_t words = (size_t)2 * WPB * (RLERC_CH + 1) * 4 + (size_t)WPB * RLERC_C_STATE + 8 * WPB + (size_t)WPB * per_warp;
 	const size_t smem = words * sizeof(uint32_t);
-	static size_t configured = 0;
+	// dynamic shared memory above 48 KB is an opt-in per kernel AND per device
+	static size_t configured_on[64] = { 0 };
+	int dev = 0;
+	cudaGetDevice(&dev);
+	size_t& configured = configured_on[dev & 63];
 	if (smem > configured)
 	{
 		cudaFuncSetAttribute(k_traverse_c<IDS, WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

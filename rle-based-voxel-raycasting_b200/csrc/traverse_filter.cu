@@ -441,7 +441,11 @@ static void launch_f(const TraverseParams& p, cudaStream_t st)
 	if (rays <= 0) return;
 	const int blocks = (rays + wpb - 1) / wpb;
 	const size_t smem = (size_t)wpb * ((RLERC_F_REC + RLERC_F_QUEUE + 16 + RLERC_PS_WORDS + p.mask_words + 3) & ~3) * sizeof(uint32_t);
-	static size_t configured = 0;
+	// dynamic shared memory above 48 KB is an opt-in per kernel AND per device
+	static size_t configured_on[64] = { 0 };
+	int dev = 0;
+	cudaGetDevice(&dev);
+	size_t& configured = configured_on[dev & 63];
 	if (smem > configured)
 	{
 		cudaFuncSetAttribute(k_traverse_f<IDS, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

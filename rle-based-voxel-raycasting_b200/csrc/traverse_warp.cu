@@ -534,7 +534,11 @@ static void launch_w(const TraverseParams& p, cudaStream_t st)
 	const int producers = (MODE == 1) ? (rays + RLERC_BLOCK - 1) / RLERC_BLOCK : 0;
 	const int blocks = producers + (rays + wpb - 1) / wpb;
 	const size_t smem = (size_t)wpb * ((RLERC_DDA_WORDS + 16 + RLERC_PS_WORDS + 3 * 6 * 32 + p.mask_words + 3) & ~3) * sizeof(uint32_t);
-	static size_t configured = 0;
+	// dynamic shared memory above 48 KB is an opt-in per kernel AND per device
+	static size_t configured_on[64] = { 0 };
+	int dev = 0;
+	cudaGetDevice(&dev);
+	size_t& configured = configured_on[dev & 63];
 	if (smem > configured)
 	{
 		cudaFuncSetAttribute(k_traverse_w<IDS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

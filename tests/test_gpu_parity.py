@@ -460,3 +460,25 @@ def test_core_h_options_clipregion_height_color(R, rb, gpu, scene_small, scene_m
     with pytest.raises(R.RlercError):
         gpu.render(R.RayMap(cfg).get_ray_map(*cams[0]), cfg)
     gpu.set_lanes_per_ray(0)
+
+
+def test_two_devices_in_one_process(R, rb, scene_small):
+    """One process, one context per GPU: kernels, shared-memory opt-in and buffers are
+    per device.  Skipped on a single-GPU box."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    cfg = R.FrameConfig.default(1920, 1080)          # > 48 KB of dynamic shared memory per block
+    pos, rot = few_cameras(-40.0)[0]
+    rm = R.RayMap(cfg).get_ray_map(pos, rot)
+    orm = oracle_raymap(rb, rm, scene_small)
+    want, _, _ = rb.orc_render(orm, cfg.render_size, cfg.rays_casted, cfg.mip_distance, cfg.z_far)
+    outs = []
+    for dev in (0, 1):
+        r = R.Renderer(dev)
+        r.all_to_gpu(scene_small)
+        r.render(rm, cfg)
+        r.unwarp(rm, cfg)
+        outs.append(r.read_warp(cfg))
+        r.close()
+    assert np.array_equal(outs[0], want) and np.array_equal(outs[1], want)
