@@ -114,6 +114,17 @@ class ClockSampler(threading.Thread):
 KERNEL_NAMES = {0: "k_traverse_f", 65: "k_traverse_f", 64: "k_traverse_w", 66: "k_traverse_c<3>", 67: "k_traverse_c<7>"}
 
 
+def measured_ncu(workload, kernel):
+    """What else the committed ncu capture says about that launch (IPC, hit rates, sectors per request)."""
+    try:
+        e = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(workload)
+        if e and e.get("kernel") == kernel:
+            return e.get("ncu")
+    except Exception:
+        pass
+    return None
+
+
 def measured_traffic(workload, kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the traversal kernel, from the committed
     `ncu --set full` capture (profiles/traffic.json; null when there is none for this workload / kernel)."""
@@ -358,6 +369,7 @@ def main():
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": measured_traffic(args.workload, KERNEL_NAMES.get(args.lanes, "k_traverse<%d>" % args.lanes)),
                 "kernel": KERNEL_NAMES.get(args.lanes, "k_traverse<%d>" % args.lanes),
+                "ncu": measured_ncu(args.workload, KERNEL_NAMES.get(args.lanes, "k_traverse<%d>" % args.lanes)),
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                 "algorithmic_bytes_per_launch": per_launch_bytes,
                 "traverse_ms_per_launch": trav_ms_max / max(kernels_timed, 1), "unwarp_ms_per_launch": unwarp_ms_max / max(kernels_timed, 1),
