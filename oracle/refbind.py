@@ -216,6 +216,9 @@ def orc_render(rm, res, rays_casted, mip_distance=None, z_far=80000, want_ids=Fa
     warp = np.zeros((rays_casted, res), np.uint32)
     ids = np.full((rays_casted, res, 2), 0xffffffff, np.uint32) if want_ids else None
     cnt = (C.c_longlong * 10)()
+    # cudaRender renders min(map_line_count, RAYS_CASTED) ray planes (R/src/Cuda_Main.cu:196); the buffer has rays_casted rows
+    limit = min(rm.map_line_count, rays_casted)
+    ray_end = limit if ray_end < 0 else min(ray_end, limit)
     rc = port().orc_render_flags(C.byref(rm), res, mip_distance or res, z_far, warp.ctypes.data,
                                  ids.ctypes.data if want_ids else None, cnt, ray_begin, ray_end, threads, flags)
     if rc:

@@ -482,3 +482,19 @@ def test_two_devices_in_one_process(R, rb, scene_small):
         outs.append(r.read_warp(cfg))
         r.close()
     assert np.array_equal(outs[0], want) and np.array_equal(outs[1], want)
+
+
+def test_more_ray_planes_than_buffer_rows(R, rb, gpu, scene_small):
+    """map_line_count > RAYS_CASTED (square window, steep pitch): the kernel renders rays_casted ray planes
+    (R/src/Cuda_Main.cu:196) and touches nothing beyond the buffer."""
+    gpu.all_to_gpu(scene_small)
+    gpu.set_lanes_per_ray(0)
+    cfg = R.FrameConfig.default(512, 512)
+    pos, rot = (812.2, -40.0, 18034.6), (-1.20644718889272, 1.5707963267948966, 0.0)
+    rm = R.RayMap(cfg).get_ray_map(pos, rot)
+    assert rm.map_line_count > cfg.rays_casted
+    _, want, _, _ = _oracle(rb, rm, scene_small, cfg)
+    _fresh_warp(gpu, cfg)
+    gpu.render(rm, cfg)
+    assert np.array_equal(gpu.read_warp(cfg), want)
+

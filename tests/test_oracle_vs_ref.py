@@ -135,3 +135,15 @@ def test_render_line_port_equals_reference_with_core_h_options(R, rb, need_ref, 
         plain, _, _ = rb.orc_render(orm, cfg.render_size, cfg.rays_casted, cfg.mip_distance, cfg.z_far)
         drew += int(cnt["pixels"] > 0 and not np.array_equal(plain, port))
     assert drew >= 3          # the options change the picture on most of these cameras
+
+
+def test_more_ray_planes_than_buffer_rows(R, rb, need_ref, scene_small):
+    """A square window looking steeply down makes map_line_count exceed RAYS_CASTED (2061 > 2048 here); cudaRender
+    renders min(count, RAYS_CASTED) ray planes (R/src/Cuda_Main.cu:196) and so do the oracle wrappers."""
+    cfg = R.FrameConfig.default(512, 512)
+    pos, rot = (812.2, -40.0, 18034.6), (-1.20644718889272, 1.5707963267948966, 0.0)
+    rm = R.RayMap(cfg).get_ray_map(pos, rot)
+    assert rm.map_line_count > cfg.rays_casted
+    ref, port, ids, cnt = _both(R, rb, scene_small, cfg, pos, rot)
+    assert ref.shape == port.shape == (cfg.rays_casted, cfg.render_size)
+    assert np.array_equal(ref, port) and cnt["pixels"] > 0
