@@ -55,12 +55,141 @@ __device__ __forceinline__ void ddaq_lod_switch(DdaQ& Q, int last_map)          
 	Q.dzi *= 2;
 }
 
+// EXPERIMENTAL DDA crossings as hand-scheduled PTX (build knob RLERC_DDA_ASM, default 0 = the C++ recurrence in
+// ddaq_batch).  All three are bit-exact on B200 and all three are SLOWER than what nvcc makes of the C++ loop
+// (tools/ab_libs.py, 1080p fly-through, four frames in flight: 0.546 ms per frame for the C++ loop):
+//   1: predicates folded with the writer flag (only the writer lane's float state is ever read); x-track quad
+//      stored by the writer, z-track quad stored over it when that track fires; 3 adds @w1, 3 adds @!w1
+//      (9 instructions + overhead, two STS.128 per crossing)                                             0.572 ms
+//   2: setp w1|w0, one store @w1, one @w0, 3 adds @w1, 3 adds @w0 (10 instructions, one active store)     0.557 ms
+//   3: no shared memory: every lane runs the recurrence, lane j keeps the record of crossing j in registers
+//      (guarded selp per field), the consumer takes record j-1 with one shuffle-up (11 instructions, no STS/LDS,
+//      no __syncwarp); same instruction total per frame, more instruction-cache misses (ncu no_instruction
+//      stall 0.21 -> 0.48 per issue), IPC 2.73 -> 2.51                                                    0.607 ms
+// The packed add.rn.f32x2 (FADD2, sm_100+) was tried too: ptxas does not predicate it (FADD2 + two SEL), a loss.
+// IEEE adds (add.rn.f32, no FMA, no FTZ), ordered compare: NaN -> x-track, like `<`.
+#ifndef RLERC_DDA_ASM
+#define RLERC_DDA_ASM 0
+#endif
+#ifndef RLERC_DDA_UNROLL
+#define RLERC_DDA_UNROLL 4
+#endif
+__device__ __forceinline__ void ddaq_cross(DdaQ& Q, float mipf, uint32_t out_s, int writer)
+{
+#if RLERC_DDA_ASM == 2
+	asm volatile("{\n"
+		" .reg .pred pw, w1, w0;\n"
+		" .reg .f32 pd1;\n"
+		" setp.ne.s32 pw, %13, 0;\n"
+		" neg.f32 pd1, %3;\n"
+		" setp.lt.and.f32 w1|w0, pd1, %0, pw;\n"
+		" @w1 st.shared.v4.f32 [%12], {%3, %4, %5, %14};\n"
+		" @w0 st.shared.v4.f32 [%12], {%0, %1, %2, %14};\n"
+		" @w1 add.rn.f32 %3, %3, %9;\n"
+		" @w0 add.rn.f32 %0, %0, %6;\n"
+		" @w1 add.rn.f32 %4, %4, %10;\n"
+		" @w0 add.rn.f32 %1, %1, %7;\n"
+		" @w1 add.rn.f32 %5, %5, %11;\n"
+		" @w0 add.rn.f32 %2, %2, %8;\n"
+		"}\n"
+		: "+f"(Q.d0), "+f"(Q.x0), "+f"(Q.y0), "+f"(Q.nd1), "+f"(Q.x1), "+f"(Q.y1)
+		: "f"(Q.gd0), "f"(Q.gx0), "f"(Q.gy0), "f"(Q.ngd1), "f"(Q.gx1), "f"(Q.gy1), "r"(out_s), "r"(writer), "f"(mipf)
+		: "memory");
+#else
+	asm volatile("{\n"
+		" .reg .pred pw, w1;\n"
+		" .reg .f32 pd1;\n"
+		" setp.ne.s32 pw, %13, 0;\n"
+		" neg.f32 pd1, %3;\n"
+		" setp.lt.and.f32 w1, pd1, %0, pw;\n"
+		" @pw st.shared.v4.f32 [%12], {%0, %1, %2, %14};\n"
+		" @w1 st.shared.v4.f32 [%12], {%3, %4, %5, %14};\n"
+		" @w1 add.rn.f32 %3, %3, %9;\n"
+		" @!w1 add.rn.f32 %0, %0, %6;\n"
+		" @w1 add.rn.f32 %4, %4, %10;\n"
+		" @!w1 add.rn.f32 %1, %1, %7;\n"
+		" @w1 add.rn.f32 %5, %5, %11;\n"
+		" @!w1 add.rn.f32 %2, %2, %8;\n"
+		"}\n"
+		: "+f"(Q.d0), "+f"(Q.x0), "+f"(Q.y0), "+f"(Q.nd1), "+f"(Q.x1), "+f"(Q.y1)
+		: "f"(Q.gd0), "f"(Q.gx0), "f"(Q.gy0), "f"(Q.ngd1), "f"(Q.gx1), "f"(Q.gy1), "r"(out_s), "r"(writer), "f"(mipf)
+		: "memory");
+#endif
+}
+
+// RLERC_DDA_ASM 3: no shared memory at all.  Every lane runs the recurrence (the state stays warp-uniform) and lane j
+// keeps the record of crossing j in its own registers: a guarded select per field, nothing to store, nothing to
+// synchronise; the consumer of crossing j needs the records j-1 and j, i.e. its own and one shuffle-up.
+//   setp t1 | setp pj = (lane == crossing) | 3 x @pj selp | 3 adds @t1 | 3 adds @!t1    -> 11 instructions, 0 stores
+struct DdaCap {
+	float cx, cy, cz; int cmip;      // record of crossing `lane` of the current batch {+-distance, pos.x, pos.y}, its mip level
+	float kx, ky, kz;                // record before crossing 0: the last crossing of the previous batch (warp-uniform)
+};
+template <int K>
+__device__ __forceinline__ void ddaq_cross_cap(DdaQ& Q, DdaCap& C, int rel)          // lane keeps the record iff rel == K
+{
+	asm volatile("{\n"
+		" .reg .pred t1, pj;\n"
+		" .reg .f32 pd1;\n"
+		" neg.f32 pd1, %3;\n"
+		" setp.lt.f32 t1, pd1, %0;\n"
+		" setp.eq.s32 pj, %15, %16;\n"
+		" @pj selp.f32 %6, %3, %0, t1;\n"
+		" @pj selp.f32 %7, %4, %1, t1;\n"
+		" @pj selp.f32 %8, %5, %2, t1;\n"
+		" @t1 add.rn.f32 %3, %3, %12;\n"
+		" @!t1 add.rn.f32 %0, %0, %9;\n"
+		" @t1 add.rn.f32 %4, %4, %13;\n"
+		" @!t1 add.rn.f32 %1, %1, %10;\n"
+		" @t1 add.rn.f32 %5, %5, %14;\n"
+		" @!t1 add.rn.f32 %2, %2, %11;\n"
+		"}\n"
+		: "+f"(Q.d0), "+f"(Q.x0), "+f"(Q.y0), "+f"(Q.nd1), "+f"(Q.x1), "+f"(Q.y1), "+f"(C.cx), "+f"(C.cy), "+f"(C.cz)
+		: "f"(Q.gd0), "f"(Q.gx0), "f"(Q.gy0), "f"(Q.ngd1), "f"(Q.gx1), "f"(Q.gy1), "r"(rel), "n"(K));
+}
+
+// Same contract as ddaq_batch below, records captured in registers (C) instead of shared memory.
+__device__ __forceinline__ int ddaq_batch_cap(DdaQ& Q, DdaCap& C, int prev_n, int last_map, int zfar_i, int gl)
+{
+	int nvalid = 32;
+	if (prev_n > 0)
+	{
+		C.kx = __shfl_sync(0xffffffffu, C.cx, prev_n - 1);
+		C.ky = __shfl_sync(0xffffffffu, C.cy, prev_n - 1);
+		C.kz = __shfl_sync(0xffffffffu, C.cz, prev_n - 1);
+	}
+	for (int s = 0; s < 32;)
+	{
+		while (Q.zi > Q.mapswitch) ddaq_lod_switch(Q, last_map);
+		const int sh = 31 - __clz(Q.dzi);
+		const int lod_free = ((Q.mapswitch - Q.zi) >> sh) + 1;        // crossings before z > mapswitch
+		const int far_free = (zfar_i - Q.zi) >> sh;                   // crossings with z + dz <= z_far (<= 0: none)
+		if (far_free <= 0) { nvalid = s; break; }
+		int n = 32 - s;
+		n = n < lod_free ? n : lod_free;
+		n = n < far_free ? n : far_free;
+		const int rel = gl - s;                                       // this lane keeps crossing j == rel of the segment
+		if (rel >= 0 && rel < n) C.cmip = Q.mip;
+		int r = rel, j = 0;
+		for (; j + 4 <= n; j += 4, r -= 4)
+		{
+			ddaq_cross_cap<0>(Q, C, r); ddaq_cross_cap<1>(Q, C, r); ddaq_cross_cap<2>(Q, C, r); ddaq_cross_cap<3>(Q, C, r);
+		}
+		#pragma unroll 1
+		for (; j < n; j++, r--) ddaq_cross_cap<0>(Q, C, r);
+		Q.zi += n << sh;
+		s += n;
+	}
+	return nvalid;
+}
+
 // Up to 32 crossings, all lanes in lockstep (one lane writes: 32 lanes storing the same 16 bytes cost four
 // shared-memory passes per crossing, which made the DDA store-bound); rec[s+1] = record of crossing s; rec[0] = the last record of the
 // previous batch (rec[prev_n], or zeros before the first).  LOD / z_far budgets by shifts (dz is a power of two).
 // Returns the number of crossings made (< 32 only when z_far was reached, Cuda_Render.h:366-367).
-__device__ __forceinline__ int ddaq_batch(DdaQ& Q, float4* rec, int prev_n, int last_map, int zfar_i, bool writer)
+__device__ __forceinline__ int ddaq_batch(DdaQ& Q, float4* rec, int prev_n, int last_map, int zfar_i, bool writer_b)
 {
+	const int writer = writer_b ? 1 : 0;
 	int nvalid = 32;
 	{
 		const float4 carry = rec[prev_n];
@@ -79,6 +208,12 @@ __device__ __forceinline__ int ddaq_batch(DdaQ& Q, float4* rec, int prev_n, int 
 		n = n < far_free ? n : far_free;
 		const float mipf = __int_as_float(Q.mip);
 		float4* out = rec + s + 1;
+#if RLERC_DDA_ASM
+		const uint32_t out_s = (uint32_t)__cvta_generic_to_shared(out);
+		constexpr int DDA_UNROLL = RLERC_DDA_UNROLL;
+		#pragma unroll DDA_UNROLL
+		for (int j = 0; j < n; j++) ddaq_cross(Q, mipf, out_s + 16u * (uint32_t)j, writer);
+#else
 		#pragma unroll 4
 		for (int j = 0; j < n; j++)
 		{
@@ -88,6 +223,7 @@ __device__ __forceinline__ int ddaq_batch(DdaQ& Q, float4* rec, int prev_n, int 
 			if (t1) { Q.nd1 += Q.ngd1; Q.x1 += Q.gx1; Q.y1 += Q.gy1; }
 			else    { Q.d0 += Q.gd0; Q.x0 += Q.gx0; Q.y0 += Q.gy0; }
 		}
+#endif
 		Q.zi += n << sh;
 		s += n;
 	}
@@ -172,6 +308,8 @@ k_traverse_f(const __grid_constant__ TraverseParams P, int rays)
 	Q.mip = 0;
 	Q.zi = 0; Q.dzi = 1;                                         // z and dz (Cuda_Render.h:181,325), integer valued
 	Q.mapswitch = P.mapswitch0;
+	DdaCap cap;
+	cap.cx = cap.cy = cap.cz = 0.0f; cap.cmip = 0; cap.kx = cap.ky = cap.kz = 0.0f;   // (register-capture DDA)
 	if (gl == 0) rec[0] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);   // no crossing yet: distance 0, x-track (Cuda_Render.h:302-305)
 	int prev_n = 0;
 	__syncwarp();
@@ -221,12 +359,18 @@ k_traverse_f(const __grid_constant__ TraverseParams P, int rays)
 			if (PROF) prof[7] += 1;
 			if (!dda_done)
 			{
+#if RLERC_DDA_ASM == 3
+				nvalid = ddaq_batch_cap(Q, cap, prev_n, last_map, zfar_i, gl);
+#else
 				nvalid = ddaq_batch(Q, rec, prev_n, last_map, zfar_i, gl == 0);
+#endif
 				prev_n = nvalid;
 				if (nvalid < G) dda_done = true;
 				if (IDS && gl == 0) Cn.c_steps += nvalid;
 			}
+#if RLERC_DDA_ASM != 3
 			__syncwarp();
+#endif
 			RLERC_TICK(1);
 			// F2. first-run test of the batch in flight, live columns -> queue
 			if (fn > 0)
@@ -270,9 +414,20 @@ k_traverse_f(const __grid_constant__ TraverseParams P, int rays)
 			// F3. geometry of the new crossings, conservative top clip, pointer-map gather (into the registers F2 freed)
 			fn = nvalid;
 			fhave = false;
+#if RLERC_DDA_ASM == 3
+			float4 ra, rb;                                             // state before / after crossing gl
+			if (nvalid > 0)
+			{
+				ra.x = __shfl_up_sync(FULL, cap.cx, 1); ra.y = __shfl_up_sync(FULL, cap.cy, 1); ra.z = __shfl_up_sync(FULL, cap.cz, 1);
+				if (gl == 0) { ra.x = cap.kx; ra.y = cap.ky; ra.z = cap.kz; }
+				rb.x = cap.cx; rb.w = __int_as_float(cap.cmip);
+			}
+#endif
 			if (gl < nvalid)
 			{
+#if RLERC_DDA_ASM != 3
 				const float4 ra = rec[gl], rb = rec[gl + 1];           // state before / after crossing gl
+#endif
 				const float db = fabsf(ra.x), dn = fabsf(rb.x);
 				const int ib = __float_as_int(ra.x) < 0 ? 1 : 0;        // index_before: sign bit of the record
 				fg.cmip = __float_as_int(rb.w);
