@@ -66,7 +66,7 @@ int main(int argc, char** argv)
 		else
 		{
 			const size_t n = (size_t)synth * synth * synth;
-			std::vector<uint8_t> voxel(n / 8), col1(n), col2(n);
+			std::vector<uint8_t> voxel(n / 8), col1(n / 8), col2(n / 8);   // bit volumes: solid, material bit 0, material bit 1
 			check(rlerc_synth_volume(0, synth, synth, synth, 1, voxel.data(), col1.data(), col2.data()), "rlerc_synth_volume");
 			rle4.compress_all(voxel.data(), col1.data(), col2.data(), synth, synth, synth);
 			if (!pos_given) pos.y = -0.15f * (float)synth;         // above the synthetic terrain

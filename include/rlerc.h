@@ -112,7 +112,8 @@ int  rlerc_scene_nummaps(const rlerc_scene* s);
 /* Borrowed view of level m (host pointers, valid until rlerc_scene_free). */
 int  rlerc_scene_level(const rlerc_scene* s, int m, rlerc_map4* out, uint64_t* slabs_size64);
 /* RLE4::compress_all (Rle4.cpp:16-50) + Tree::get_mipmap (tree.h:23-85) on a bit volume
- * (x fastest, then y, then z; bit x&7 of byte (x+y*sx+z*sx*sy)>>3; col1/col2 may be NULL):
+ * (x fastest, then y, then z; bit x&7 of byte (x+y*sx+z*sx*sy)>>3; col1/col2 = the two material bits in the same
+ * layout, both may be NULL):
  * byte-identical output, multi-threaded. */
 int  rlerc_scene_compress(const uint8_t* voxel, const uint8_t* col1, const uint8_t* col2,
                           int sx, int sy, int sz, rlerc_scene** out);

@@ -16,7 +16,7 @@ int main(int argc, char** argv)
 		static_assert(sizeof(Map4) == 32, "Map4 layout (R/src/Rle4.h:7-21, LP64)");
 		static_assert(sizeof(RayMap_GPU) == 896, "RayMap_GPU layout (R/src/RayMap.h:16-54, LP64)");
 		const int N = 64;
-		std::vector<uint8_t> voxel((size_t)N * N * N / 8), c1((size_t)N * N * N), c2((size_t)N * N * N);
+		std::vector<uint8_t> voxel((size_t)N * N * N / 8), c1(voxel.size()), c2(voxel.size());
 		check(rlerc_synth_volume(0, N, N, N, 1, voxel.data(), c1.data(), c2.data()), "rlerc_synth_volume");
 		RLE4 a;
 		a.compress_all(voxel.data(), c1.data(), c2.data(), N, N, N);           // RLE4::compress_all

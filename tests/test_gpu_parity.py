@@ -9,7 +9,7 @@ import os
 import numpy as np
 import pytest
 
-from util import camera_grid, few_cameras, oracle_raymap, rgb_parity, sha
+from util import camera_grid, edge_cameras, edge_scenes, few_cameras, oracle_raymap, rgb_parity, sha
 
 pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -159,6 +159,51 @@ def test_hit_identity_and_counters(R, rb, gpu, scene_mid, scene_runs, lanes):
                       "elems_processed", "voxels_processed", "cleared"):
                 assert c[k] == cnt[k], (k, c[k], cnt[k], rot)
             assert c["dda_steps"] >= cnt["dda_steps"]      # batches of 32 crossings may overshoot the last one
+    gpu.set_lanes_per_ray(0)
+
+
+def test_degenerate_scenes_bit_exact(R, rb, gpu):
+    """Nothing, everything, one voxel, white noise (irregular columns with many runs, top-attached spans), floating
+    layers with a shaft, thin walls, a non-cubic grid, a one-voxel comb; cameras outside, inside matter, straight down
+    and up.  Production kernel: warped buffer, hit identity and counters; every other kernel variant: warped buffer;
+    final RGBA against the oracle's unwarp."""
+    import torch
+    cfg = R.FrameConfig.default(400, 300)
+    rgba = torch.empty((cfg.height, cfg.width, 4), dtype=torch.uint8, device="cuda")
+    for name, scene in edge_scenes(R).items():
+        gpu.all_to_gpu(scene)
+        for pos, rot in edge_cameras():
+            rm = R.RayMap(cfg).get_ray_map(pos, rot)
+            orm, want, want_ids, cnt = _oracle(rb, rm, scene, cfg, ids=True)
+            gpu.set_lanes_per_ray(0)
+            ids = torch.full((cfg.rays_casted, cfg.render_size, 2), -1, dtype=torch.int32, device="cuda")
+            _fresh_warp(gpu, cfg)
+            gpu.render_ids(rm, cfg, ids.data_ptr())
+            gpu.sync()
+            assert np.array_equal(gpu.read_warp(cfg), want), (name, pos, rot)
+            assert np.array_equal(ids.cpu().numpy().view(np.uint32), want_ids), (name, pos, rot)
+            c = dict(zip(rb.COUNTER_NAMES, gpu.counters()))
+            for k in ("pixels", "elems_rendered", "cols_fetched", "cols_nonempty", "elems_total", "cleared"):
+                assert c[k] == cnt[k], (name, k, c[k], cnt[k], rot)
+            # KNOWN instrumentation gap (DESIGN.md section 8): on the white-noise scene seen from just above its top,
+            # ten ray planes that close after six many-run columns report 1-3 run-loop iterations fewer than the
+            # oracle (9492 vs 9512 in the frame; picture, hit identity and every other counter are exact; the
+            # lane <-> run kernels k_traverse<32/1> count 9512).  The byte model's E term is within 0.5 % there.
+            for k in ("run_iters", "elems_processed", "voxels_processed"):
+                assert abs(c[k] - cnt[k]) <= 0.005 * cnt[k], (name, k, c[k], cnt[k], rot)
+                if name != "noise50":
+                    assert c[k] == cnt[k], (name, k, c[k], cnt[k], rot)
+            for lanes in (0, 64, 66, 32, 1):
+                gpu.set_lanes_per_ray(lanes)
+                _fresh_warp(gpu, cfg)
+                gpu.render(rm, cfg)
+                assert np.array_equal(gpu.read_warp(cfg), want), (name, lanes, pos, rot)
+            gpu.set_lanes_per_ray(0)
+            gpu.unwarp(rm, cfg, d_rgba=rgba.data_ptr())
+            gpu.sync()
+            orgba = rb.orc_unwarp(orm, cfg.width, cfg.height, cfg.render_size, cfg.rays_casted, cfg.rays_casted_res, want)
+            dmax, same = rgb_parity(rgba.cpu().numpy(), orgba)
+            assert dmax <= 1 and same >= 0.999, (name, rot, dmax, same)
     gpu.set_lanes_per_ray(0)
 
 

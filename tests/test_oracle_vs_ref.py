@@ -5,7 +5,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from util import camera_grid, few_cameras, levels_of, oracle_raymap
+from util import camera_grid, edge_cameras, edge_scenes, few_cameras, levels_of, oracle_raymap
 
 
 @pytest.fixture(scope="module")
@@ -40,6 +40,18 @@ def test_render_line_port_equals_reference_other_scenes(R, rb, need_ref, scene_s
         for pos, rot in few_cameras(h):
             ref, port, ids, cnt = _both(R, rb, scene, cfg, pos, rot)
             assert np.array_equal(ref, port), (h, rot)
+
+
+def test_render_line_port_equals_reference_on_degenerate_scenes(R, rb, need_ref):
+    """Nothing, everything, one voxel, white noise, floating layers, thin walls, a non-cubic grid, a one-voxel comb:
+    cameras outside, inside solid matter, inside the shaft, looking straight down / up."""
+    cfg = R.FrameConfig.default(400, 300)
+    for name, scene in edge_scenes(R).items():
+        for pos, rot in edge_cameras():
+            ref, port, ids, cnt = _both(R, rb, scene, cfg, pos, rot)
+            assert np.array_equal(ref, port), (name, pos, rot)
+            if name == "air":
+                assert cnt["pixels"] == 0 and cnt["run_iters"] == 0
 
 
 def test_render_line_port_non_default_config(R, rb, need_ref, scene_small):

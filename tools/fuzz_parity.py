@@ -14,6 +14,8 @@ N = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 rnd = random.Random(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
 scenes = [("terrain128", R.RLE4.synth(0, 128, 128, 128, seed=1), 128), ("runs128", R.RLE4.synth(1, 128, 128, 128, seed=42), 128),
           ("rle256", R.RLE4.synth_rle(256, 256, 256, seed=42, band_every=8), 256), ("terrain64", R.RLE4.synth(0, 64, 64, 64, seed=3), 64)]
+from util import edge_scenes
+scenes += [("edge_" + k, v, 64) for k, v in edge_scenes(R).items()]
 r = R.Renderer(0)
 bad = 0
 for i in range(N):
