@@ -214,7 +214,8 @@ __device__ __forceinline__ int ddaq_batch(DdaQ& Q, float4* rec, int prev_n, int 
 		#pragma unroll DDA_UNROLL
 		for (int j = 0; j < n; j++) ddaq_cross(Q, mipf, out_s + 16u * (uint32_t)j, writer);
 #else
-		#pragma unroll 4
+		constexpr int DDA_UNROLL = RLERC_DDA_UNROLL;
+		#pragma unroll DDA_UNROLL
 		for (int j = 0; j < n; j++)
 		{
 			const bool t1 = -Q.nd1 < Q.d0;                            // Cuda_Render.h:398-414
