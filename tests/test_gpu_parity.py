@@ -185,10 +185,10 @@ def test_degenerate_scenes_bit_exact(R, rb, gpu):
             c = dict(zip(rb.COUNTER_NAMES, gpu.counters()))
             for k in ("pixels", "elems_rendered", "cols_fetched", "cols_nonempty", "elems_total", "cleared"):
                 assert c[k] == cnt[k], (name, k, c[k], cnt[k], rot)
-            # KNOWN instrumentation gap: on the white-noise scene seen from just above its top,
-            # ten ray planes that close after six many-run columns report 1-3 run-loop iterations fewer than the
-            # oracle (9492 vs 9512 in the frame; picture, hit identity and every other counter are exact; the
-            # lane <-> run kernels k_traverse<32/1> count 9512).  The byte model's E term is within 0.5 % there.
+            # Dead iterations: a column that closes its ray plane with crossed bounds keeps
+            # iterating in the reference (clamped, empty spans; y_clip_min moves down, Cuda_Render.h:564-577); the
+            # warp kernels stop it at the first run that breaks at projection time.  Seen on the white-noise scene
+            # from just above its top only: 9492 vs 9512 iterations, picture and every other counter exact.
             for k in ("run_iters", "elems_processed", "voxels_processed"):
                 assert abs(c[k] - cnt[k]) <= 0.005 * cnt[k], (name, k, c[k], cnt[k], rot)
                 if name != "noise50":
