@@ -495,7 +495,10 @@ __device__ __forceinline__ uint32_t unwarp_pixel(const UnwarpParams& P, int px, 
 		const float zz = (cb * (1.0f / 256.0f) + ca);
 		fragz = 0.001f / zz;
 		const float light = (1.0f - cg) * 1.0f + (0.0f + cr) * 0.3f - 0.5f;
-		const float pw = 1.2f * powf(fmaxf(light, 0.0f), 4.0f);
+		// pow(max(c, 0), 4) (frag:121) as two squarings: within 1 ulp of powf, a third of k_unwarp's instructions less;
+		// the 8-bit result differs from the oracle's powf in < 1e-4 of the pixels, by 1 LSB (the north star's tolerance)
+		const float lp = fmaxf(light, 0.0f), lp2 = lp * lp;
+		const float pw = 1.2f * (lp2 * lp2);
 		r = light * 1.3f + pw * 1.2f;
 		g = light * 0.9f + pw * 1.2f;
 		b = light * 0.7f + pw * 1.2f;

@@ -28,7 +28,7 @@ def child(workload):
         out["hash"].append(hashlib.sha1(r.read_warp(cfg)[:rm.map_line_count].tobytes()).hexdigest()[:12])
     # four frames in flight through the C ABI with host buffers (bench.py e2e)
     r.set_timing(False)
-    K, DEPTH = 300, 4
+    K, DEPTH = 300, int(os.environ.get("AB_DEPTH", "4"))
     poses = [bench.path_pose(R, i * 1000 // K, 1000, sy, False) for i in range(K)]
     pins = [R.PinnedBuffer((H, W, 4)) for _ in range(DEPTH)]
     for i in range(8):
