@@ -314,7 +314,12 @@ def main():
     wall = time.perf_counter() - wall0
     clocks = sampler.summary()
     r.set_timing(False)
+    per_step = sorted(s.elapsed_time(e) for s, e in ev[:K if farm is None else rounds])
     dev_ms = sum(s.elapsed_time(e) for s, e in ev)
+    # frame-time distribution on this rank (mean / p50 / p99); frames mode: per round
+    frame_ms = {"mean": sum(per_step) / len(per_step), "p50": per_step[len(per_step) // 2],
+                "p99": per_step[min(len(per_step) - 1, int(0.99 * len(per_step)))], "max": per_step[-1],
+                "per": "frame" if farm is None else "round of %d frames" % world} if per_step else None
     t = torch.tensor([dev_ms, trav_ms, unwarp_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -493,7 +498,7 @@ def main():
                                             if farm is not None else
                                             "every frame split into ray-plane slices x%d, interleaved blocks of %d, NCCL reduce to rank 0" % (world, args.slice_block))),
                            "wall_s_timed_region": wall},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": 2 * K, "roofline": roof}
+                "clocks": clocks, "e2e": e2e, "gpu_launches": 2 * K, "frame_ms": frame_ms, "roofline": roof}
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), file=json_out, flush=True)
