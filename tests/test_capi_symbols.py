@@ -61,3 +61,19 @@ def test_version_and_error_strings(R):
     p = C.c_void_p()
     assert R.lib().rlerc_scene_load(b"/nonexistent/file.rle4", C.byref(p)) == -2
     assert b"cannot open" in R.lib().rlerc_last_error()
+
+
+def test_header_is_plain_c99_and_links(tmp_path):
+    """include/rlerc.h is the drop-in boundary: it must compile as C (no C++ types in the signatures) and a C program
+    must link against librlerc.so and call a host-only entry point."""
+    import subprocess
+    src = tmp_path / "c99.c"
+    src.write_text('#include "rlerc.h"\n'
+                   'int main(void){ rlerc_frame_config c; rlerc_frame_config_default(1024, 768, &c);\n'
+                   '  return (c.width == 1024 && c.render_size == 1024 && c.rays_casted == 4096 && sizeof(rlerc_raymap) == 896\n'
+                   '          && sizeof(rlerc_map4) == 32) ? 0 : 1; }\n')
+    exe = str(tmp_path / "c99")
+    pkg = os.path.join(ROOT, "rle-based-voxel-raycasting_b200")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", exe,
+                    "-L", pkg, "-lrlerc", "-Wl,-rpath," + pkg], check=True)
+    assert subprocess.run([exe]).returncode == 0
