@@ -10,6 +10,7 @@
 #include <vector>
 #include <cuda_runtime.h>
 #include "kernels.cuh"
+#include "device_common.cuh"
 #include "rlerc_internal.h"
 
 using namespace rlerc;
@@ -55,7 +56,8 @@ struct rlerc_ctx {
 	size_t rgba_bytes = 0;
 	uint32_t* d_ids_scratch = nullptr;
 	unsigned long long* d_counters = nullptr;
-	int lanes = 0;                      // 0 = auto
+	int lanes = 0;                      // 0 = auto (pick_lanes)
+	int sm_count = 148;
 	int dda_mode = 0;                   // 0 serial (default: fastest measured), 2 merge path (k_traverse_w)
 	int producer = 0;                   // decoupled DDA producer blocks (k_traverse_w): optional, off by default
 	float4* d_ring = nullptr;
@@ -177,10 +179,17 @@ int fill_unwarp(const rlerc_raymap* rm, const rlerc_frame_config* cfg, const uin
 	return RLERC_OK;
 }
 
-int pick_lanes(const rlerc_ctx* c, int rays)
+// 0 = automatic: the production kernel k_traverse_f (one warp per ray plane), except for launches whose ray planes are
+// all resident at once in the paired kernel (12 per SM: filter warp + consume warp per ray plane, k_traverse_p).
+// Such a launch is bound by the serial chain of its slowest ray planes, which the pair shortens (measured on B200:
+// 1/4 of a 4K frame 0.79 -> 0.67 ms, 1/8 0.79 -> 0.59 ms; a full frame is throughput-bound and 15-30 % slower on
+// the pair).  That is the multi-GPU slice mode from 4 GPUs up and small windows.  65 = k_traverse_f always,
+// 68 = k_traverse_p always, 64 = k_traverse_w, 66/67 = k_traverse_c, else k_traverse<lanes>.
+int pick_lanes(const rlerc_ctx* c, int rays, bool ids)
 {
-	(void)rays;
-	return c->lanes;   // 0 = k_traverse_f (filter + warp per ray plane), 64 = k_traverse_w, else k_traverse<lanes>
+	if (c->lanes != 0) return c->lanes;
+	if (!ids && c->dda_mode != 99 && rays > 0 && rays <= 12 * c->sm_count) return 68;
+	return 0;
 }
 
 } // namespace
@@ -198,6 +207,7 @@ int rlerc_create(int device, rlerc_ctx** out)
 	rlerc_ctx* c = new rlerc_ctx();
 	c->device = device;
 	CK(cudaSetDevice(device));
+	CK(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
 	CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
 	for (int i = 0; i < 4; i++) CK(cudaEventCreate(&c->ev[i]));
@@ -299,9 +309,9 @@ int rlerc_scene_device_maps(rlerc_ctx* c, rlerc_map4* out16, int* nummaps)
 
 int rlerc_set_lanes_per_ray(rlerc_ctx* c, int lanes)
 {
-	if (!c || !(lanes == 0 || lanes == 1 || lanes == 2 || lanes == 4 || lanes == 8 || lanes == 16 || lanes == 32 || (lanes >= 64 && lanes <= 67)))
+	if (!c || !(lanes == 0 || lanes == 1 || lanes == 2 || lanes == 4 || lanes == 8 || lanes == 16 || lanes == 32 || (lanes >= 64 && lanes <= 68)))
 	{
-		set_error("lanes per ray must be 0,1,2,4,8,16,32 or a kernel code 64..67");
+		set_error("lanes per ray must be 0,1,2,4,8,16,32 or a kernel code 64..68");
 		return RLERC_ERR_ARG;
 	}
 	c->lanes = lanes;
@@ -357,9 +367,9 @@ static int render_impl(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_c
 	}
 	TraverseParams P;
 	if ((rc = fill_traverse(c, rm, cfg, ray_begin, ray_end, d_warp, P))) return rc;
-	if (cfg->flags != 0 && !(c->lanes == 0 || c->lanes == 65))
+	if (cfg->flags != 0 && !(c->lanes == 0 || c->lanes == 65 || c->lanes == 68))
 	{
-		set_error("frame config flags (CLIPREGION / HEIGHT_COLOR) are implemented by the production traversal kernel only (lanes_per_ray = 0)");
+		set_error("frame config flags (CLIPREGION / HEIGHT_COLOR) are implemented by the production traversal kernels only (lanes_per_ray = 0, 65, 68)");
 		return RLERC_ERR_ARG;
 	}
 	if (slice_n > 1) { P.slice_block = slice_block; P.slice_n = slice_n; P.slice_rank = slice_rank; P.ray_begin = 0; }
@@ -381,7 +391,8 @@ static int render_impl(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_c
 		P.dda_ring = c->d_ring; P.dda_head = c->d_ring_ctl; P.dda_tail = c->d_ring_ctl + cap; P.dda_err = c->d_ring_ctl + 2 * cap;
 	}
 	if (c->timing) CK(cudaEventRecord(c->ev[0], c->stream));
-	launch_traverse(P, pick_lanes(c, P.ray_end - P.ray_begin), ids, c->stream);
+	const int launch_rays = (P.slice_n > 1) ? owned_count(P.ray_end, P.slice_block, P.slice_n, P.slice_rank) : P.ray_end - P.ray_begin;
+	launch_traverse(P, pick_lanes(c, launch_rays, ids), ids, c->stream);
 	if (c->timing) { CK(cudaEventRecord(c->ev[1], c->stream)); c->ev_valid[0] = true; }
 	CK(cudaGetLastError());
 	return RLERC_OK;

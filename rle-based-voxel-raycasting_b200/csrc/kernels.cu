@@ -414,6 +414,7 @@ static void launch_traverse_t(const TraverseParams& p, cudaStream_t st)
 void launch_traverse(const TraverseParams& p, int lanes, bool ids, cudaStream_t st)
 {
 	if (lanes == 0 || lanes == 65) { launch_traverse_filter(p, ids, st); return; }
+	if (lanes == 68) { if (ids) launch_traverse_filter(p, ids, st); else launch_traverse_pair(p, st); return; }
 	if (lanes == 64) { launch_traverse_warp(p, ids, st); return; }
 	if (lanes == 66 || lanes == 67) { launch_traverse_chunk(p, ids, lanes == 67 ? 7 : 3, st); return; }
 	switch (lanes)

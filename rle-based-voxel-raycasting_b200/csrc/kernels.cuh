@@ -72,6 +72,7 @@ void launch_soft(const SoftParams& p, cudaStream_t st);
 void launch_traverse(const TraverseParams& p, int lanes_per_ray, bool ids, cudaStream_t st);
 void launch_traverse_warp(const TraverseParams& p, bool ids, cudaStream_t st);   // traverse_warp.cu
 void launch_traverse_filter(const TraverseParams& p, bool ids, cudaStream_t st); // traverse_filter.cu
+void launch_traverse_pair(const TraverseParams& p, cudaStream_t st);              // traverse_filter.cu (k_traverse_p, variant 68)
 void launch_traverse_chunk(const TraverseParams& p, bool ids, int wpb, cudaStream_t st); // traverse_chunk.cu
 size_t traverse_ring_bytes(int rays);
 void launch_unwarp(const UnwarpParams& p, cudaStream_t st);

@@ -610,6 +610,390 @@ static void launch_f(const TraverseParams& p, cudaStream_t st)
 	k_traverse_f<IDS, PROF><<<blocks, wpb * 32, smem, st>>>(p, rays);
 }
 
+
+// ================================================================================================================
+// k_traverse_p (variant 68; picked automatically for launches of at most 12 ray planes per SM, capi.cu pick_lanes):
+// the same algorithm with the two loops of k_traverse_f on TWO warps per
+// ray plane.  Warp F runs the FILTER (DDA, first-run test, pointer-map gather) and pushes the live columns into a ring
+// in shared memory; warp C pops batches of 32, loads and projects their runs and runs consume_batch.  A ray plane's
+// chain becomes max(filter, consume) instead of their sum.  The filter only ever drops provable no-ops under a horizon
+// that can only rise, so a stale y_clip_min (published by C after every batch) lets more columns through but cannot
+// change the result: the picture does not depend on timing.
+// Protocol (volatile words in shared memory, one writer each): tail (F), head (C), ycmin (C), done (F), closed (C).
+// F waits while the ring has no room for 32 more entries, C waits until 32 entries are there or F is done; both
+// waits are bounded (a broken protocol raises `closed`/`done` instead of hanging the GPU).
+#ifndef RLERC_P_RCAP
+#define RLERC_P_RCAP 128
+#endif
+//                    // ring capacity in columns (power of two, >= 64)
+#define RLERC_P_RING (8 * RLERC_P_RCAP)     // words: 8 fields x RCAP, field-major
+#define RLERC_P_PLANES 4                    // ray planes per block (8 warps: F0..F3 | C0..C3, roles by warpgroup)
+#define RLERC_P_SPIN_MAX (1 << 22)
+
+// Register re-balancing between the roles (setmaxnreg, sm_90+): launch with a cap that admits 3 blocks per SM
+// (84 registers), the filter warpgroup gives registers back, the consume warpgroup takes them: 24 warps and 12 ray
+// planes per SM instead of 16 and 8.  RLERC_P_REG_F = 0 switches it off (2 blocks per SM, 128 registers for both roles).
+#ifndef RLERC_P_REG_F
+#define RLERC_P_REG_F 48
+#endif
+#ifndef RLERC_P_REG_C
+#define RLERC_P_REG_C 112
+#endif
+// The pool is what the block was LAUNCHED with: ptxas rounds the 3-blocks-per-SM cap (85) down to 80 registers per
+// thread, so the consume side can take at most 2 * 80 - RLERC_P_REG_F; asking for more spins in USETMAXREG.TRY_ALLOC
+// forever (measured the hard way).
+static_assert(RLERC_P_REG_F == 0 || RLERC_P_REG_F + RLERC_P_REG_C <= 160, "setmaxnreg: the consume warpgroup cannot take more registers than the filter warpgroup gives back");
+#define RLERC_STR2(x) #x
+#define RLERC_STR(x) RLERC_STR2(x)
+
+__global__ void __launch_bounds__(RLERC_P_PLANES * 64, RLERC_P_REG_F ? 3 : 2)
+k_traverse_p(const __grid_constant__ TraverseParams P, int rays)
+{
+	constexpr bool IDS = false, PROF = false;
+	extern __shared__ __align__(16) uint32_t smem[];
+	constexpr int G = 32;
+	const int gl = threadIdx.x & 31;
+	const int wid = threadIdx.x >> 5;
+	const bool roleC = wid >= RLERC_P_PLANES;
+	const int pl = roleC ? wid - RLERC_P_PLANES : wid;               // ray plane of this warp inside the block
+	const unsigned FULL = 0xffffffffu;
+	const unsigned lt_mask = (1u << gl) - 1u;
+
+	const int ray_i = (int)blockIdx.x * RLERC_P_PLANES + pl;         // launch-local ray index
+	// no early return before setmaxnreg (every warp of a warpgroup has to execute it): an out-of-range pair
+	// computes on a valid dummy ray plane and stays inactive
+	const bool inrange = ray_i < rays && owned_ray(P, ray_i) < P.ray_end;
+	const int x = inrange ? owned_ray(P, ray_i) : P.ray_begin;
+
+	// shared per ray plane: crossing records | ring | ctl | DrawJob | projections + span records | occlusion bits
+	const int per_plane = (RLERC_F_REC + RLERC_P_RING + 8 + 16 + RLERC_PS_WORDS + P.mask_words + 3) & ~3;
+	uint32_t* wbase = smem + (size_t)pl * per_plane;
+	float4* rec = reinterpret_cast<float4*>(wbase);
+	uint32_t* ring = wbase + RLERC_F_REC;                            // [8][RCAP]
+	volatile int* ctl = reinterpret_cast<volatile int*>(wbase + RLERC_F_REC + RLERC_P_RING);   // tail, head, ycmin, done, closed
+	DrawJob* job = reinterpret_cast<DrawJob*>(wbase + RLERC_F_REC + RLERC_P_RING + 8);
+	int2* proj = reinterpret_cast<int2*>(wbase + RLERC_F_REC + RLERC_P_RING + 8 + 16);
+	uint32_t* shade = wbase + RLERC_F_REC + RLERC_P_RING + 8 + 16 + RLERC_RW * 64;
+	uint32_t* ymask = wbase + RLERC_F_REC + RLERC_P_RING + 8 + 16 + RLERC_PS_WORDS;
+
+	const int res_y = P.res_y;
+	const float res_y2 = (float)(res_y / 2);
+	uint32_t* row = P.warp + (size_t)x * res_y;
+	RayInit ri;
+	ray_init(P, x, ri);
+	const float ray_x = ri.ray_x, ray_z = ri.ray_z, rx2mr = ri.rx2mr;
+	const bool vertical = ri.vertical;
+	const float sin_x = P.sin_x, cos_x = P.cos_x;
+	const float vpx = P.viewpos[0], mountain = P.viewpos[1], vpz = P.viewpos[2];
+	const float pz_add = sin_x;
+	const float py_add = (vertical ? cos_x : 0.0f) * rx2mr;
+	const int ymin0 = ri.ycmin, ymax0 = ri.ycmax;
+
+	// control words: C initialises, the named barrier below (both warps of the pair) publishes them
+	if (roleC)
+	{
+		if (inrange) clear_outside<G>(row, res_y, ri, gl);
+		for (int w = gl; w < P.mask_words; w += G) ymask[w] = 0;
+		if (gl == 0) { ctl[0] = 0; ctl[1] = 0; ctl[2] = ri.ycmin; ctl[3] = 0; ctl[4] = (ri.skip || !inrange) ? 1 : 0; }
+	}
+	asm volatile("bar.sync %0, 64;" :: "r"(1 + pl) : "memory");     // named barrier per ray plane: 2 warps
+	const bool active = inrange && !ri.skip;
+
+	if (!roleC)
+	{
+#if RLERC_P_REG_F
+		asm volatile("setmaxnreg.dec.sync.aligned.u32 " RLERC_STR(RLERC_P_REG_F) ";");
+#endif
+		if (!active) return;
+		// ================= warp F: DDA -> geometry + gather -> first-run test -> ring ==========================
+		int fixx, fixz;
+		DdaQ Q;
+		{
+			Dda dd;
+			dda_init(P, ray_x, ray_z, dd);
+			fixx = dd.fixx; fixz = dd.fixz;
+			Q.d0 = dd.d0; Q.x0 = dd.i0x; Q.y0 = dd.i0y; Q.nd1 = -dd.d1; Q.x1 = dd.i1x; Q.y1 = dd.i1y;
+			Q.gd0 = dd.gd0; Q.gx0 = dd.g0x; Q.gy0 = dd.g0y; Q.ngd1 = -dd.gd1; Q.gx1 = dd.g1x; Q.gy1 = dd.g1y;
+		}
+		Q.mip = 0; Q.zi = 0; Q.dzi = 1; Q.mapswitch = P.mapswitch0;
+		if (gl == 0) rec[0] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+		int prev_n = 0;
+		__syncwarp();
+		const int zfar_i = P.z_far;
+		const int last_map = P.nummaps - 1;
+		for (float yms = mountain; yms > 512.0f; yms = yms * 0.5f) ddaq_lod_switch(Q, last_map);
+		Geo fg;
+		fg.pz = fg.py = fg.czz = fg.cyy = 0; fg.cmip = 0; fg.cidx = 0;
+		unsigned fe0 = 0, fe1 = 0;
+		bool fhave = false;
+		int fn = 0;
+		bool dda_done = false;
+		int tail = 0;
+		bool closed = false;
+		while (!dda_done || fn > 0)
+		{
+			// room for 32 more entries?  (head only grows)
+			// (lane 0 reads the control words and broadcasts them: every decision on them is warp-uniform)
+			int spins = 0, ycmin = 0;
+			while (true)
+			{
+				int h = 0, c = 0, y = 0;
+				if (gl == 0) { h = ctl[1]; c = ctl[4]; y = ctl[2]; }
+				h = __shfl_sync(FULL, h, 0); c = __shfl_sync(FULL, c, 0); ycmin = __shfl_sync(FULL, y, 0);
+				if (c) { closed = true; break; }
+				if (tail + 32 - h <= RLERC_P_RCAP) break;
+				__nanosleep(64);
+				if (++spins > RLERC_P_SPIN_MAX) { if (gl == 0) ctl[4] = 1; closed = true; break; }
+			}
+			if (closed) break;                                         // ycmin: possibly stale, lower than the truth, never higher
+			int nvalid = 0;
+			if (!dda_done)
+			{
+				nvalid = ddaq_batch(Q, rec, prev_n, last_map, zfar_i, gl == 0);
+				prev_n = nvalid;
+				if (nvalid < G) dda_done = true;
+			}
+			__syncwarp();
+			if (fn > 0)
+			{
+				bool live = false;
+				if (gl < fn && fhave)
+				{
+					const int slen = (int)(fe1 & 0xffffu);
+					const unsigned first = fe1 >> 16;
+					const int solid = (int)(first >> 10), skip = (int)(first & 1023u);
+					if (slen == 0) live = false;
+					else if (solid == 0) live = true;
+					else
+					{
+						const float ft = (float)(skip << fg.cmip);
+						float zz1 = fg.pz, yy1 = fg.py;
+						if (mountain + ft >= 0) { zz1 += fg.czz; yy1 += fg.cyy; }
+						const float z1 = zz1 + pz_add * ft;
+						if (z1 <= 0) live = true;
+						else
+						{
+							const float y1 = yy1 + py_add * ft;
+							live = f2i(res_y2 + y1 / z1) > ycmin;
+						}
+					}
+				}
+				const unsigned lb = __ballot_sync(FULL, live);
+				if (live)
+				{
+					uint32_t* q = ring + ((tail + __popc(lb & lt_mask)) & (RLERC_P_RCAP - 1));
+					q[0 * RLERC_P_RCAP] = __float_as_uint(fg.pz); q[1 * RLERC_P_RCAP] = __float_as_uint(fg.py);
+					q[2 * RLERC_P_RCAP] = __float_as_uint(fg.czz); q[3 * RLERC_P_RCAP] = __float_as_uint(fg.cyy);
+					q[4 * RLERC_P_RCAP] = (uint32_t)fg.cmip; q[5 * RLERC_P_RCAP] = (uint32_t)fg.cidx;
+					q[6 * RLERC_P_RCAP] = fe0; q[7 * RLERC_P_RCAP] = fe1;
+				}
+				tail += __popc(lb);
+				__threadfence_block();
+				__syncwarp();
+				if (gl == 0 && lb) ctl[0] = tail;
+			}
+			fn = nvalid;
+			fhave = false;
+			if (gl < nvalid)
+			{
+				const float4 ra = rec[gl], rb = rec[gl + 1];
+				const float db = fabsf(ra.x), dn = fabsf(rb.x);
+				const int ib = __float_as_int(ra.x) < 0 ? 1 : 0;
+				fg.cmip = __float_as_int(rb.w);
+				const int fix_x = (1 - ib) * fixx, fix_z = ib * fixz;
+				const float ddelta = dn - db;
+				const float vsx = ray_x * db, vsz = ray_z * db;
+				const int voxel_x = f2i(vpx + ra.y) + fix_x;
+				const int voxel_z = f2i(vpz + ra.z) + fix_z;
+				const int gx = P.level[fg.cmip].sx, gz = P.level[fg.cmip].sz;
+				const bool outside = (P.flags & 1) && (voxel_x < 0 || voxel_z < 0 || (voxel_x >> fg.cmip) > gx - 1 || (voxel_z >> fg.cmip) > gz - 1);
+				const int vx = (voxel_x >> fg.cmip) & (gx - 1);
+				const int vz = (voxel_z >> fg.cmip) & (gz - 1);
+				fg.cidx = vx + vz * gx;
+				const float corx = ray_x * ddelta, corz = ray_z * ddelta;
+				fg.pz = cos_x * vsz + sin_x * mountain;
+				fg.py = vertical ? (cos_x * mountain - sin_x * vsz) : vsx;
+				fg.py *= rx2mr;
+				fg.czz = cos_x * corz;
+				fg.cyy = vertical ? (-sin_x * corz) : corx;
+				fg.cyy *= rx2mr;
+				fhave = !outside && (!(fg.pz * res_y2 + fg.py <= fg.pz * (float)ycmin) || !(fg.pz > 0));
+				if (fhave)
+				{
+					const uint2 ent = __ldg(P.level[fg.cmip].map + fg.cidx);
+					fe0 = ent.x; fe1 = ent.y;
+				}
+			}
+			__syncwarp();
+		}
+		__threadfence_block();
+		__syncwarp();
+		if (gl == 0 && !closed) { ctl[0] = tail; __threadfence_block(); ctl[3] = 1; }
+		return;
+	}
+
+	// ===================== warp C: ring -> run words -> projection -> consume_batch ============================
+#if RLERC_P_REG_F
+	asm volatile("setmaxnreg.inc.sync.aligned.u32 " RLERC_STR(RLERC_P_REG_C) ";");
+#endif
+	if (!active) return;
+	HorizonState Hs;
+	Hs.ycmin = ri.ycmin; Hs.ycmax = ri.ycmax; Hs.hiw = 0;
+	Counters Cn;
+	memset(&Cn, 0, sizeof(Cn));
+	RayCtx R;
+	R.row = row; R.ymask = ymask; R.ids = nullptr;
+	R.res_y2 = res_y2; R.pz_add = pz_add; R.py_add = py_add; R.mountain = mountain; R.gl = gl;
+	R.stat = nullptr;
+	R.hc_on = (P.flags & 2) ? 1 : 0;
+	R.hc = f2i((4095.0f - mountain) + P.viewpos[1]);
+	Geo g0;
+	g0.pz = g0.py = g0.czz = g0.cyy = 0; g0.cmip = 0; g0.cidx = 0;
+	Stage s0;
+	s0.nvalid = 0; s0.have = false; s0.e0 = s0.e1 = 0;
+	#pragma unroll
+	for (int k = 0; k < 4; k++) s0.rw[k] = 0;
+	int head = 0;
+	while (true)
+	{
+		if (Hs.ycmin >= Hs.ycmax) break;
+		// C1. wait for a full batch (or the end of the ray plane), pop it, request its run words
+		int done = 0, avail = 0, spins = 0;
+		while (true)
+		{
+			int d = 0, t = 0;
+			if (gl == 0)
+			{
+				d = ctl[3];                                           // read BEFORE tail: done implies the final tail is visible
+				__threadfence_block();
+				t = ctl[0];
+			}
+			done = __shfl_sync(FULL, d, 0);
+			avail = __shfl_sync(FULL, t, 0) - head;
+			if (avail >= 32 || done) break;
+			__nanosleep(64);
+			if (++spins > RLERC_P_SPIN_MAX) { done = 1; break; }
+		}
+		__syncwarp();
+		Stage s1;
+		Geo g1;
+		{
+			const int n1 = avail < 32 ? avail : 32;
+			s1.nvalid = n1; s1.have = gl < n1;
+			s1.e0 = s1.e1 = 0;
+			#pragma unroll
+			for (int k = 0; k < 4; k++) s1.rw[k] = 0;
+			g1.pz = g1.py = g1.czz = g1.cyy = 0; g1.cmip = 0; g1.cidx = 0;
+			if (s1.have)
+			{
+				const uint32_t* q = ring + ((head + gl) & (RLERC_P_RCAP - 1));
+				g1.pz = __uint_as_float(q[0 * RLERC_P_RCAP]); g1.py = __uint_as_float(q[1 * RLERC_P_RCAP]);
+				g1.czz = __uint_as_float(q[2 * RLERC_P_RCAP]); g1.cyy = __uint_as_float(q[3 * RLERC_P_RCAP]);
+				g1.cmip = (int)q[4 * RLERC_P_RCAP]; g1.cidx = (int)q[5 * RLERC_P_RCAP];
+				s1.e0 = q[6 * RLERC_P_RCAP]; s1.e1 = q[7 * RLERC_P_RCAP];
+				const int sl = (int)(s1.e1 & 0xffffu);
+				const unsigned i0 = 2u + s1.e0;
+				const uint32_t* w32 = reinterpret_cast<const uint32_t*>(P.level[g1.cmip].slabs);
+				const uint32_t* p = w32 + ((i0 + (i0 & 1u)) >> 1);
+				const int odd = (int)(i0 & 1u);
+				s1.rw[0] = (sl > 1) ? __ldg(p) : 0u;
+				s1.rw[1] = (sl > 2 + odd) ? __ldg(p + 1) : 0u;
+				s1.rw[2] = (sl > 4 + odd) ? __ldg(p + 2) : 0u;
+				s1.rw[3] = (sl > 6 + odd) ? __ldg(p + 3) : 0u;
+			}
+			head += n1;
+			__syncwarp();
+			if (gl == 0 && n1) ctl[1] = head;                          // the slots may be overwritten from now on
+		}
+		// C2. project the runs of batch s0
+		if (s0.nvalid > 0)
+		{
+			const int ycmin = Hs.ycmin;
+			int slen = 0, nr = 0;
+			bool longcol = false;
+			unsigned flags = 0;
+			if (s0.have)
+			{
+				{
+					const unsigned first = s0.e1 >> 16;
+					const unsigned a = s0.rw[0], b = s0.rw[1], c = s0.rw[2], d = s0.rw[3];
+					if (!((2u + s0.e0) & 1u)) s0.rw[0] = first | (a & 0xffff0000u);
+					else
+					{
+						s0.rw[0] = first | (a << 16);
+						s0.rw[1] = __funnelshift_r(a, b, 16);
+						s0.rw[2] = __funnelshift_r(b, c, 16);
+						s0.rw[3] = __funnelshift_r(c, d, 16);
+					}
+				}
+				slen = (int)(s0.e1 & 0xffffu);
+				nr = slen < RLERC_RW ? slen : RLERC_RW;
+				longcol = slen > RLERC_RW;
+				int blen = 0;
+				for (int r = 0; r < nr; r++)
+				{
+					const unsigned rw = run_word(s0.rw, r);
+					const int skip = (int)(rw & 1023u), solid = (int)(rw >> 10);
+					const int top = (blen + skip) << g0.cmip;
+					const int bot = top + (solid << g0.cmip);
+					blen += skip + solid;
+					if (solid == 0) continue;
+					const float ft = (float)top, fb = (float)bot;
+					float zz1 = g0.pz, yy1 = g0.py;
+					if (mountain + ft >= 0) { zz1 += g0.czz; yy1 += g0.cyy; }
+					const float z1 = zz1 + pz_add * ft;
+					if (z1 <= 0) continue;
+					flags |= 1u << r;
+					const float y1 = yy1 + py_add * ft;
+					const int sy2 = f2i(res_y2 + y1 / z1);
+					int sy1 = 0;
+					if (sy2 > ycmin)
+					{
+						float zz2 = g0.pz, yy2 = g0.py;
+						if (mountain + fb < 0) { zz2 += g0.czz; yy2 += g0.cyy; }
+						const float z2 = zz2 + pz_add * fb;
+						if (!(z2 <= 0))
+						{
+							flags |= 1u << (8 + r);
+							const float y2 = yy2 + py_add * fb;
+							sy1 = f2i(res_y2 + y2 / z2 - 1);
+						}
+					}
+					proj[r * 32 + gl] = make_int2(sy1, sy2);
+					if (sy2 <= ycmin) { nr = r + 1; longcol = false; break; }
+				}
+			}
+			const bool finished = consume_batch<IDS, PROF>(P, R, Hs, Cn, s0, g0, slen, nr, longcol, flags, proj, shade, job);
+			if (gl == 0) ctl[2] = Hs.ycmin;                            // the filter's (stale) horizon
+			if (finished) break;
+		}
+		else if (s1.nvalid == 0 && done) break;                        // drained
+		s0 = s1; g0 = g1;
+	}
+	__syncwarp();
+	if (gl == 0) ctl[4] = 1;                                           // releases a filter warp that is still running
+	for (int y = ymin0 + gl; y <= ymax0; y += G)
+		if (!((ymask[y >> 5] >> (y & 31)) & 1u)) row[y] = RLERC_SKY;
+}
+
+void launch_traverse_pair(const TraverseParams& p, cudaStream_t st)
+{
+	const int rays = (p.slice_n > 1) ? owned_count(p.ray_end, p.slice_block, p.slice_n, p.slice_rank) : p.ray_end - p.ray_begin;
+	if (rays <= 0) return;
+	const int blocks = (rays + RLERC_P_PLANES - 1) / RLERC_P_PLANES;
+	const size_t smem = (size_t)RLERC_P_PLANES * ((RLERC_F_REC + RLERC_P_RING + 8 + 16 + RLERC_PS_WORDS + p.mask_words + 3) & ~3) * sizeof(uint32_t);
+	static size_t configured_on[64] = { 0 };
+	int dev = 0;
+	cudaGetDevice(&dev);
+	size_t& configured = configured_on[dev & 63];
+	if (smem > configured)
+	{
+		cudaFuncSetAttribute(k_traverse_p, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		configured = smem;
+	}
+	k_traverse_p<<<blocks, RLERC_P_PLANES * 64, smem, st>>>(p, rays);
+}
+
 void launch_traverse_filter(const TraverseParams& p, bool ids, cudaStream_t st)
 {
 	if (p.dda_mode == 99) launch_f<false, true>(p, st);          // tools/ray_profile.py

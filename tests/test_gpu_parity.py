@@ -37,7 +37,7 @@ def _oracle(rb, rm, scene, cfg, ids=False):
     return orm, warp, oid, cnt
 
 
-@pytest.mark.parametrize("lanes", [0, 66, 67, 65, 64, 32, 8, 1])
+@pytest.mark.parametrize("lanes", [0, 68, 66, 67, 65, 64, 32, 8, 1])
 def test_warp_buffer_bit_exact_camera_grid(R, rb, gpu, scene_mid, lanes):
     gpu.all_to_gpu(scene_mid)
     gpu.set_lanes_per_ray(lanes)
@@ -193,7 +193,7 @@ def test_degenerate_scenes_bit_exact(R, rb, gpu):
                 assert abs(c[k] - cnt[k]) <= 0.005 * cnt[k], (name, k, c[k], cnt[k], rot)
                 if name != "noise50":
                     assert c[k] == cnt[k], (name, k, c[k], cnt[k], rot)
-            for lanes in (0, 64, 66, 32, 1):
+            for lanes in (0, 65, 68, 64, 66, 32, 1):
                 gpu.set_lanes_per_ray(lanes)
                 _fresh_warp(gpu, cfg)
                 gpu.render(rm, cfg)
@@ -495,10 +495,12 @@ def test_core_h_options_clipregion_height_color(R, rb, gpu, scene_small, scene_m
                 rm = R.RayMap(cfg).get_ray_map(pos, rot)
                 orm = oracle_raymap(rb, rm, scene)
                 want, _, _ = rb.orc_render(orm, cfg.render_size, cfg.rays_casted, cfg.mip_distance, cfg.z_far, flags=flags)
-                _fresh_warp(gpu, cfg)
-                gpu.render(rm, cfg)
-                got = gpu.read_warp(cfg)
-                assert np.array_equal(got, want), (flags, wh, pos, int((got != want).sum()))
+                for lanes in (0, 65, 68):          # automatic choice, k_traverse_f, k_traverse_p
+                    gpu.set_lanes_per_ray(lanes)
+                    _fresh_warp(gpu, cfg)
+                    gpu.render(rm, cfg)
+                    got = gpu.read_warp(cfg)
+                    assert np.array_equal(got, want), (flags, lanes, wh, pos, int((got != want).sum()))
     cfg = R.FrameConfig.default(512, 384)
     cfg.flags = flags
     gpu.set_lanes_per_ray(64)

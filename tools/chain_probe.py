@@ -12,6 +12,7 @@ scene, name, sy = bench.build_scene(R, workload, lambda m: None)
 W, H = bench.WORKLOADS[workload][3]
 cfg = R.FrameConfig.default(W, H)
 r = R.Renderer(0); r.all_to_gpu(scene); r.set_timing(True); r.set_dda_mode(mode)
+r.set_lanes_per_ray(int(os.environ.get("CHAIN_LANES", "65")))     # 65 = k_traverse_f always (0 would pick k_traverse_p for the small shares)
 for t in (0, 250, 750):
     pos, rot = bench.path_pose(R, t, 1000, sy, False)
     rm = R.RayMap(cfg).get_ray_map(pos, rot)

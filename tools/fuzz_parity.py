@@ -17,6 +17,7 @@ scenes = [("terrain128", R.RLE4.synth(0, 128, 128, 128, seed=1), 128), ("runs128
 from util import edge_scenes
 scenes += [("edge_" + k, v, 64) for k, v in edge_scenes(R).items()]
 r = R.Renderer(0)
+r.set_lanes_per_ray(int(os.environ.get("FUZZ_LANES", "0")))      # 0 = automatic choice, 65 = k_traverse_f, 68 = k_traverse_p
 bad = 0
 for i in range(N):
     name, scene, size = rnd.choice(scenes)
