@@ -83,7 +83,7 @@ typedef struct rlerc_frame_config {
 #define RLERC_FLAG_CLIPREGION   1
 /* R/src/core.h:22 HEIGHT_COLOR: the low attribute byte is scaled by the camera height (R/src/Cuda_Render.h:674-676,716-722). */
 #define RLERC_FLAG_HEIGHT_COLOR 2
-/* Both are implemented by the production traversal kernel (lanes_per_ray = 0) only. */
+/* Both are implemented by the production traversal kernels (lanes_per_ray = 0, 65, 68) only. */
 
 /* Defaults exactly as R/src/core.h for a W x H window: render_size=W, rays=4W,
  * z_far=80000, mip_distance=W, border=(1-H/W)/2 (=0.125 for 1024x768, main.cpp:774-776). */
@@ -136,9 +136,12 @@ void rlerc_destroy(rlerc_ctx* c);
 int  rlerc_scene_upload(rlerc_ctx* c, const rlerc_scene* s);
 /* Device-side Map4 table as main.cpp:277-278 copies it into the ray map (all levels). */
 int  rlerc_scene_device_maps(rlerc_ctx* c, rlerc_map4* out16, int* nummaps);
-/* Traversal kernel variant, all bit-identical: 0 = production kernel k_traverse_f (one warp per ray plane, column
- * filter in front of the occlusion machinery); 64 = k_traverse_w (one warp per ray plane, three-stage pipeline
- * over all columns); 1,2,4,8,16,32 = k_traverse<lanes> (lane <-> run; 1 is the reference's thread-per-ray scheme). */
+/* Traversal kernel variant, all bit-identical: 0 = automatic (default): the production kernel k_traverse_f (one warp
+ * per ray plane, column filter in front of the occlusion machinery), or k_traverse_p (a filter warp and a consume warp
+ * per ray plane) when the launch has at most 12 ray planes per SM and is therefore bound by its longest ray planes
+ * (multi-GPU slices, small windows); 65 = k_traverse_f always; 68 = k_traverse_p always; 64 = k_traverse_w (one warp
+ * per ray plane, three-stage pipeline over all columns); 66, 67 = k_traverse_c (DDA in a dedicated warp);
+ * 1,2,4,8,16,32 = k_traverse<lanes> (lane <-> run; 1 is the reference's thread-per-ray scheme). */
 int  rlerc_set_lanes_per_ray(rlerc_ctx* c, int lanes);
 /* k_traverse_w only: run the DDA in dedicated producer blocks or inside every warp (default). */
 int  rlerc_set_dda_producer(rlerc_ctx* c, int on);
