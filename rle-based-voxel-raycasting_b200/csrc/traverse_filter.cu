@@ -621,7 +621,13 @@ static void launch_f(const TraverseParams& p, cudaStream_t st)
 // change the result: the picture does not depend on timing.
 // Protocol (volatile words in shared memory, one writer each): tail (F), head (C), ycmin (C), done (F), closed (C).
 // F waits while the ring has no room for 32 more entries, C waits until 32 entries are there or F is done; both
-// waits are bounded (a broken protocol raises `closed`/`done` instead of hanging the GPU).
+// waits are bounded (a broken protocol raises `closed`/`done` instead of hanging the GPU).  Waiting is __nanosleep(64)
+// polling by the whole warp; on a full frame the polling loops are up to 30 % of the kernel's instructions (ncu source
+// view).  Tried instead, all bit-exact, all slower (1080p frame 0, full frame / uncontended chain, ms; shipped: 0.86 /
+// 0.36): back-off 128 ns .. 2 us 0.85 / 0.37; back-off 512 ns .. 8 us 0.94 / 0.46; mbarrier.try_wait as "sleep until
+// the partner signals" (one arrive per tail / head update; the phase bookkeeping falls behind when nobody waits, so
+// waits run into their time limit) 1.09 / 0.41; lane 0 polling alone with one vector load of the control words, the
+// other lanes parked at the broadcast shuffle 1.16 / 0.48.
 #ifndef RLERC_P_RCAP
 #define RLERC_P_RCAP 128
 #endif
