@@ -621,7 +621,7 @@ static void launch_f(const TraverseParams& p, cudaStream_t st)
 // change the result: the picture does not depend on timing.
 // Protocol (volatile words in shared memory, one writer each): tail (F), head (C), ycmin (C), done (F), closed (C).
 // F waits while the ring has no room for 32 more entries, C waits until 32 entries are there or F is done; both
-// waits are bounded (a broken protocol raises `closed`/`done` instead of hanging the GPU).  Waiting is __nanosleep(64)
+// waits are bounded (a broken protocol traps after >= 1 s of polling: a launch error, neither a hang nor a wrong picture).  Waiting is __nanosleep(64)
 // polling by the whole warp; on a full frame the polling loops are up to 30 % of the kernel's instructions (ncu source
 // view).  Tried instead, all bit-exact, all slower (1080p frame 0, full frame / uncontended chain, ms; shipped: 0.86 /
 // 0.36): back-off 128 ns .. 2 us 0.85 / 0.37; back-off 512 ns .. 8 us 0.94 / 0.46; mbarrier.try_wait as "sleep until
@@ -634,7 +634,7 @@ static void launch_f(const TraverseParams& p, cudaStream_t st)
 //                    // ring capacity in columns (power of two, >= 64)
 #define RLERC_P_RING (8 * RLERC_P_RCAP)     // words: 8 fields x RCAP, field-major
 #define RLERC_P_PLANES 4                    // ray planes per block (8 warps: F0..F3 | C0..C3, roles by warpgroup)
-#define RLERC_P_SPIN_MAX (1 << 22)
+#define RLERC_P_SPIN_MAX (1 << 24)            // >= 1 s of polling: the protocol is broken; fail loudly (launch error), never a wrong picture
 
 // Register re-balancing between the roles (setmaxnreg, sm_90+): launch with a cap that admits 3 blocks per SM
 // (84 registers), the filter warpgroup gives registers back, the consume warpgroup takes them: 24 warps and 12 ray
@@ -651,6 +651,8 @@ static void launch_f(const TraverseParams& p, cudaStream_t st)
 static_assert(RLERC_P_REG_F == 0 || RLERC_P_REG_F + RLERC_P_REG_C <= 160, "setmaxnreg: the consume warpgroup cannot take more registers than the filter warpgroup gives back");
 #define RLERC_STR2(x) #x
 #define RLERC_STR(x) RLERC_STR2(x)
+
+__device__ __noinline__ void pair_protocol_broken() { __trap(); }     // cold: keeps the trap out of the wait loops' code
 
 __global__ void __launch_bounds__(RLERC_P_PLANES * 64, RLERC_P_REG_F ? 3 : 2)
 k_traverse_p(const __grid_constant__ TraverseParams P, int rays)
@@ -749,7 +751,7 @@ k_traverse_p(const __grid_constant__ TraverseParams P, int rays)
 				if (c) { closed = true; break; }
 				if (tail + 32 - h <= RLERC_P_RCAP) break;
 				__nanosleep(64);
-				if (++spins > RLERC_P_SPIN_MAX) { if (gl == 0) ctl[4] = 1; closed = true; break; }
+				if (++spins > RLERC_P_SPIN_MAX) { pair_protocol_broken(); if (gl == 0) ctl[4] = 1; closed = true; break; }
 			}
 			if (closed) break;                                         // ycmin: possibly stale, lower than the truth, never higher
 			int nvalid = 0;
@@ -878,7 +880,7 @@ k_traverse_p(const __grid_constant__ TraverseParams P, int rays)
 			avail = __shfl_sync(FULL, t, 0) - head;
 			if (avail >= 32 || done) break;
 			__nanosleep(64);
-			if (++spins > RLERC_P_SPIN_MAX) { done = 1; break; }
+			if (++spins > RLERC_P_SPIN_MAX) { pair_protocol_broken(); done = 1; break; }
 		}
 		__syncwarp();
 		Stage s1;
