@@ -6,6 +6,21 @@
 
 namespace rlerc {
 
+// Stores into the warped ray buffer.  RLERC_STREAM_STORES: cache-streaming (evict-first) stores, so that the 56-225 MB
+// the traversal writes per frame do not push the compressed scene (gathered on the ray planes' critical chain) out of L2.
+#ifndef RLERC_STREAM_STORES
+#define RLERC_STREAM_STORES 0
+#endif
+__device__ __forceinline__ void st_warp(uint32_t* p, uint32_t v)
+{
+#if RLERC_STREAM_STORES
+	__stcs(p, v);
+#else
+	*p = v;
+#endif
+}
+
+
 #define RLERC_BLOCK 128
 #define RLERC_SKY 0xff8844u
 
@@ -154,8 +169,8 @@ template <int G>
 __device__ __forceinline__ void clear_outside(uint32_t* row, int res_y, const RayInit& r, int gl)
 {
 	const int lo = r.skip ? res_y : r.ycmin, hi = r.skip ? res_y - 1 : r.ycmax;
-	for (int y = gl; y < lo; y += G) row[y] = 0;
-	for (int y = hi + 1 + gl; y < res_y; y += G) row[y] = 0;
+	for (int y = gl; y < lo; y += G) st_warp(row + y, 0u);
+	for (int y = hi + 1 + gl; y < res_y; y += G) st_warp(row + y, 0u);
 }
 
 // D (Cuda_Render.h:270-305): 2-D DDA over the x-z pointer map

@@ -124,7 +124,7 @@ __device__ __noinline__ int coop_span(const RayCtx& R, const uint16_t* send, flo
 			const unsigned real_z = (unsigned)f2i(1.0f / monez) & 0xfffeu;
 			unsigned c16 = (unsigned)__ldg(send + ui);
 			if (R.hc_on) c16 = height_color16(c16, R.hc);
-			R.row[yy] = c16 + (real_z << 16);
+			st_warp(R.row + yy, c16 + (real_z << 16));
 			if (IDS) { R.ids[yy * 2] = (uint32_t)colid; R.ids[yy * 2 + 1] = ((uint32_t)m << 16) | (uint32_t)ui; }
 		}
 		const unsigned wb = __ballot_sync(FULL, wr);
@@ -184,7 +184,7 @@ static __device__ __noinline__ void coop_span_claim(const RayCtx& R, const uint1
 			const unsigned real_z = (unsigned)f2i(1.0f / monez) & 0xfffeu;
 			unsigned c16 = (unsigned)__ldg(send + ui);
 			if (R.hc_on) c16 = height_color16(c16, R.hc);
-			R.row[yy] = c16 + (real_z << 16);
+			st_warp(R.row + yy, c16 + (real_z << 16));
 		}
 	}
 }
@@ -964,7 +964,7 @@ __device__ __forceinline__ bool consume_batch(const TraverseParams& P, const Ray
 				}
 				#pragma unroll
 				for (int k = 0; k < 4; k++)
-					if (k0 + k < n && ((clear >> k) & 1u)) row[y + k] = (R.hc_on ? height_color16(colr[k], R.hc) : colr[k]) + (zz[k] << 16);
+					if (k0 + k < n && ((clear >> k) & 1u)) st_warp(row + y + k, (R.hc_on ? height_color16(colr[k], R.hc) : colr[k]) + (zz[k] << 16));
 				y += 4; clear >>= 4;
 			}
 		}

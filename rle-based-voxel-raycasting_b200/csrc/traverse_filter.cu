@@ -577,7 +577,7 @@ k_traverse_f(const __grid_constant__ TraverseParams P, int rays)
 
 	// sky sentinel on every pixel of the clip range that no run covered
 	for (int y = ymin0 + gl; y <= ymax0; y += G)
-		if (!((ymask[y >> 5] >> (y & 31)) & 1u)) row[y] = RLERC_SKY;
+		if (!((ymask[y >> 5] >> (y & 31)) & 1u)) st_warp(row + y, RLERC_SKY);
 
 	if (IDS) flush_counters(P, Cn, gl, ymax0 - ymin0 + 1);
 	if (PROF && gl == 0)
@@ -981,7 +981,7 @@ k_traverse_p(const __grid_constant__ TraverseParams P, int rays)
 	__syncwarp();
 	if (gl == 0) ctl[4] = 1;                                           // releases a filter warp that is still running
 	for (int y = ymin0 + gl; y <= ymax0; y += G)
-		if (!((ymask[y >> 5] >> (y & 31)) & 1u)) row[y] = RLERC_SKY;
+		if (!((ymask[y >> 5] >> (y & 31)) & 1u)) st_warp(row + y, RLERC_SKY);
 }
 
 void launch_traverse_pair(const TraverseParams& p, cudaStream_t st)
