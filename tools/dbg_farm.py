@@ -1,3 +1,5 @@
+"""Debug helper for the frame-parallel multi-GPU mode (FrameFarm): per-round timings of render / gather on every rank.
+usage: python -m torch.distributed.run --nproc-per-node N tools/dbg_farm.py"""
 import importlib, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)

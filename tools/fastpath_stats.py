@@ -1,3 +1,5 @@
+"""How many consume batches take the B0 fast path and why the others were refused (debug counters of the instrumented
+build).  usage: python tools/fastpath_stats.py WORKLOAD"""
 import ctypes as C, importlib, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
