@@ -1,5 +1,5 @@
 """Render one interleaved ray-plane slice of a bench frame a few times (for ncu / timing of the slice mode).
-usage: python tools/profile_slice.py WORKLOAD FRAME_T NRANKS [RANK]"""
+usage: python tools/profile_slice.py WORKLOAD FRAME_T NRANKS"""
 import importlib, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
