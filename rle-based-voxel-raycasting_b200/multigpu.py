@@ -63,15 +63,17 @@ class FrameFarm:
     next round's rendering (double-buffered).  This is BASELINE config 5's "one camera per GPU with
     NVLink compositing" applied to the fly-through; per-frame latency is that of one GPU."""
 
-    def __init__(self, renderer, cfg, torch, rank, world, dist):
+    def __init__(self, renderer, cfg, torch, rank, world, dist, device=None):
         self.r, self.cfg, self.torch, self.rank, self.world, self.dist = renderer, cfg, torch, rank, world, dist
-        dev = torch.device("cuda", renderer.device)
+        # device: only the CPU tests of the dealing / gathering logic (gloo, a stand-in renderer) pass one
+        dev = device if device is not None else torch.device("cuda", renderer.device)
         shape = (cfg.height, cfg.width, 4)
         self.bufs = [torch.zeros(shape, dtype=torch.uint8, device=dev) for _ in range(2)]
         self.lists = [[torch.empty(shape, dtype=torch.uint8, device=dev) for _ in range(world)] if rank == 0 else None
                       for _ in range(2)]
         self.handles = [None, None]
-        renderer.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+        if dev.type == "cuda":
+            renderer.set_stream(torch.cuda.current_stream(dev).cuda_stream)
 
     def render_round(self, rd, raymap_gpu):
         """Render this rank's frame of round `rd` (None: no frame left) and start gathering the round."""

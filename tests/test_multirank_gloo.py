@@ -66,3 +66,76 @@ def test_interleaved_partition_arithmetic():
                 assert all(sum(m[i] for m in masks) == 1 for i in range(count))
                 for r in range(n):
                     assert MG.owned_count(count, block, n, r) == sum(masks[r])
+
+
+class _OracleRenderer:
+    """Stand-in for Renderer in the CPU test of FrameFarm: `render` + `unwarp` produce the oracle's frame for the ray
+    map and copy it to the destination pointer (the product renderer launches the CUDA kernels there)."""
+    device = 0
+
+    def __init__(self, rb, scene, cfg):
+        self.rb, self.scene, self.cfg, self.frames = rb, scene, cfg, 0
+
+    def set_stream(self, s):
+        pass
+
+    def render(self, rm, cfg):
+        from util import oracle_raymap
+        self.orm = oracle_raymap(self.rb, rm, self.scene)
+        self.warp, _, _ = self.rb.orc_render(self.orm, cfg.render_size, cfg.rays_casted, cfg.mip_distance, cfg.z_far)
+
+    def unwarp(self, rm, cfg, d_rgba=None):
+        import ctypes as C
+        img = self.rb.orc_unwarp(self.orm, cfg.width, cfg.height, cfg.render_size, cfg.rays_casted, cfg.rays_casted_res, self.warp)
+        C.memmove(d_rgba, img.ctypes.data, img.nbytes)
+        self.frames += 1
+
+
+def _farm_worker(rank, world, port, out_path, nframes):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    R = importlib.import_module("rle-based-voxel-raycasting_b200")
+    MG = importlib.import_module("rle-based-voxel-raycasting_b200.multigpu")
+    from oracle import refbind as rb
+    scene = R.RLE4.synth(0, 64, 64, 64, seed=1)
+    cfg = R.FrameConfig.default(128, 96)
+    poses = [((10000.0 + 3.0 * i, -40.0, 10000.0), (0.4, 1.9 + 0.2 * i, 0.0)) for i in range(nframes)]
+    rend = _OracleRenderer(rb, scene, cfg)
+    farm = MG.FrameFarm(rend, cfg, torch, rank, world, dist, device=torch.device("cpu"))
+    rounds = (nframes + world - 1) // world
+    got = {}
+    for rd in range(rounds + 1):                                 # the loop of bench.py: gather of round rd-1 overlaps round rd
+        if rd < rounds:
+            i = rd * world + rank
+            farm.render_round(rd, R.RayMap(cfg).get_ray_map(*poses[i]) if i < nframes else None)
+        if rd > 0 and rank == 0:
+            done = farm.wait_round(rd - 1)
+            for j in range(world):
+                if (rd - 1) * world + j < nframes:
+                    got[(rd - 1) * world + j] = done[j].numpy().copy()
+    farm.finish()
+    dist.barrier()
+    assert rend.frames == len(range(rank, nframes, world))      # every rank rendered exactly its own frames
+    if rank == 0:
+        solo = _OracleRenderer(rb, scene, cfg)
+        ok = len(got) == nframes
+        for i in range(nframes):
+            buf = np.zeros((cfg.height, cfg.width, 4), np.uint8)
+            solo.render(R.RayMap(cfg).get_ray_map(*poses[i]), cfg)
+            solo.unwarp(None, cfg, d_rgba=buf.ctypes.data)
+            ok = ok and np.array_equal(got[i], buf)
+        open(out_path, "w").write("%d" % ok)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("nframes", [4, 5])
+def test_frame_farm_deals_and_gathers_whole_frames(tmp_path, nframes):
+    """Frames mode (the default for N > 1): frames dealt round-robin, double-buffered gather on rank 0, in order, also
+    when the last round is incomplete."""
+    out = str(tmp_path / "farm.txt")
+    port = 31500 + (os.getpid() % 2000) + nframes
+    mp.spawn(_farm_worker, args=(2, port, out, nframes), nprocs=2, join=True)
+    assert open(out).read() == "1"
