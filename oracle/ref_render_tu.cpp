@@ -28,6 +28,13 @@
 #define ushort ushort
 #include "Core.h"
 
+/* -DPERPIXELFORWARD (R/src/core.h:31): the per-pixel skip list REPLACES the shared-memory occlusion mask.  With both
+ * on, the pixel loop's `continue` at the mask test skips the loop's own ++y (Cuda_Render.h:682-731) and the loop
+ * never ends, so that build is SHAREMEMCLIP off (core.h:32 defines it unconditionally). */
+#ifdef PERPIXELFORWARD
+#undef SHAREMEMCLIP
+#endif
+
 static int g_ref_screen_size_x = 1024;
 static int g_ref_rays_distance = 80000;
 #undef SCREEN_SIZE_X
@@ -110,14 +117,27 @@ int ref_render_frame(const void* raymap_gpu, int res_x, int res_y, int mip_dista
 	{
 		unsigned int* mask = (unsigned int*)malloc(mask_words * sizeof(unsigned int));
 		uint dummy[4];
+#ifdef PERPIXELFORWARD
+		/* that build really uses the skip row (ushort[res_y], cleared by render_line over the clip range) and still
+		 * writes ((uint*)skip)[x*res_y] = 0: one private buffer per thread that holds both */
+		uint* skipbuf = (uint*)calloc((size_t)(ray_end > 0 ? ray_end : 1) * res_y + res_y + 4, sizeof(uint));
+#endif
 		#pragma omp for schedule(dynamic, 16)
 		for (int x = ray_begin; x < ray_end; x++)
 		{
 			memset(mask, 0, mask_words * sizeof(unsigned int));
+#ifdef PERPIXELFORWARD
+			memset(skipbuf, 0, (size_t)res_y * sizeof(ushort));
+			ushort* skip = (ushort*)skipbuf;
+#else
 			/* render_line writes ((uint*)skip)[x*res_y] = 0 */
 			ushort* skip = (ushort*)(dummy - (long long)x * res_y);
+#endif
 			g_render.render_line(x, mask, pos, rot, res_x, res_y, skip);
 		}
+#ifdef PERPIXELFORWARD
+		free(skipbuf);
+#endif
 		free(mask);
 	}
 #ifdef DETAIL_BENCH

@@ -96,8 +96,10 @@ def ref_host():
 
 
 def ref_render(bench=False, flags=0):
-    """flags: 1 = built with -DCLIPREGION, 2 = -DHEIGHT_COLOR (R/src/core.h:18,22), 3 = both."""
-    name = {0: "libref_render.so", 1: "libref_render_clip.so", 2: "libref_render_hc.so", 3: "libref_render_cliphc.so"}[flags]
+    """flags: 1 = built with -DCLIPREGION, 2 = -DHEIGHT_COLOR (R/src/core.h:18,22), 3 = both;
+    "centerseg" / "normalclip" = built with the alternative culling mode -DCENTERSEG / -DNORMALCLIP (core.h:27-30)."""
+    name = {0: "libref_render.so", 1: "libref_render_clip.so", 2: "libref_render_hc.so", 3: "libref_render_cliphc.so",
+            "centerseg": "libref_render_centerseg.so", "normalclip": "libref_render_normalclip.so"}[flags]
     lib = _load("libref_render_bench.so" if bench else name)
     if not getattr(lib, "_typed", False):
         lib.ref_render_frame.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,

@@ -54,6 +54,28 @@ def test_render_line_port_equals_reference_on_degenerate_scenes(R, rb, need_ref)
                 assert cnt["pixels"] == 0 and cnt["run_iters"] == 0
 
 
+@pytest.mark.parametrize("mode", ["centerseg", "normalclip"])
+def test_reference_culling_modes_render_the_same_picture(R, rb, need_ref, scene_mid, scene_runs, mode):
+    """the reference built with -DCENTERSEG / -DNORMALCLIP (alternative culling, R/src/core.h:
+    27-30) writes the SAME warped ray buffer as the shipped configuration, also on the adversarial scenes: these
+    modes are ablations of the culling work, not of the picture, so the B200 path is a drop-in for those builds too.
+    (-DPERPIXELFORWARD is not: with SHAREMEMCLIP on its pixel loop never terminates, Cuda_Render.h:682-731, and with
+    the mask off it draws different pictures)"""
+    cfg = R.FrameConfig.default(400, 300)
+    scenes = [(scene_mid, list(camera_grid(-100.0))[::4] + few_cameras(-100.0)), (scene_runs, few_cameras(-90.0))]
+    scenes += [(s, edge_cameras()) for k, s in edge_scenes(R).items() if k in ("noise50", "layers", "walls", "comb")]
+    n = 0
+    for scene, cams in scenes:
+        for pos, rot in cams:
+            rm = R.RayMap(cfg).get_ray_map(pos, rot)
+            orm = oracle_raymap(rb, rm, scene)
+            a, _ = rb.ref_render_frame(orm, cfg.render_size, mip_distance=cfg.mip_distance, z_far=cfg.z_far, rays=cfg.rays_casted)
+            b, _ = rb.ref_render_frame(orm, cfg.render_size, mip_distance=cfg.mip_distance, z_far=cfg.z_far, rays=cfg.rays_casted, flags=mode)
+            assert np.array_equal(a, b), (mode, pos, rot)
+            n += 1
+    assert n >= 40
+
+
 def test_render_line_port_non_default_config(R, rb, need_ref, scene_small):
     """z_far, mip_distance and a non power-of-two render size are run-time here."""
     cfg = R.FrameConfig.default(600, 400)
