@@ -139,10 +139,14 @@ int  rlerc_scene_device_maps(rlerc_ctx* c, rlerc_map4* out16, int* nummaps);
 /* Traversal kernel variant, all bit-identical: 0 = automatic (default): the production kernel k_traverse_f (one warp
  * per ray plane, column filter in front of the occlusion machinery), or k_traverse_p (a filter warp and a consume warp
  * per ray plane) when the launch has at most 12 ray planes per SM and is therefore bound by its longest ray planes
- * (multi-GPU slices, small windows); 65 = k_traverse_f always; 68 = k_traverse_p always; 64 = k_traverse_w (one warp
- * per ray plane, three-stage pipeline over all columns); 66, 67 = k_traverse_c (DDA in a dedicated warp);
- * 1,2,4,8,16,32 = k_traverse<lanes> (lane <-> run; 1 is the reference's thread-per-ray scheme). */
+ * (multi-GPU slices, small windows); 65 = k_traverse_f always; 68 = k_traverse_p always (both run the DDA pre-pass
+ * k_dda_states first); 1,2,4,8,16,32 = k_traverse<lanes> (lane <-> run; 1 is the reference's thread-per-ray scheme).
+ * Only in a library built with `make VARIANTS=1` (rlerc_has_variants() == 1; measured and rejected in round 1):
+ * 64 = k_traverse_w (three-stage pipeline over all columns); 66, 67 = k_traverse_c (DDA in a dedicated warp). */
 int  rlerc_set_lanes_per_ray(rlerc_ctx* c, int lanes);
+int  rlerc_has_variants(void);
+/* Name of the traversal kernel the last rlerc_render* call launched (static string). */
+const char* rlerc_last_kernel(rlerc_ctx* c);
 /* k_traverse_w only: run the DDA in dedicated producer blocks or inside every warp (default). */
 int  rlerc_set_dda_producer(rlerc_ctx* c, int on);
 /* k_traverse_w only: 0 = serial DDA recurrence in every warp (default), 2 = merge-path DDA, 3 = closed-form

@@ -94,6 +94,8 @@ _SIGS = {
     "rlerc_scene_upload": (C.c_int, [_P, _P]),
     "rlerc_scene_device_maps": (C.c_int, [_P, _P, C.POINTER(C.c_int)]),
     "rlerc_set_lanes_per_ray": (C.c_int, [_P, C.c_int]),
+    "rlerc_has_variants": (C.c_int, []),
+    "rlerc_last_kernel": (C.c_char_p, [_P]),
     "rlerc_set_dda_producer": (C.c_int, [_P, C.c_int]),
     "rlerc_set_dda_mode": (C.c_int, [_P, C.c_int]),
     "rlerc_frame_setup": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_float), _P, _P]),
@@ -316,6 +318,10 @@ class Renderer:
 
     def set_lanes_per_ray(self, lanes):
         _check(lib().rlerc_set_lanes_per_ray(self._c, lanes))
+
+    @property
+    def last_kernel(self):
+        return lib().rlerc_last_kernel(self._c).decode()
 
     def set_dda_mode(self, mode):
         _check(lib().rlerc_set_dda_mode(self._c, mode))

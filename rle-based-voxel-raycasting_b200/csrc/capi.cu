@@ -29,7 +29,8 @@ namespace {
 struct FrameSlot {            // one in-flight frame of the pipelined path
 	uint32_t* d_warp = nullptr;
 	uint8_t* d_rgba = nullptr;
-	size_t warp_bytes = 0, rgba_bytes = 0;
+	float2* d_states = nullptr;      // DDA states of the frame's ray planes (k_dda_states -> k_traverse_f / _p)
+	size_t warp_bytes = 0, rgba_bytes = 0, states_bytes = 0;
 	cudaEvent_t done = nullptr;
 	cudaStream_t stream = nullptr;   // each in-flight frame renders on its own stream: the tail of one
 	                                 // frame's traversal (a few long ray planes) overlaps the next frame
@@ -54,6 +55,12 @@ struct rlerc_ctx {
 	size_t warp_bytes = 0;
 	uint8_t* d_rgba = nullptr;
 	size_t rgba_bytes = 0;
+	float2* d_states = nullptr;         // DDA states of the ray planes of the frame on c->stream
+	size_t states_bytes = 0;
+	float2** cur_states = nullptr;      // the states buffer render_impl uses (rlerc_frame_submit points it at the slot's)
+	size_t* cur_states_bytes = nullptr;
+	unsigned int dda_epoch = 0;         // epoch of the last traversal launch (k_dda_states -> traversal hand-over)
+	const char* last_kernel = "";       // traversal kernel of the last launch
 	uint32_t* d_ids_scratch = nullptr;
 	unsigned long long* d_counters = nullptr;
 	int lanes = 0;                      // 0 = auto (pick_lanes)
@@ -89,14 +96,45 @@ void free_scene(rlerc_ctx* c)
 	c->nummaps = 0;
 }
 
-int ensure(void** p, size_t* have, size_t need)
+// (Re)allocate a device buffer.  A new buffer is zero-filled ON THE STREAM THAT WILL USE IT: the streams here are
+// cudaStreamNonBlocking, which a memset on the legacy default stream does not order with.  zero = false: the buffer is
+// fully written before it is read (DDA states).
+int ensure(void** p, size_t* have, size_t need, cudaStream_t st, bool zero = true)
 {
 	if (*have >= need && *p) return RLERC_OK;
-	if (*p) cudaFree(*p);
+	if (*p) cudaFree(*p);                                        // synchronises the device: nothing still uses the old buffer
 	*p = nullptr; *have = 0;
 	CK(cudaMalloc(p, need));
-	CK(cudaMemset(*p, 0, need));
+	if (zero) CK(cudaMemsetAsync(*p, 0, need, st));
 	*have = need;
+	return RLERC_OK;
+}
+
+// The frame's LOD / z schedule (kernels.cuh LodSched): the integer half of the traversal loop, Cuda_Render.h:343-367,
+// followed exactly as the kernels' ddaq_run32 steps it.
+int fill_lod_sched(TraverseParams& P)
+{
+	LodSched& L = P.lod;
+	memset(&L, 0, sizeof(L));
+	int nsw = 0;
+	for (float yms = P.viewpos[1]; yms > 512.0f; yms = yms * 0.5f)      // Cuda_Render.h:343: y_map_switch halves until <= 512
+		if (++nsw > 24) { set_error("camera height %g is out of range", (double)P.viewpos[1]); return RLERC_ERR_ARG; }
+	long long zi = 0, k = 0;
+	int np = 0;
+	while (true)
+	{
+		long long ms = (long long)P.mapswitch0 << nsw;
+		while (zi > ms) { nsw++; ms *= 2; }
+		if (nsw > 29 || ms > 0x7fffffffll) { set_error("z_far %d needs more LOD doublings than 32-bit z allows (mip_distance %d)", P.z_far, P.mapswitch0); return RLERC_ERR_ARG; }
+		const long long lod_free = ((ms - zi) >> nsw) + 1;          // crossings before z > mapswitch
+		const long long far_free = ((long long)P.z_far - zi) >> nsw; // crossings with z + dz <= z_far
+		if (far_free <= 0) break;
+		const long long n = lod_free < far_free ? lod_free : far_free;
+		if (np == 32) { set_error("LOD schedule has more than 32 phases"); return RLERC_ERR_ARG; }
+		L.ph_k[np] = (int)k; L.ph_z[np] = (int)zi; L.ph_nsw[np] = nsw; np++;
+		k += n; zi += n << nsw;
+	}
+	L.nphase = np; L.k_total = (int)k; L.ph_k[np] = (int)k;
 	return RLERC_OK;
 }
 
@@ -142,6 +180,13 @@ int fill_traverse(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_config
 		int mapswitch = cfg->mip_distance;
 		mapswitch = mapswitch * (0.25 * (4 - std::abs(rx)));
 		P.mapswitch0 = mapswitch;
+		// mapswitch doubles until it passes z: from 0 (or below) it never would, the reference loops forever there
+		if (mapswitch < 1) { set_error("mip_distance %d at pitch %g gives mapswitch %d < 1", cfg->mip_distance, (double)rx, mapswitch); return RLERC_ERR_ARG; }
+	}
+	if (!std::isfinite(rm->position.x) || !std::isfinite(rm->position.y) || !std::isfinite(rm->position.z))
+	{
+		set_error("camera position is not finite");
+		return RLERC_ERR_ARG;
 	}
 	P.z_far = cfg->z_far;
 	if (ray_end < 0 || ray_end > count) ray_end = count;
@@ -151,7 +196,7 @@ int fill_traverse(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_config
 	P.flags = cfg->flags;
 	P.warp = d_warp;
 	P.slice_block = 1; P.slice_n = 1; P.slice_rank = 0;
-	return RLERC_OK;
+	return fill_lod_sched(P);
 }
 
 // Uniforms of the colorize pass exactly as main.cpp:578-603 computes them.
@@ -226,12 +271,14 @@ void rlerc_destroy(rlerc_ctx* c)
 	if (c->d_warp) cudaFree(c->d_warp);
 	if (c->d_rgba) cudaFree(c->d_rgba);
 	if (c->d_counters) cudaFree(c->d_counters);
+	if (c->d_states) cudaFree(c->d_states);
 	if (c->d_ring) cudaFree(c->d_ring);
 	if (c->d_ring_ctl) cudaFree(c->d_ring_ctl);
 	for (int i = 0; i < rlerc_ctx::kSlots; i++)
 	{
 		if (c->slot[i].d_warp) cudaFree(c->slot[i].d_warp);
 		if (c->slot[i].d_rgba) cudaFree(c->slot[i].d_rgba);
+		if (c->slot[i].d_states) cudaFree(c->slot[i].d_states);
 		if (c->slot[i].done) cudaEventDestroy(c->slot[i].done);
 		if (c->slot[i].stream) cudaStreamDestroy(c->slot[i].stream);
 	}
@@ -307,6 +354,8 @@ int rlerc_scene_device_maps(rlerc_ctx* c, rlerc_map4* out16, int* nummaps)
 	return RLERC_OK;
 }
 
+int rlerc_has_variants(void) { return RLERC_VARIANTS ? 1 : 0; }
+
 int rlerc_set_lanes_per_ray(rlerc_ctx* c, int lanes)
 {
 	if (!c || !(lanes == 0 || lanes == 1 || lanes == 2 || lanes == 4 || lanes == 8 || lanes == 16 || lanes == 32 || (lanes >= 64 && lanes <= 68)))
@@ -314,9 +363,16 @@ int rlerc_set_lanes_per_ray(rlerc_ctx* c, int lanes)
 		set_error("lanes per ray must be 0,1,2,4,8,16,32 or a kernel code 64..68");
 		return RLERC_ERR_ARG;
 	}
+	if (!RLERC_VARIANTS && (lanes == 64 || lanes == 66 || lanes == 67))
+	{
+		set_error("kernel variant %d is not in this build (make VARIANTS=1)", lanes);
+		return RLERC_ERR_ARG;
+	}
 	c->lanes = lanes;
 	return RLERC_OK;
 }
+
+const char* rlerc_last_kernel(rlerc_ctx* c) { return c ? c->last_kernel : ""; }
 
 int rlerc_set_dda_producer(rlerc_ctx* c, int on)
 {
@@ -345,7 +401,7 @@ int rlerc_warp_buffer(rlerc_ctx* c, const rlerc_frame_config* cfg, uint32_t** d_
 	if (rc) return rc;
 	if (!c || !d_warp) { set_error("rlerc_warp_buffer: null argument"); return RLERC_ERR_ARG; }
 	if ((rc = set_dev(c))) return rc;
-	rc = ensure((void**)&c->d_warp, &c->warp_bytes, (size_t)cfg->rays_casted * cfg->render_size * 4);
+	rc = ensure((void**)&c->d_warp, &c->warp_bytes, (size_t)cfg->rays_casted * cfg->render_size * 4, c->stream);
 	if (rc) return rc;
 	*d_warp = c->d_warp;
 	return RLERC_OK;
@@ -361,7 +417,7 @@ static int render_impl(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_c
 	if ((rc = set_dev(c))) return rc;
 	if (!d_warp)
 	{
-		rc = ensure((void**)&c->d_warp, &c->warp_bytes, (size_t)cfg->rays_casted * cfg->render_size * 4);
+		rc = ensure((void**)&c->d_warp, &c->warp_bytes, (size_t)cfg->rays_casted * cfg->render_size * 4, c->stream);
 		if (rc) return rc;
 		d_warp = c->d_warp;
 	}
@@ -382,18 +438,50 @@ static int render_impl(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_c
 	}
 	P.dda_mode = c->dda_mode;
 	if (prof_out) P.ids = prof_out;
+#if RLERC_VARIANTS
 	if (c->lanes == 64 && c->producer)
 	{
+		// one ring per context: the pipelined path (several frames in flight on separate streams) cannot share it
+		if (c->cur_states) { set_error("the DDA producer variant (lanes 64) cannot be used with rlerc_frame_submit"); return RLERC_ERR_STATE; }
 		const int cap = cfg->rays_casted;
-		if ((rc = ensure((void**)&c->d_ring, &c->ring_bytes, traverse_ring_bytes(cap)))) return rc;
-		if ((rc = ensure((void**)&c->d_ring_ctl, &c->ring_ctl_bytes, (size_t)(2 * cap + 4) * sizeof(int)))) return rc;
+		if ((rc = ensure((void**)&c->d_ring, &c->ring_bytes, traverse_ring_bytes(cap), c->stream))) return rc;
+		if ((rc = ensure((void**)&c->d_ring_ctl, &c->ring_ctl_bytes, (size_t)(2 * cap + 4) * sizeof(int), c->stream))) return rc;
 		CK(cudaMemsetAsync(c->d_ring_ctl, 0, (size_t)(2 * cap + 4) * sizeof(int), c->stream));
 		P.dda_ring = c->d_ring; P.dda_head = c->d_ring_ctl; P.dda_tail = c->d_ring_ctl + cap; P.dda_err = c->d_ring_ctl + 2 * cap;
 	}
-	if (c->timing) CK(cudaEventRecord(c->ev[0], c->stream));
+#endif
 	const int launch_rays = (P.slice_n > 1) ? owned_count(P.ray_end, P.slice_block, P.slice_n, P.slice_rank) : P.ray_end - P.ray_begin;
-	launch_traverse(P, pick_lanes(c, launch_rays, ids), ids, c->stream);
+	const int lanes = pick_lanes(c, launch_rays, ids);
+	const bool production = lanes == 0 || lanes == 65 || lanes == 68;
+	if (production)
+	{
+		// DDA states of this launch's ray planes: sized for the most ray planes a launch of this configuration can have,
+		// so that the buffer is allocated once (a reallocation synchronises the device)
+		// (most ray planes: rays_casted; most crossings: pitch 0, camera below y = 512 -> mapswitch = mip_distance, no
+		// initial LOD switch)
+		TraverseParams Pmax = P;
+		Pmax.ray_begin = 0; Pmax.ray_end = cfg->rays_casted;
+		Pmax.slice_n = 1;
+		Pmax.mapswitch0 = cfg->mip_distance; Pmax.viewpos[1] = 0.0f;
+		if (fill_lod_sched(Pmax) != RLERC_OK || Pmax.lod.k_total < P.lod.k_total) Pmax.lod = P.lod;
+		float2** sp = c->cur_states ? c->cur_states : &c->d_states;
+		size_t* sb = c->cur_states_bytes ? c->cur_states_bytes : &c->states_bytes;
+		const size_t state_bytes = (traverse_dda_state_bytes(Pmax) + 255) & ~(size_t)255;
+		const bool fresh = *sb < state_bytes + traverse_dda_progress_bytes(Pmax) || !*sp;
+		if ((rc = ensure((void**)sp, sb, state_bytes + traverse_dda_progress_bytes(Pmax), c->stream, false))) return rc;
+		P.dda_states = *sp;
+		P.dda_progress = (unsigned long long*)((char*)*sp + state_bytes);
+		// a new buffer's progress words are garbage that could carry any epoch
+		if (fresh) CK(cudaMemsetAsync(P.dda_progress, 0, traverse_dda_progress_bytes(Pmax), c->stream));
+		P.dda_epoch = ++c->dda_epoch;
+		if (P.dda_epoch == 0) P.dda_epoch = ++c->dda_epoch;
+	}
+	if (c->timing) CK(cudaEventRecord(c->ev[0], c->stream));
+	if (production) launch_dda_states(P, c->stream);
+	launch_traverse(P, lanes, ids, c->stream);
 	if (c->timing) { CK(cudaEventRecord(c->ev[1], c->stream)); c->ev_valid[0] = true; }
+	c->last_kernel = (lanes == 0 || lanes == 65) ? (ids ? "k_traverse_f<ids>" : "k_traverse_f") : lanes == 68 ? (ids ? "k_traverse_f<ids>" : "k_traverse_p")
+	               : lanes == 64 ? "k_traverse_w" : lanes == 66 ? "k_traverse_c<3>" : lanes == 67 ? "k_traverse_c<7>" : "k_traverse<G>";
 	CK(cudaGetLastError());
 	return RLERC_OK;
 }
@@ -426,9 +514,26 @@ int rlerc_debug_profile_rays(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_f
 	if (!c || !d_out) return RLERC_ERR_ARG;
 	const int saved_mode = c->dda_mode, saved_lanes = c->lanes;
 	c->dda_mode = 99; c->lanes = 0;
-	const int rc = render_impl(c, rm, cfg, 0, -1, nullptr, nullptr, false, 1, 1, 0, (uint32_t*)d_out);
+	// RLERC_PROF_SLICE=k: only every k-th ray plane (the uncontended chain: every warp has an SM sub-partition to itself)
+	const char* sl = getenv("RLERC_PROF_SLICE");
+	const int k = sl ? atoi(sl) : 1;
+	const int rc = render_impl(c, rm, cfg, 0, -1, nullptr, nullptr, false, 1, k > 1 ? k : 1, 0, (uint32_t*)d_out);
 	c->dda_mode = saved_mode; c->lanes = saved_lanes;
 	return rc;
+}
+
+/* undocumented (tests/test_lod_sched.py): the LOD / z schedule fill_traverse computes for a frame.
+ * out = { nphase, k_total, ph_k[33], ph_z[32], ph_nsw[32] } = 99 ints */
+int rlerc_debug_lod_sched(int mapswitch0, int z_far, float mountain, int* out)
+{
+	if (!out) return RLERC_ERR_ARG;
+	TraverseParams P;
+	memset(&P, 0, sizeof(P));
+	P.mapswitch0 = mapswitch0; P.z_far = z_far; P.viewpos[1] = mountain;
+	int rc = fill_lod_sched(P);
+	if (rc) return rc;
+	memcpy(out, &P.lod, sizeof(P.lod));
+	return RLERC_OK;
 }
 
 /* undocumented: raw copy of all 32 debug counter slots (tools/ only) */
@@ -457,7 +562,7 @@ static int unwarp_impl(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_c
 	}
 	if (!d_rgba)
 	{
-		rc = ensure((void**)&c->d_rgba, &c->rgba_bytes, (size_t)cfg->width * cfg->height * 4);
+		rc = ensure((void**)&c->d_rgba, &c->rgba_bytes, (size_t)cfg->width * cfg->height * 4, c->stream);
 		if (rc) return rc;
 		d_rgba = c->d_rgba;
 	}
@@ -567,8 +672,6 @@ int rlerc_frame_submit(rlerc_ctx* c, const float pos[3], const float rot[3], con
 	const int ticket = c->next_ticket;
 	FrameSlot& s = c->slot[ticket % rlerc_ctx::kSlots];
 	if (s.busy) { CK(cudaEventSynchronize(s.done)); s.busy = false; }
-	if ((rc = ensure((void**)&s.d_warp, &s.warp_bytes, (size_t)cfg->rays_casted * cfg->render_size * 4))) return rc;
-	if ((rc = ensure((void**)&s.d_rgba, &s.rgba_bytes, (size_t)cfg->width * cfg->height * 4))) return rc;
 	rlerc_raymap rm;
 	memset(&rm, 0, sizeof(rm));
 	if ((rc = rlerc_frame_setup(pos, rot, cfg, &rm))) return rc;
@@ -580,9 +683,13 @@ int rlerc_frame_submit(rlerc_ctx* c, const float pos[3], const float rot[3], con
 		c->stream = s.stream;
 	}
 	cudaStream_t const fs = c->stream;
-	rc = render_impl(c, &rm, cfg, 0, -1, s.d_warp, nullptr, false);
+	c->cur_states = &s.d_states; c->cur_states_bytes = &s.states_bytes;
+	rc = ensure((void**)&s.d_warp, &s.warp_bytes, (size_t)cfg->rays_casted * cfg->render_size * 4, fs);
+	if (!rc) rc = ensure((void**)&s.d_rgba, &s.rgba_bytes, (size_t)cfg->width * cfg->height * 4, fs);
+	if (!rc) rc = render_impl(c, &rm, cfg, 0, -1, s.d_warp, nullptr, false);
 	if (!rc) rc = unwarp_impl(c, &rm, cfg, s.d_warp, s.d_rgba, 0, -1, 0, -1);
 	c->stream = main_stream;
+	c->cur_states = nullptr; c->cur_states_bytes = nullptr;
 	if (rc) return rc;
 	// hand the finished frame to the copy stream so the next frame's traversal overlaps the D2H
 	CK(cudaEventRecord(s.done, fs));

@@ -11,7 +11,18 @@ struct LevelDev {
 	int sx, sz;
 };
 
-// Everything the traversal kernel needs for one frame (~700 B), passed as a
+// The LOD / z schedule of a frame (Cuda_Render.h:343-367): z counts crossings in steps of dz, dz doubles whenever
+// z passes mapswitch (which doubles too), the ray plane ends at z_far.  All integer and the same for every ray plane
+// of a frame, so the host tabulates its phases (constant dz) once: crossing k of any ray plane has a known z, dz, mip.
+struct LodSched {
+	int nphase;              // phases until z_far (<= 32)
+	int k_total;             // crossings until z_far
+	int ph_k[33];            // first crossing of phase p; ph_k[nphase] = k_total
+	int ph_z[32];            // z before that crossing
+	int ph_nsw[32];          // LOD switches made before it: dz = 1 << nsw, mapswitch = mapswitch0 << nsw, mip = min(nsw, nummaps-1)
+};
+
+// Everything the traversal kernel needs for one frame (~1 KB), passed as a
 // __grid_constant__ kernel parameter: replaces the 82,832-byte `Render` block the reference
 // copies host->device every frame (R/src/Cuda_Main.cu:218).
 struct TraverseParams {
@@ -44,6 +55,13 @@ struct TraverseParams {
 	int* dda_tail;           // [rays] batches consumed, -1 = ray plane finished
 	int* dda_err;            // protocol time-out flag
 	int dda_mode;            // 0: serial DDA in every warp, otherwise merge-path DDA (ignored when dda_ring is set)
+	// production kernels (traverse_filter.cu): DDA state of every ray plane of the launch at every 32nd crossing
+	LodSched lod;
+	float2* dda_states;      // [launch rays][ceil(k_total / 32)][3], written by k_dda_states
+	// k_dda_states runs CONCURRENTLY with the traversal kernel (programmatic dependent launch): per ray plane of the launch,
+	// (epoch << 32) | number of batches whose states are published
+	unsigned long long* dda_progress;
+	unsigned int dda_epoch;  // this launch's epoch: anything else in dda_progress is left over from an earlier launch
 };
 
 struct UnwarpParams {
@@ -73,6 +91,9 @@ void launch_traverse(const TraverseParams& p, int lanes_per_ray, bool ids, cudaS
 void launch_traverse_warp(const TraverseParams& p, bool ids, cudaStream_t st);   // traverse_warp.cu
 void launch_traverse_filter(const TraverseParams& p, bool ids, cudaStream_t st); // traverse_filter.cu
 void launch_traverse_pair(const TraverseParams& p, cudaStream_t st);              // traverse_filter.cu (k_traverse_p, variant 68)
+void launch_dda_states(const TraverseParams& p, cudaStream_t st);                 // traverse_filter.cu (k_dda_states, before either of the two)
+size_t traverse_dda_state_bytes(const TraverseParams& p);
+size_t traverse_dda_progress_bytes(const TraverseParams& p);
 void launch_traverse_chunk(const TraverseParams& p, bool ids, int wpb, cudaStream_t st); // traverse_chunk.cu
 size_t traverse_ring_bytes(int rays);
 void launch_unwarp(const UnwarpParams& p, cudaStream_t st);

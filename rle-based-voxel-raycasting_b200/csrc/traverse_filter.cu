@@ -1,23 +1,26 @@
-// k_traverse_f — the production traversal kernel: one WARP per ray plane, a column FILTER in front of the
-// occlusion machinery.  Replaces cudaRender + Render::render_line (R/src/Cuda_Main.cu:150-181,
-// R/src/Cuda_Render.h:96-737) and gives the same warped ray buffer bit for bit (arithmetic contract: DESIGN.md §3).
+// The production traversal: k_dda_states (pre-pass) + k_traverse_f (one WARP per ray plane) / k_traverse_p (two warps
+// per ray plane).  Replaces cudaRender + Render::render_line (R/src/Cuda_Main.cu:150-181, R/src/Cuda_Render.h:96-737)
+// and gives the same warped ray buffer bit for bit (arithmetic contract: DESIGN.md §3).
 //
-// Measured on B200 (tools/chain_probe.py): a frame's traversal time is the serial chain of its longest ray planes
-// (the ones that see sky and walk all ~7000 cell crossings to z_far), not throughput; and on those ray planes
-// > 90 % of the visited columns are no-ops: their first visible run already projects at or below the floating
-// horizon y_clip_min, so the reference breaks out of the run loop without touching any state
-// (Cuda_Render.h:542-543).  That test needs nothing but the 8-byte pointer-map entry (the first run rides in it)
-// and it is monotone: the horizon only rises, so a column that is dead under today's horizon is dead under
-// every later one.  Hence two loops instead of one pipeline over all columns:
+// Measured on B200 in round 1: a frame's traversal time is the serial chain of its longest ray planes (the ones that
+// see sky and walk all ~7000 cell crossings to z_far); > 90 % of the visited columns are no-ops (their first visible
+// run already projects at or below the floating horizon y_clip_min, Cuda_Render.h:542-543, a test that needs nothing
+// but the 8-byte pointer-map entry and is monotone: the horizon only rises); and 48 % of the warp instructions of a
+// frame were the DDA's float recurrence (Cuda_Render.h:398-414), which a warp that owns one ray plane can only
+// execute redundantly in all 32 lanes.  Hence three pieces:
 //
-//   FILTER   per 32 crossings: DDA (uniform serial recurrence) -> per lane column address, projected cell,
-//            conservative top-clip test (Cuda_Render.h:467), pointer-map gather (consumed one step later, the
-//            DDA of the next step hides its latency) -> first-run test -> the LIVE columns are compacted
-//            (ballot + popc) into a small queue in shared memory, in crossing order.
+//   DDA      k_dda_states: one THREAD per ray plane runs the recurrence once, to z_far, and keeps the six floats of
+//            its state at every 32nd crossing (24 bytes per 32 crossings; the LOD / z schedule is integer and the
+//            same for every ray plane of a frame: LodSched).  In the traversal kernel lane j of a warp restarts
+//            from saved state j and re-runs crossings 32j .. 32j+31 of the current 512-crossing chunk into shared
+//            memory: the same float operations in the same order, 16 lanes wide instead of one.
+//   FILTER   per 32 crossings (lane <-> crossing): column address, projected cell, conservative top-clip test
+//            (Cuda_Render.h:467), pointer-map gather (two batches in flight) -> first-run test -> the LIVE columns
+//            are compacted (ballot + popc) into a small queue in shared memory, in crossing order.
 //   CONSUME  per 32 LIVE columns: run-word loads (issued one round early), projection of up to RW runs,
-//            then consume_batch (traverse_common.cuh): rising-horizon prefix-max fast path, owner-lane event
-//            loop, cooperative long spans, deferred parallel shading — unchanged exact semantics, it re-tests
-//            every column under the exact state.
+//            then consume_batch (traverse_common.cuh): rising-horizon prefix-max fast path, ownership-resolved
+//            prefix-OR path, owner-lane event loop, cooperative long spans, deferred parallel shading — the exact
+//            semantics, every column is re-tested under the exact state.
 //
 // The filter only ever removes columns that are provable no-ops, so the result does not depend on how far it
 // runs ahead.  The instrumented build (IDS) passes every column that survives the top-clip test, because the
@@ -31,12 +34,20 @@
 namespace rlerc {
 
 #define RLERC_QCAP 64                       // queue capacity in columns (ring, power of two): < 32 left + <= 32 new
-#define RLERC_F_REC 136                     // words: 33 crossing records (float4), padded
+#ifndef RLERC_F_CH
+#define RLERC_F_CH 16                       // 32-crossing batches per DDA chunk = lanes that run the recurrence side by side
+#endif
+#define RLERC_F_SLOTS (RLERC_F_CH * 33)     // record slots per chunk: crossing c of the chunk sits in slot c + (c >> 5), so that
+                                            // the DDA lanes (stride 33) and the filter lanes (stride 1) are both conflict-free
+#define RLERC_F_REC (3 * RLERC_F_SLOTS + (RLERC_F_SLOTS + 3) / 4)   // words: distance, pos.x, pos.y (float) + mip level (byte) per slot
 #define RLERC_F_QUEUE (8 * RLERC_QCAP)      // words: 8 fields x QCAP, field-major
 
-// The DDA state as two register quads, one per track, laid out like the crossing record a lane consumes:
-// {distance, pos.x, pos.y, mip}.  The z-track keeps its distance NEGATED (the record marks the track that fired
-// by the sign of its distance, and -(a + b) == (-a) + (-b) exactly), so a crossing is: compare, store the quad of
+static_assert(RLERC_F_CH >= 1 && RLERC_F_CH <= 32, "one lane per batch of a chunk");
+static_assert((RLERC_F_REC & 3) == 0, "the areas behind the records are 16-byte aligned");
+
+// The DDA state as two register triples, one per track, laid out like the crossing record a lane consumes:
+// {distance, pos.x, pos.y}.  The z-track keeps its distance NEGATED (the record marks the track that fired
+// by the sign of its distance, and -(a + b) == (-a) + (-b) exactly), so a crossing is: compare, keep the triple of
 // the track that fires, three adds.
 struct DdaQ {
 	float d0, x0, y0;        // x-track: dds_dist0, isect0           (Cuda_Render.h:286-300)
@@ -55,180 +66,359 @@ __device__ __forceinline__ void ddaq_lod_switch(DdaQ& Q, int last_map)          
 	Q.dzi *= 2;
 }
 
-// EXPERIMENTAL DDA crossings as hand-scheduled PTX (build knob RLERC_DDA_ASM, default 0 = the C++ recurrence in
-// ddaq_batch).  All three are bit-exact on B200 and all three are SLOWER than what nvcc makes of the C++ loop
-// (tools/ab_libs.py, 1080p fly-through, four frames in flight: 0.546 ms per frame for the C++ loop):
-//   1: predicates folded with the writer flag (only the writer lane's float state is ever read); x-track quad
-//      stored by the writer, z-track quad stored over it when that track fires; 3 adds @w1, 3 adds @!w1
-//      (9 instructions + overhead, two STS.128 per crossing)                                             0.572 ms
-//   2: setp w1|w0, one store @w1, one @w0, 3 adds @w1, 3 adds @w0 (10 instructions, one active store)     0.557 ms
-//   3: no shared memory: every lane runs the recurrence, lane j keeps the record of crossing j in registers
-//      (guarded selp per field), the consumer takes record j-1 with one shuffle-up (11 instructions, no STS/LDS,
-//      no __syncwarp); same instruction total per frame, more instruction-cache misses (ncu no_instruction
-//      stall 0.21 -> 0.48 per issue), IPC 2.73 -> 2.51                                                    0.607 ms
-// The packed add.rn.f32x2 (FADD2, sm_100+) was tried too: ptxas does not predicate it (FADD2 + two SEL), a loss.
-// IEEE adds (add.rn.f32, no FMA, no FTZ), ordered compare: NaN -> x-track, like `<`.
-#ifndef RLERC_DDA_ASM
-#define RLERC_DDA_ASM 0
-#endif
-#ifndef RLERC_DDA_UNROLL
-#define RLERC_DDA_UNROLL 4
-#endif
-__device__ __forceinline__ void ddaq_cross(DdaQ& Q, float mipf, uint32_t out_s, int writer)
+// DDA state of a ray plane before its first crossing (Cuda_Render.h:270-305) and after the y_map_switch half of the
+// LOD loop condition (Cuda_Render.h:343), which can only be true on the first crossing (it halves until <= 512 and
+// never grows) where z = 0 <= mapswitch.
+__device__ __forceinline__ void ddaq_init(const TraverseParams& P, float ray_x, float ray_z, DdaQ& Q, int& fixx, int& fixz)
 {
-#if RLERC_DDA_ASM == 2
-	asm volatile("{\n"
-		" .reg .pred pw, w1, w0;\n"
-		" .reg .f32 pd1;\n"
-		" setp.ne.s32 pw, %13, 0;\n"
-		" neg.f32 pd1, %3;\n"
-		" setp.lt.and.f32 w1|w0, pd1, %0, pw;\n"
-		" @w1 st.shared.v4.f32 [%12], {%3, %4, %5, %14};\n"
-		" @w0 st.shared.v4.f32 [%12], {%0, %1, %2, %14};\n"
-		" @w1 add.rn.f32 %3, %3, %9;\n"
-		" @w0 add.rn.f32 %0, %0, %6;\n"
-		" @w1 add.rn.f32 %4, %4, %10;\n"
-		" @w0 add.rn.f32 %1, %1, %7;\n"
-		" @w1 add.rn.f32 %5, %5, %11;\n"
-		" @w0 add.rn.f32 %2, %2, %8;\n"
-		"}\n"
-		: "+f"(Q.d0), "+f"(Q.x0), "+f"(Q.y0), "+f"(Q.nd1), "+f"(Q.x1), "+f"(Q.y1)
-		: "f"(Q.gd0), "f"(Q.gx0), "f"(Q.gy0), "f"(Q.ngd1), "f"(Q.gx1), "f"(Q.gy1), "r"(out_s), "r"(writer), "f"(mipf)
-		: "memory");
-#else
-	asm volatile("{\n"
-		" .reg .pred pw, w1;\n"
-		" .reg .f32 pd1;\n"
-		" setp.ne.s32 pw, %13, 0;\n"
-		" neg.f32 pd1, %3;\n"
-		" setp.lt.and.f32 w1, pd1, %0, pw;\n"
-		" @pw st.shared.v4.f32 [%12], {%0, %1, %2, %14};\n"
-		" @w1 st.shared.v4.f32 [%12], {%3, %4, %5, %14};\n"
-		" @w1 add.rn.f32 %3, %3, %9;\n"
-		" @!w1 add.rn.f32 %0, %0, %6;\n"
-		" @w1 add.rn.f32 %4, %4, %10;\n"
-		" @!w1 add.rn.f32 %1, %1, %7;\n"
-		" @w1 add.rn.f32 %5, %5, %11;\n"
-		" @!w1 add.rn.f32 %2, %2, %8;\n"
-		"}\n"
-		: "+f"(Q.d0), "+f"(Q.x0), "+f"(Q.y0), "+f"(Q.nd1), "+f"(Q.x1), "+f"(Q.y1)
-		: "f"(Q.gd0), "f"(Q.gx0), "f"(Q.gy0), "f"(Q.ngd1), "f"(Q.gx1), "f"(Q.gy1), "r"(out_s), "r"(writer), "f"(mipf)
-		: "memory");
-#endif
+	Dda dd;
+	dda_init(P, ray_x, ray_z, dd);
+	fixx = dd.fixx; fixz = dd.fixz;
+	Q.d0 = dd.d0; Q.x0 = dd.i0x; Q.y0 = dd.i0y; Q.nd1 = -dd.d1; Q.x1 = dd.i1x; Q.y1 = dd.i1y;
+	Q.gd0 = dd.gd0; Q.gx0 = dd.g0x; Q.gy0 = dd.g0y; Q.ngd1 = -dd.gd1; Q.gx1 = dd.g1x; Q.gy1 = dd.g1y;
+	Q.mip = 0; Q.zi = 0; Q.dzi = 1;                              // z and dz (Cuda_Render.h:181,325)
+	Q.mapswitch = P.mapswitch0;
 }
 
-// RLERC_DDA_ASM 3: no shared memory at all.  Every lane runs the recurrence (the state stays warp-uniform) and lane j
-// keeps the record of crossing j in its own registers: a guarded select per field, nothing to store, nothing to
-// synchronise; the consumer of crossing j needs the records j-1 and j, i.e. its own and one shuffle-up.
-//   setp t1 | setp pj = (lane == crossing) | 3 x @pj selp | 3 adds @t1 | 3 adds @!t1    -> 11 instructions, 0 stores
-struct DdaCap {
-	float cx, cy, cz; int cmip;      // record of crossing `lane` of the current batch {+-distance, pos.x, pos.y}, its mip level
-	float kx, ky, kz;                // record before crossing 0: the last crossing of the previous batch (warp-uniform)
+// One crossing (Cuda_Render.h:398-414).  REC: write its record {+-distance, pos.x, pos.y, mip}.
+template <bool REC>
+__device__ __forceinline__ void ddaq_cross(DdaQ& Q, float* rd, float* rx, float* ry, uint8_t* rm, int i)
+{
+	const bool t1 = -Q.nd1 < Q.d0;
+	if (REC)
+	{
+		rd[i] = t1 ? Q.nd1 : Q.d0; rx[i] = t1 ? Q.x1 : Q.x0; ry[i] = t1 ? Q.y1 : Q.y0;
+		rm[i] = (uint8_t)Q.mip;
+	}
+	if (t1) { Q.nd1 += Q.ngd1; Q.x1 += Q.gx1; Q.y1 += Q.gy1; }
+	else    { Q.d0 += Q.gd0; Q.x0 += Q.gx0; Q.y0 += Q.gy0; }
+}
+
+// Up to 32 crossings of ONE lane's DDA.  LOD / z_far budgets by shifts (dz is a power of two); stops early only
+// when z_far is reached (Cuda_Render.h:366-367).
+template <bool REC>
+__device__ __forceinline__ void ddaq_run32(DdaQ& Q, int last_map, int zfar_i, float* rd, float* rx, float* ry, uint8_t* rm)
+{
+	for (int s = 0; s < 32;)
+	{
+		while (Q.zi > Q.mapswitch) ddaq_lod_switch(Q, last_map);
+		const int sh = 31 - __clz(Q.dzi);
+		const int lod_free = ((Q.mapswitch - Q.zi) >> sh) + 1;        // crossings before z > mapswitch
+		const int far_free = (zfar_i - Q.zi) >> sh;                   // crossings with z + dz <= z_far (<= 0: none)
+		if (far_free <= 0) break;
+		int n = 32 - s;
+		n = n < lod_free ? n : lod_free;
+		n = n < far_free ? n : far_free;
+		#pragma unroll 4
+		for (int j = 0; j < n; j++) ddaq_cross<REC>(Q, rd, rx, ry, rm, s + j);
+		Q.zi += n << sh;
+		s += n;
+	}
+}
+
+// ---- pre-pass: the DDA of every ray plane of the launch, one thread each, state kept at every 32nd crossing -------
+// states[(ray_i * nb + b) * 3 + 0..2] = {d0, x0}, {y0, -d1}, {x1, y1} before crossing 32 b (ray_i: launch-local index)
+//
+// The traversal kernel is launched behind it with programmatic stream serialization and starts as soon as every block
+// of this kernel is resident (griddepcontrol.launch_dependents at the top): a ray plane's chain of ~7000 dependent
+// crossings takes ~0.1 ms here, which would otherwise sit in front of every frame.  Hand-over per ray plane:
+// dda_progress = (epoch << 32) | batches published, written with release semantics after the states, at batch counts
+// CH, 3 CH, 7 CH, ... (a fence per publication costs this thread ~1 us, so they thin out) and at the end.
+__device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v)
+{
+	asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p)
+{
+	unsigned long long v;
+	asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+	return v;
+}
+
+__global__ void __launch_bounds__(64)
+k_dda_states(const __grid_constant__ TraverseParams P, int rays)
+{
+	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+	const int ray_i = (int)blockIdx.x * 64 + (int)threadIdx.x;
+	if (ray_i >= rays) return;
+	const int x = owned_ray(P, ray_i);
+	if (x >= P.ray_end) return;
+	RayInit ri;
+	ray_init(P, x, ri);
+	if (ri.skip) return;
+	DdaQ Q;
+	int fixx, fixz;
+	ddaq_init(P, ri.ray_x, ri.ray_z, Q, fixx, fixz);
+	const int last_map = P.nummaps - 1;
+	for (float yms = P.viewpos[1]; yms > 512.0f; yms = yms * 0.5f) ddaq_lod_switch(Q, last_map);
+	const int nb = (P.lod.k_total + 31) >> 5;
+	float2* out = P.dda_states + (size_t)ray_i * nb * 3;
+	unsigned long long* const flag = P.dda_progress + ray_i;
+	const unsigned long long epoch = (unsigned long long)P.dda_epoch << 32;
+	int publish_at = RLERC_F_CH;
+	for (int b = 0; b < nb; b++, out += 3)
+	{
+		out[0] = make_float2(Q.d0, Q.x0); out[1] = make_float2(Q.y0, Q.nd1); out[2] = make_float2(Q.x1, Q.y1);
+		if (b + 1 == publish_at || b + 1 == nb)
+		{
+			st_release_u64(flag, epoch | (unsigned)(b + 1));
+			publish_at = 2 * publish_at + RLERC_F_CH;
+		}
+		ddaq_run32<false>(Q, last_map, P.z_far, nullptr, nullptr, nullptr, nullptr);
+	}
+}
+
+// ---- the crossing records of one chunk, in shared memory -----------------------------------------------------------
+struct RecView {
+	float* d; float* x; float* y; uint8_t* m;        // [RLERC_F_SLOTS] each
 };
-template <int K>
-__device__ __forceinline__ void ddaq_cross_cap(DdaQ& Q, DdaCap& C, int rel)          // lane keeps the record iff rel == K
+__device__ __forceinline__ RecView rec_view(uint32_t* base)
 {
-	asm volatile("{\n"
-		" .reg .pred t1, pj;\n"
-		" .reg .f32 pd1;\n"
-		" neg.f32 pd1, %3;\n"
-		" setp.lt.f32 t1, pd1, %0;\n"
-		" setp.eq.s32 pj, %15, %16;\n"
-		" @pj selp.f32 %6, %3, %0, t1;\n"
-		" @pj selp.f32 %7, %4, %1, t1;\n"
-		" @pj selp.f32 %8, %5, %2, t1;\n"
-		" @t1 add.rn.f32 %3, %3, %12;\n"
-		" @!t1 add.rn.f32 %0, %0, %9;\n"
-		" @t1 add.rn.f32 %4, %4, %13;\n"
-		" @!t1 add.rn.f32 %1, %1, %10;\n"
-		" @t1 add.rn.f32 %5, %5, %14;\n"
-		" @!t1 add.rn.f32 %2, %2, %11;\n"
-		"}\n"
-		: "+f"(Q.d0), "+f"(Q.x0), "+f"(Q.y0), "+f"(Q.nd1), "+f"(Q.x1), "+f"(Q.y1), "+f"(C.cx), "+f"(C.cy), "+f"(C.cz)
-		: "f"(Q.gd0), "f"(Q.gx0), "f"(Q.gy0), "f"(Q.ngd1), "f"(Q.gx1), "f"(Q.gy1), "r"(rel), "n"(K));
+	RecView v;
+	v.d = reinterpret_cast<float*>(base); v.x = v.d + RLERC_F_SLOTS; v.y = v.x + RLERC_F_SLOTS;
+	v.m = reinterpret_cast<uint8_t*>(v.y + RLERC_F_SLOTS);
+	return v;
 }
 
-// Same contract as ddaq_batch below, records captured in registers (C) instead of shared memory.
-__device__ __forceinline__ int ddaq_batch_cap(DdaQ& Q, DdaCap& C, int prev_n, int last_map, int zfar_i, int gl)
+// Chunk `chunk` of the ray plane: lane j < CH restarts the DDA from saved state chunk * CH + j (the LOD / z side of
+// it from the frame's schedule) and writes the records of its 32 crossings.  `carry` = record of the last crossing
+// before this chunk (what the chunk's first crossing starts from).
+#define RLERC_DDA_SPIN_MAX (1 << 22)          // x 100 ns: the pre-pass never came; fail loudly (launch error), never a wrong picture
+__device__ __noinline__ void dda_states_missing() { __trap(); }
+
+__device__ __forceinline__ void dda_chunk(const TraverseParams& P, const float2* st, const unsigned long long* flag, int& published,
+                                          float ray_x, float ray_z, int chunk, int gl, const RecView& rec, float3& carry)
 {
-	int nvalid = 32;
-	if (prev_n > 0)
+	if (chunk > 0)
 	{
-		C.kx = __shfl_sync(0xffffffffu, C.cx, prev_n - 1);
-		C.ky = __shfl_sync(0xffffffffu, C.cy, prev_n - 1);
-		C.kz = __shfl_sync(0xffffffffu, C.cz, prev_n - 1);
+		const int last = RLERC_F_CH * 33 - 2;                        // slot of crossing CH * 32 - 1
+		carry = make_float3(rec.d[last], rec.x[last], rec.y[last]);
 	}
-	for (int s = 0; s < 32;)
+	// the states of this chunk's batches have to be published (k_dda_states runs concurrently, normally far ahead)
 	{
-		while (Q.zi > Q.mapswitch) ddaq_lod_switch(Q, last_map);
-		const int sh = 31 - __clz(Q.dzi);
-		const int lod_free = ((Q.mapswitch - Q.zi) >> sh) + 1;        // crossings before z > mapswitch
-		const int far_free = (zfar_i - Q.zi) >> sh;                   // crossings with z + dz <= z_far (<= 0: none)
-		if (far_free <= 0) { nvalid = s; break; }
-		int n = 32 - s;
-		n = n < lod_free ? n : lod_free;
-		n = n < far_free ? n : far_free;
-		const int rel = gl - s;                                       // this lane keeps crossing j == rel of the segment
-		if (rel >= 0 && rel < n) C.cmip = Q.mip;
-		int r = rel, j = 0;
-		for (; j + 4 <= n; j += 4, r -= 4)
+		const int nb = (P.lod.k_total + 31) >> 5;
+		int need = (chunk + 1) * RLERC_F_CH;
+		need = need < nb ? need : nb;
+		int spins = 0;
+		while (published < need)                                     // warp-uniform: every lane reads the same word
 		{
-			ddaq_cross_cap<0>(Q, C, r); ddaq_cross_cap<1>(Q, C, r); ddaq_cross_cap<2>(Q, C, r); ddaq_cross_cap<3>(Q, C, r);
+			const unsigned long long v = ld_acquire_u64(flag);
+			if ((unsigned)(v >> 32) == P.dda_epoch) published = (int)(unsigned)v;
+			if (published >= need) break;
+			__nanosleep(100);
+			if (++spins > RLERC_DDA_SPIN_MAX) { dda_states_missing(); break; }
 		}
-		#pragma unroll 1
-		for (; j < n; j++, r--) ddaq_cross_cap<0>(Q, C, r);
-		Q.zi += n << sh;
-		s += n;
 	}
-	return nvalid;
+	__syncwarp();
+	const int b = chunk * RLERC_F_CH + gl;
+	const int k0 = b << 5;
+	if (gl < RLERC_F_CH && k0 < P.lod.k_total)
+	{
+		const float2* s = st + (size_t)b * 3;
+		const float2 a0 = __ldcg(s), a1 = __ldcg(s + 1), a2 = __ldcg(s + 2);   // L2: written by a kernel that is still running
+		DdaQ Q;
+		int fixx, fixz;
+		ddaq_init(P, ray_x, ray_z, Q, fixx, fixz);
+		Q.d0 = a0.x; Q.x0 = a0.y; Q.y0 = a1.x; Q.nd1 = a1.y; Q.x1 = a2.x; Q.y1 = a2.y;
+		int p = 0;
+		while (p + 1 < P.lod.nphase && P.lod.ph_k[p + 1] <= k0) p++;
+		const int nsw = P.lod.ph_nsw[p];
+		// nsw doublings of a float are one multiplication by 2^nsw (both exact, both saturate to inf alike)
+		const float sc = __int_as_float((127 + nsw) << 23);
+		Q.gd0 *= sc; Q.gx0 *= sc; Q.gy0 *= sc; Q.ngd1 *= sc; Q.gx1 *= sc; Q.gy1 *= sc;
+		Q.dzi = 1 << nsw;
+		Q.zi = P.lod.ph_z[p] + ((k0 - P.lod.ph_k[p]) << nsw);
+		Q.mapswitch = P.mapswitch0 << nsw;
+		Q.mip = nsw < P.nummaps - 1 ? nsw : P.nummaps - 1;
+		const int s0 = gl * 33;
+		ddaq_run32<true>(Q, P.nummaps - 1, P.z_far, rec.d + s0, rec.x + s0, rec.y + s0, rec.m + s0);
+	}
+	__syncwarp();
 }
 
-// Up to 32 crossings, all lanes in lockstep (one lane writes: 32 lanes storing the same 16 bytes cost four
-// shared-memory passes per crossing, which made the DDA store-bound); rec[s+1] = record of crossing s; rec[0] = the last record of the
-// previous batch (rec[prev_n], or zeros before the first).  LOD / z_far budgets by shifts (dz is a power of two).
-// Returns the number of crossings made (< 32 only when z_far was reached, Cuda_Render.h:366-367).
-__device__ __forceinline__ int ddaq_batch(DdaQ& Q, float4* rec, int prev_n, int last_map, int zfar_i, bool writer_b)
+// ---- FILTER, geometry half: crossing gl of batch bl of the chunk -> projected cell, top clip, pointer-map gather -------
+struct FilterRay {                                   // per ray plane, constant
+	float ray_x, ray_z, rx2mr, sin_x, cos_x, vpx, vpz, mountain, res_y2, pz_add, py_add;
+	int fixx, fixz;
+	bool vertical;
+};
+
+__device__ __forceinline__ bool filter_geometry(const TraverseParams& P, const FilterRay& F, const RecView& rec, const float3& carry,
+                                                int bl, int gl, int ycmin, Geo& g, unsigned& e0, unsigned& e1)
 {
-	const int writer = writer_b ? 1 : 0;
-	int nvalid = 32;
+	const int slot = bl * 33 + gl;
+	float ad, ax, ay;                                             // state before / after crossing gl
+	if (gl > 0) { ad = rec.d[slot - 1]; ax = rec.x[slot - 1]; ay = rec.y[slot - 1]; }
+	else if (bl > 0) { ad = rec.d[slot - 2]; ax = rec.x[slot - 2]; ay = rec.y[slot - 2]; }
+	else { ad = carry.x; ax = carry.y; ay = carry.z; }
+	const float bd = rec.d[slot];
+	g.cmip = (int)rec.m[slot];
+	const float db = fabsf(ad), dn = fabsf(bd);
+	const int ib = __float_as_int(ad) < 0 ? 1 : 0;                // index_before: sign bit of the record
+	const int fix_x = (1 - ib) * F.fixx, fix_z = ib * F.fixz;     // Cuda_Render.h:418-419
+	const float ddelta = dn - db;
+	const float vsx = F.ray_x * db, vsz = F.ray_z * db;
+	const int voxel_x = f2i(F.vpx + ax) + fix_x;                  // Cuda_Render.h:429-430
+	const int voxel_z = f2i(F.vpz + ay) + fix_z;
+	const int gx = P.level[g.cmip].sx, gz = P.level[g.cmip].sz;
+	// CLIPREGION (Cuda_Render.h:432-437): finite scene, columns outside the grid are skipped
+	const bool outside = (P.flags & 1) && (voxel_x < 0 || voxel_z < 0 || (voxel_x >> g.cmip) > gx - 1 || (voxel_z >> g.cmip) > gz - 1);
+	const int vx = (voxel_x >> g.cmip) & (gx - 1);                // Cuda_Render.h:441-442
+	const int vz = (voxel_z >> g.cmip) & (gz - 1);
+	g.cidx = vx + vz * gx;
+	const float corx = F.ray_x * ddelta, corz = F.ray_z * ddelta;
+	g.pz = F.cos_x * vsz + F.sin_x * F.mountain;                  // Cuda_Render.h:459-464
+	g.py = F.vertical ? (F.cos_x * F.mountain - F.sin_x * vsz) : vsx;
+	g.py *= F.rx2mr;
+	g.czz = F.cos_x * corz;                                       // Cuda_Render.h:483-486
+	g.cyy = F.vertical ? (-F.sin_x * corz) : corx;
+	g.cyy *= F.rx2mr;
+	// The horizon only rises.  For pz > 0 a column culled now stays culled; for pz <= 0 (or NaN)
+	// the test can flip, so keep those.
+	const bool have = !outside && (!(g.pz * F.res_y2 + g.py <= g.pz * (float)ycmin) || !(g.pz > 0));   // Cuda_Render.h:467
+	if (have)
 	{
-		const float4 carry = rec[prev_n];
-		__syncwarp();
-		if (writer) rec[0] = make_float4(carry.x, carry.y, carry.z, 0.0f);
+		const uint2 ent = __ldg(P.level[g.cmip].map + g.cidx);    // Cuda_Render.h:474-478
+		e0 = ent.x; e1 = ent.y;
 	}
-	for (int s = 0; s < 32;)
-	{
-		while (Q.zi > Q.mapswitch) ddaq_lod_switch(Q, last_map);
-		const int sh = 31 - __clz(Q.dzi);
-		const int lod_free = ((Q.mapswitch - Q.zi) >> sh) + 1;        // crossings before z > mapswitch
-		const int far_free = (zfar_i - Q.zi) >> sh;                   // crossings with z + dz <= z_far (<= 0: none)
-		if (far_free <= 0) { nvalid = s; break; }
-		int n = 32 - s;
-		n = n < lod_free ? n : lod_free;
-		n = n < far_free ? n : far_free;
-		const float mipf = __int_as_float(Q.mip);
-		float4* out = rec + s + 1;
-#if RLERC_DDA_ASM
-		const uint32_t out_s = (uint32_t)__cvta_generic_to_shared(out);
-		constexpr int DDA_UNROLL = RLERC_DDA_UNROLL;
-		#pragma unroll DDA_UNROLL
-		for (int j = 0; j < n; j++) ddaq_cross(Q, mipf, out_s + 16u * (uint32_t)j, writer);
-#else
-		constexpr int DDA_UNROLL = RLERC_DDA_UNROLL;
-		#pragma unroll DDA_UNROLL
-		for (int j = 0; j < n; j++)
+	return have;
+}
+
+// ---- FILTER, test half: can the column do anything under horizon ycmin (or any later, higher one)? -------------------
+template <bool IDS>
+__device__ __forceinline__ bool filter_live(const FilterRay& F, const Geo& g, unsigned e1, int ycmin)
+{
+	const int slen = (int)(e1 & 0xffffu);
+	const unsigned first = e1 >> 16;
+	const int solid = (int)(first >> 10), skip = (int)(first & 1023u);
+	if (IDS) return true;                                 // the byte model counts no-op columns too
+	if (slen == 0) return false;                          // empty column: the run loop does not execute
+	if (solid == 0) return true;                          // pure skip run: undecided, let the machinery look
+	const float ft = (float)(skip << g.cmip);             // Cuda_Render.h:529-543 for run 0
+	float zz1 = g.pz, yy1 = g.py;
+	if (F.mountain + ft >= 0) { zz1 += g.czz; yy1 += g.cyy; }
+	const float z1 = zz1 + F.pz_add * ft;
+	if (z1 <= 0) return true;                             // `continue`: a later run may be the first visible one
+	const float y1 = yy1 + F.py_add * ft;
+	return f2i(F.res_y2 + y1 / z1) > ycmin;               // else: break, now and under every later horizon
+}
+
+// entry of the live-column queue / ring: 8 words, field-major with stride `cap`
+__device__ __forceinline__ void column_put(uint32_t* q, int cap, const Geo& g, unsigned e0, unsigned e1)
+{
+	q[0 * cap] = __float_as_uint(g.pz); q[1 * cap] = __float_as_uint(g.py);
+	q[2 * cap] = __float_as_uint(g.czz); q[3 * cap] = __float_as_uint(g.cyy);
+	q[4 * cap] = (uint32_t)g.cmip; q[5 * cap] = (uint32_t)g.cidx;
+	q[6 * cap] = e0; q[7 * cap] = e1;
+}
+
+// ---- C1: take a live column, request its run words (runs 0..7 as aligned 32-bit words; run 0 rides in the map entry) --
+__device__ __forceinline__ void column_take(const TraverseParams& P, const uint32_t* q, int cap, Geo& g, Stage& s)
+{
+	g.pz = __uint_as_float(q[0 * cap]); g.py = __uint_as_float(q[1 * cap]);
+	g.czz = __uint_as_float(q[2 * cap]); g.cyy = __uint_as_float(q[3 * cap]);
+	g.cmip = (int)q[4 * cap]; g.cidx = (int)q[5 * cap];
+	s.e0 = q[6 * cap]; s.e1 = q[7 * cap];
+	const int sl = (int)(s.e1 & 0xffffu);
+	const unsigned i0 = 2u + s.e0;                                 // element i0 of the slab stream is run 0
+	const uint32_t* w32 = reinterpret_cast<const uint32_t*>(P.level[g.cmip].slabs);
+	const uint32_t* p = w32 + ((i0 + (i0 & 1u)) >> 1);
+	const int odd = (int)(i0 & 1u);                                // odd: words hold runs (1,2) (3,4) (5,6) (7,8)
+	s.rw[0] = (sl > 1) ? __ldg(p) : 0u;
+	s.rw[1] = (sl > 2 + odd) ? __ldg(p + 1) : 0u;
+	s.rw[2] = (sl > 4 + odd) ? __ldg(p + 2) : 0u;
+	s.rw[3] = (sl > 6 + odd) ? __ldg(p + 3) : 0u;
+}
+
+__device__ __forceinline__ void stage_clear(Stage& s, Geo& g)
+{
+	s.nvalid = 0; s.have = false; s.e0 = s.e1 = 0;
+	#pragma unroll
+	for (int k = 0; k < 4; k++) s.rw[k] = 0;
+	g.pz = g.py = g.czz = g.cyy = 0; g.cmip = 0; g.cidx = 0;
+}
+
+// ---- C2: project the runs of a lane's column to screen rows (Cuda_Render.h:529-560) under horizon ycmin ---------------
+// proj[r * 32 + gl] = {sy1, sy2}; flags bit r: run r can be seen (z1 > 0); bit 8 + r: its bottom too (z2 > 0)
+__device__ __forceinline__ void column_project(const FilterRay& F, Stage& s0, const Geo& g0, int ycmin, int gl, int2* proj,
+                                               int& slen, int& nr, bool& longcol, unsigned& flags)
+{
+	{	// run words as loaded in C1 -> runs 0..7, two per register
+		const unsigned first = s0.e1 >> 16;
+		const unsigned a = s0.rw[0], b = s0.rw[1], c = s0.rw[2], d = s0.rw[3];
+		if (!((2u + s0.e0) & 1u)) s0.rw[0] = first | (a & 0xffff0000u);
+		else
 		{
-			const bool t1 = -Q.nd1 < Q.d0;                            // Cuda_Render.h:398-414
-			const float4 cur = make_float4(t1 ? Q.nd1 : Q.d0, t1 ? Q.x1 : Q.x0, t1 ? Q.y1 : Q.y0, mipf);
-			if (writer) out[j] = cur;
-			if (t1) { Q.nd1 += Q.ngd1; Q.x1 += Q.gx1; Q.y1 += Q.gy1; }
-			else    { Q.d0 += Q.gd0; Q.x0 += Q.gx0; Q.y0 += Q.gy0; }
+			s0.rw[0] = first | (a << 16);
+			s0.rw[1] = __funnelshift_r(a, b, 16);
+			s0.rw[2] = __funnelshift_r(b, c, 16);
+			s0.rw[3] = __funnelshift_r(c, d, 16);
 		}
-#endif
-		Q.zi += n << sh;
-		s += n;
 	}
-	return nvalid;
+	slen = (int)(s0.e1 & 0xffffu);
+	nr = slen < RLERC_RW ? slen : RLERC_RW;
+	longcol = slen > RLERC_RW;
+	int blen = 0;
+	for (int r = 0; r < nr; r++)
+	{
+		const unsigned rw = run_word(s0.rw, r);
+		const int skip = (int)(rw & 1023u), solid = (int)(rw >> 10);
+		const int top = (blen + skip) << g0.cmip;                // sti_general_sti_skip
+		const int bot = top + (solid << g0.cmip);                // sti_general
+		blen += skip + solid;
+		if (solid == 0) continue;
+		const float ft = (float)top, fb = (float)bot;
+		float zz1 = g0.pz, yy1 = g0.py;
+		if (F.mountain + ft >= 0) { zz1 += g0.czz; yy1 += g0.cyy; }
+		const float z1 = zz1 + F.pz_add * ft;
+		if (z1 <= 0) continue;
+		flags |= 1u << r;
+		const float y1 = yy1 + F.py_add * ft;
+		const int sy2 = f2i(F.res_y2 + y1 / z1);
+		int sy1 = 0;
+		if (sy2 > ycmin)
+		{
+			float zz2 = g0.pz, yy2 = g0.py;
+			if (F.mountain + fb < 0) { zz2 += g0.czz; yy2 += g0.cyy; }
+			const float z2 = zz2 + F.pz_add * fb;
+			if (!(z2 <= 0))
+			{
+				flags |= 1u << (8 + r);
+				const float y2 = yy2 + F.py_add * fb;
+				sy1 = f2i(F.res_y2 + y2 / z2 - 1);
+			}
+		}
+		proj[r * 32 + gl] = make_int2(sy1, sy2);
+		if (sy2 <= ycmin)
+		{
+			// breaks now, hence under every later (higher) horizon: later runs are dead
+			nr = r + 1; longcol = false;
+			break;
+		}
+	}
+}
+
+__device__ __forceinline__ void filter_ray_init(const TraverseParams& P, const RayInit& ri, FilterRay& F)
+{
+	F.ray_x = ri.ray_x; F.ray_z = ri.ray_z; F.rx2mr = ri.rx2mr; F.vertical = ri.vertical;
+	F.sin_x = P.sin_x; F.cos_x = P.cos_x;
+	F.vpx = P.viewpos[0]; F.mountain = P.viewpos[1]; F.vpz = P.viewpos[2];
+	F.res_y2 = (float)(P.res_y / 2);                              // Cuda_Render.h:108 (integer division)
+	F.pz_add = P.sin_x;                                           // pos3d_z_add (Cuda_Render.h:313)
+	F.py_add = (ri.vertical ? P.cos_x : 0.0f) * ri.rx2mr;         // pos3d_y_add (Cuda_Render.h:314-315)
+	Dda dd;
+	dda_init(P, ri.ray_x, ri.ray_z, dd);
+	F.fixx = dd.fixx; F.fixz = dd.fixz;
+}
+
+__device__ __forceinline__ void ray_ctx_init(const TraverseParams& P, const FilterRay& F, uint32_t* row, uint32_t* ymask, uint32_t* ids,
+                                             long long* stat, int gl, RayCtx& R)
+{
+	R.row = row; R.ymask = ymask; R.ids = ids;
+	R.res_y2 = F.res_y2; R.pz_add = F.pz_add; R.py_add = F.py_add; R.mountain = F.mountain; R.gl = gl;
+	R.stat = stat;
+	R.hc_on = (P.flags & 2) ? 1 : 0;
+	R.hc = f2i((4095.0f - F.mountain) + P.viewpos[1]);            // int height_color = 4095-mountain+viewpos.y (Cuda_Render.h:675)
 }
 
 // PROF (tools/ray_profile.py only): per ray plane, clock64() cycles spent in each phase, written as
@@ -244,6 +434,16 @@ __device__ __forceinline__ int ddaq_batch(DdaQ& Q, float4* rec, int prev_n, int 
 #ifndef RLERC_F_MINB
 #define RLERC_F_MINB (16 / RLERC_F_WPB)       // resident blocks per SM the register allocation is capped for (128 registers)
 #endif
+
+// The traversal kernels are launched with programmatic stream serialization behind k_dda_states and never wait for it
+// as a whole; before a thread leaves, it does (normally long over by then): whatever follows in the stream — the next
+// frame's k_dda_states into the same buffers — must not start while the old one still writes.
+#define RLERC_EXIT_AFTER_PREPASS() asm volatile("griddepcontrol.wait;" ::: "memory")
+
+__host__ __device__ inline int f_words_per_warp(int mask_words)
+{
+	return (RLERC_F_REC + RLERC_F_QUEUE + 16 + RLERC_PS_WORDS + mask_words + 3) & ~3;
+}
 
 template <bool IDS, bool PROF>
 __global__ void __launch_bounds__(RLERC_F_WPB * 32, RLERC_F_MINB)
@@ -263,13 +463,12 @@ k_traverse_f(const __grid_constant__ TraverseParams P, int rays)
 
 	const int ray_i = (int)blockIdx.x * WPB + wid;                  // launch-local ray index
 	const int x = owned_ray(P, ray_i);
-	if (ray_i >= rays || x >= P.ray_end) return;
+	if (ray_i >= rays || x >= P.ray_end) { RLERC_EXIT_AFTER_PREPASS(); return; }
 
-	// shared per warp: crossing records | live-column queue | DrawJob | RW x 32 projected runs (int2) |
+	// shared per warp: crossing records of a chunk | live-column queue | DrawJob | RW x 32 projected runs (int2) |
 	//                  RW x 32 deferred short spans | occlusion bits
-	const int per_warp = (RLERC_F_REC + RLERC_F_QUEUE + 16 + RLERC_PS_WORDS + P.mask_words + 3) & ~3;
-	uint32_t* wbase = smem + (size_t)wid * per_warp;
-	float4* rec = reinterpret_cast<float4*>(wbase);
+	uint32_t* wbase = smem + (size_t)wid * f_words_per_warp(P.mask_words);
+	const RecView rec = rec_view(wbase);
 	uint32_t* queue = wbase + RLERC_F_REC;                           // [8][QCAP]
 	DrawJob* job = reinterpret_cast<DrawJob*>(wbase + RLERC_F_REC + RLERC_F_QUEUE);
 	int2* proj = reinterpret_cast<int2*>(wbase + RLERC_F_REC + RLERC_F_QUEUE + 16);
@@ -277,16 +476,14 @@ k_traverse_f(const __grid_constant__ TraverseParams P, int rays)
 	uint32_t* ymask = wbase + RLERC_F_REC + RLERC_F_QUEUE + 16 + RLERC_PS_WORDS;
 
 	const int res_y = P.res_y;
-	const float res_y2 = (float)(res_y / 2);             // Cuda_Render.h:108 (integer division)
 	uint32_t* row = P.warp + (size_t)x * res_y;
 
 	RayInit ri;
 	ray_init(P, x, ri);
 	clear_outside<G>(row, res_y, ri, gl);
-	if (ri.skip) return;
-	const float ray_x = ri.ray_x, ray_z = ri.ray_z, rx2mr = ri.rx2mr;
-	const bool vertical = ri.vertical;
-	const float sin_x = P.sin_x, cos_x = P.cos_x;
+	if (ri.skip) { RLERC_EXIT_AFTER_PREPASS(); return; }
+	FilterRay F;
+	filter_ray_init(P, ri, F);
 	HorizonState Hs;
 	Hs.ycmin = ri.ycmin; Hs.ycmax = ri.ycmax; Hs.hiw = 0;
 	const int ymin0 = Hs.ycmin, ymax0 = Hs.ycmax;
@@ -296,202 +493,84 @@ k_traverse_f(const __grid_constant__ TraverseParams P, int rays)
 	for (int w = gl; w < P.mask_words; w += G) ymask[w] = 0;
 	__syncwarp();
 
-	const float vpx = P.viewpos[0], mountain = P.viewpos[1], vpz = P.viewpos[2];
-	int fixx, fixz;
-	DdaQ Q;
-	{
-		Dda dd;
-		dda_init(P, ray_x, ray_z, dd);
-		fixx = dd.fixx; fixz = dd.fixz;
-		Q.d0 = dd.d0; Q.x0 = dd.i0x; Q.y0 = dd.i0y; Q.nd1 = -dd.d1; Q.x1 = dd.i1x; Q.y1 = dd.i1y;
-		Q.gd0 = dd.gd0; Q.gx0 = dd.g0x; Q.gy0 = dd.g0y; Q.ngd1 = -dd.gd1; Q.gx1 = dd.g1x; Q.gy1 = dd.g1y;
-	}
-	Q.mip = 0;
-	Q.zi = 0; Q.dzi = 1;                                         // z and dz (Cuda_Render.h:181,325), integer valued
-	Q.mapswitch = P.mapswitch0;
-	DdaCap cap;
-	cap.cx = cap.cy = cap.cz = 0.0f; cap.cmip = 0; cap.kx = cap.ky = cap.kz = 0.0f;   // (register-capture DDA)
-	if (gl == 0) rec[0] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);   // no crossing yet: distance 0, x-track (Cuda_Render.h:302-305)
-	int prev_n = 0;
-	__syncwarp();
-	const float pz_add = sin_x;                                  // pos3d_z_add (Cuda_Render.h:313)
-	const float py_add = (vertical ? cos_x : 0.0f) * rx2mr;      // pos3d_y_add (Cuda_Render.h:314-315)
-	const int zfar_i = P.z_far;
-	const int last_map = P.nummaps - 1;
-	// The y_map_switch half of the LOD loop condition (Cuda_Render.h:343) can only be true on
-	// the first crossing (it halves until <= 512 and never grows), where z = 0 < mapswitch.
-	for (float yms = mountain; yms > 512.0f; yms = yms * 0.5f) ddaq_lod_switch(Q, last_map);
-
 	Counters Cn;
 	memset(&Cn, 0, sizeof(Cn));
-
 	RayCtx R;
-	R.row = row; R.ymask = ymask; R.ids = (IDS && !PROF) ? P.ids + (size_t)x * res_y * 2 : nullptr;
-	R.res_y2 = res_y2; R.pz_add = pz_add; R.py_add = py_add; R.mountain = mountain; R.gl = gl;
-	R.stat = PROF ? stat : nullptr;
-	R.hc_on = (P.flags & 2) ? 1 : 0;
-	R.hc = f2i((4095.0f - mountain) + P.viewpos[1]);              // int height_color = 4095-mountain+viewpos.y (Cuda_Render.h:675)
+	ray_ctx_init(P, F, row, ymask, (IDS && !PROF) ? P.ids + (size_t)x * res_y * 2 : nullptr, PROF ? stat : nullptr, gl, R);
 
+	// DDA: this ray plane's saved states, the chunk in shared memory
+	const int k_total = P.lod.k_total;
+	const float2* const st = P.dda_states + (size_t)ray_i * ((k_total + 31) >> 5) * 3;
+	const unsigned long long* const flag = P.dda_progress + ray_i;
+	int published = 0;                                           // batches of this ray plane k_dda_states is known to have published
+	float3 carry = make_float3(0.0f, 0.0f, 0.0f);                 // no crossing yet: distance 0, x-track (Cuda_Render.h:302-305)
+	int chunk = -1, bl = RLERC_F_CH;                             // next batch: bl of chunk (bl == CH: the next chunk is due)
+	int k_next = 0;                                              // first crossing of the next batch
 	// filter: the batch whose pointer-map gather is in flight
 	Geo fg;
 	fg.pz = fg.py = fg.czz = fg.cyy = 0; fg.cmip = 0; fg.cidx = 0;
 	unsigned fe0 = 0, fe1 = 0;
 	bool fhave = false;
 	int fn = 0;                        // crossings in that batch (0: none in flight)
-	bool dda_done = false;
 	int qhead = 0, qcount = 0;         // live-column queue (uniform)
 	// consume: the batch whose run words are in flight
 	Stage s0;
-	Geo g0 = fg;
-	s0.nvalid = 0; s0.have = false; s0.e0 = s0.e1 = 0;
-	#pragma unroll
-	for (int k = 0; k < 4; k++) s0.rw[k] = 0;
+	Geo g0;
+	stage_clear(s0, g0);
 
 	while (true)
 	{
 		if (Hs.ycmin >= Hs.ycmax) break;                         // Cuda_Render.h:370
 
 		// ---- FILTER: until a full batch of live columns is queued (or the ray plane has reached z_far) -------------
-		while (qcount < 32 && (!dda_done || fn > 0))
+		while (qcount < 32 && (k_next < k_total || fn > 0))
 		{
-			// F1. DDA for the next 32 crossings; the gather of the batch in flight lands meanwhile
-			int nvalid = 0;
 			RLERC_TICK(0);
 			if (PROF) prof[7] += 1;
-			if (!dda_done)
+			// F1. geometry of the next 32 crossings, conservative top clip, pointer-map gather; the gather of the
+			//     batch before it (fg, fe0, fe1) lands meanwhile
+			Geo ng;
+			ng.pz = ng.py = ng.czz = ng.cyy = 0; ng.cmip = 0; ng.cidx = 0;
+			unsigned ne0 = 0, ne1 = 0;
+			bool nhave = false;
+			int nn = 0;
+			if (k_next < k_total)
 			{
-#if RLERC_DDA_ASM == 3
-				nvalid = ddaq_batch_cap(Q, cap, prev_n, last_map, zfar_i, gl);
-#else
-				nvalid = ddaq_batch(Q, rec, prev_n, last_map, zfar_i, gl == 0);
-#endif
-				prev_n = nvalid;
-				if (nvalid < G) dda_done = true;
-				if (IDS && gl == 0) Cn.c_steps += nvalid;
+				if (bl == RLERC_F_CH)
+				{
+					dda_chunk(P, st, flag, published, F.ray_x, F.ray_z, ++chunk, gl, rec, carry);
+					bl = 0;
+					RLERC_TICK(1);
+				}
+				nn = k_total - k_next < G ? k_total - k_next : G;
+				if (gl < nn) nhave = filter_geometry(P, F, rec, carry, bl, gl, Hs.ycmin, ng, ne0, ne1);
+				bl++;
+				k_next += nn;
+				if (IDS && gl == 0) Cn.c_steps += nn;
 			}
-#if RLERC_DDA_ASM != 3
-			__syncwarp();
-#endif
-			RLERC_TICK(1);
+			RLERC_TICK(3);
 			// F2. first-run test of the batch in flight, live columns -> queue
 			if (fn > 0)
 			{
-				const int ycmin = Hs.ycmin;
-				bool live = false;
-				if (gl < fn && fhave)
-				{
-					const int slen = (int)(fe1 & 0xffffu);
-					const unsigned first = fe1 >> 16;
-					const int solid = (int)(first >> 10), skip = (int)(first & 1023u);
-					if (IDS) live = true;                                // the byte model counts no-op columns too
-					else if (slen == 0) live = false;                    // empty column: the run loop does not execute
-					else if (solid == 0) live = true;                    // pure skip run: undecided, let the machinery look
-					else
-					{
-						const float ft = (float)(skip << fg.cmip);         // Cuda_Render.h:529-543 for run 0
-						float zz1 = fg.pz, yy1 = fg.py;
-						if (mountain + ft >= 0) { zz1 += fg.czz; yy1 += fg.cyy; }
-						const float z1 = zz1 + pz_add * ft;
-						if (z1 <= 0) live = true;                          // `continue`: a later run may be the first visible one
-						else
-						{
-							const float y1 = yy1 + py_add * ft;
-							live = f2i(res_y2 + y1 / z1) > ycmin;          // else: break, now and under every later horizon
-						}
-					}
-				}
+				const bool live = gl < fn && fhave && filter_live<IDS>(F, fg, fe1, Hs.ycmin);
 				const unsigned lb = __ballot_sync(FULL, live);
-				if (live)
-				{
-					uint32_t* q = queue + ((qhead + qcount + __popc(lb & lt_mask)) & (RLERC_QCAP - 1));
-					q[0 * RLERC_QCAP] = __float_as_uint(fg.pz); q[1 * RLERC_QCAP] = __float_as_uint(fg.py);
-					q[2 * RLERC_QCAP] = __float_as_uint(fg.czz); q[3 * RLERC_QCAP] = __float_as_uint(fg.cyy);
-					q[4 * RLERC_QCAP] = (uint32_t)fg.cmip; q[5 * RLERC_QCAP] = (uint32_t)fg.cidx;
-					q[6 * RLERC_QCAP] = fe0; q[7 * RLERC_QCAP] = fe1;
-				}
+				if (live) column_put(queue + ((qhead + qcount + __popc(lb & lt_mask)) & (RLERC_QCAP - 1)), RLERC_QCAP, fg, fe0, fe1);
 				qcount += __popc(lb);
 			}
-			RLERC_TICK(2);
-			// F3. geometry of the new crossings, conservative top clip, pointer-map gather (into the registers F2 freed)
-			fn = nvalid;
-			fhave = false;
-#if RLERC_DDA_ASM == 3
-			float4 ra, rb;                                             // state before / after crossing gl
-			if (nvalid > 0)
-			{
-				ra.x = __shfl_up_sync(FULL, cap.cx, 1); ra.y = __shfl_up_sync(FULL, cap.cy, 1); ra.z = __shfl_up_sync(FULL, cap.cz, 1);
-				if (gl == 0) { ra.x = cap.kx; ra.y = cap.ky; ra.z = cap.kz; }
-				rb.x = cap.cx; rb.w = __int_as_float(cap.cmip);
-			}
-#endif
-			if (gl < nvalid)
-			{
-#if RLERC_DDA_ASM != 3
-				const float4 ra = rec[gl], rb = rec[gl + 1];           // state before / after crossing gl
-#endif
-				const float db = fabsf(ra.x), dn = fabsf(rb.x);
-				const int ib = __float_as_int(ra.x) < 0 ? 1 : 0;        // index_before: sign bit of the record
-				fg.cmip = __float_as_int(rb.w);
-				const int fix_x = (1 - ib) * fixx, fix_z = ib * fixz;    // Cuda_Render.h:418-419
-				const float ddelta = dn - db;
-				const float vsx = ray_x * db, vsz = ray_z * db;
-				const int voxel_x = f2i(vpx + ra.y) + fix_x;             // Cuda_Render.h:429-430
-				const int voxel_z = f2i(vpz + ra.z) + fix_z;
-				const int gx = P.level[fg.cmip].sx, gz = P.level[fg.cmip].sz;
-				// CLIPREGION (Cuda_Render.h:432-437): finite scene, columns outside the grid are skipped
-				const bool outside = (P.flags & 1) && (voxel_x < 0 || voxel_z < 0 || (voxel_x >> fg.cmip) > gx - 1 || (voxel_z >> fg.cmip) > gz - 1);
-				const int vx = (voxel_x >> fg.cmip) & (gx - 1);          // Cuda_Render.h:441-442
-				const int vz = (voxel_z >> fg.cmip) & (gz - 1);
-				fg.cidx = vx + vz * gx;
-				const float corx = ray_x * ddelta, corz = ray_z * ddelta;
-				fg.pz = cos_x * vsz + sin_x * mountain;                  // Cuda_Render.h:459-464
-				fg.py = vertical ? (cos_x * mountain - sin_x * vsz) : vsx;
-				fg.py *= rx2mr;
-				fg.czz = cos_x * corz;                                   // Cuda_Render.h:483-486
-				fg.cyy = vertical ? (-sin_x * corz) : corx;
-				fg.cyy *= rx2mr;
-				// The horizon only rises.  For pz > 0 a column culled now stays culled; for pz <= 0 (or NaN)
-				// the test can flip, so keep those.
-				fhave = !outside && (!(fg.pz * res_y2 + fg.py <= fg.pz * (float)Hs.ycmin) || !(fg.pz > 0));   // Cuda_Render.h:467
-				if (fhave)
-				{
-					const uint2 ent = __ldg(P.level[fg.cmip].map + fg.cidx);         // Cuda_Render.h:474-478
-					fe0 = ent.x; fe1 = ent.y;
-				}
-			}
+			fg = ng; fe0 = ne0; fe1 = ne1; fhave = nhave; fn = nn;
 			__syncwarp();
-			RLERC_TICK(3);
+			RLERC_TICK(2);
 		}
 		RLERC_TICK(0);
 
 		// ---- C1. take the next batch of live columns off the queue, request their run words ---------------------
 		Stage s1;
 		Geo g1;
+		stage_clear(s1, g1);
 		{
 			const int n1 = qcount < 32 ? qcount : 32;
 			s1.nvalid = n1; s1.have = gl < n1;
-			s1.e0 = s1.e1 = 0;
-			#pragma unroll
-			for (int k = 0; k < 4; k++) s1.rw[k] = 0;
-			g1.pz = g1.py = g1.czz = g1.cyy = 0; g1.cmip = 0; g1.cidx = 0;
-			if (s1.have)
-			{
-				const uint32_t* q = queue + ((qhead + gl) & (RLERC_QCAP - 1));
-				g1.pz = __uint_as_float(q[0 * RLERC_QCAP]); g1.py = __uint_as_float(q[1 * RLERC_QCAP]);
-				g1.czz = __uint_as_float(q[2 * RLERC_QCAP]); g1.cyy = __uint_as_float(q[3 * RLERC_QCAP]);
-				g1.cmip = (int)q[4 * RLERC_QCAP]; g1.cidx = (int)q[5 * RLERC_QCAP];
-				s1.e0 = q[6 * RLERC_QCAP]; s1.e1 = q[7 * RLERC_QCAP];
-				const int sl = (int)(s1.e1 & 0xffffu);
-				// element i0 of the slab stream is run 0; runs 0..7 are fetched as aligned 32-bit words
-				const unsigned i0 = 2u + s1.e0;
-				const uint32_t* w32 = reinterpret_cast<const uint32_t*>(P.level[g1.cmip].slabs);
-				const uint32_t* p = w32 + ((i0 + (i0 & 1u)) >> 1);
-				const int odd = (int)(i0 & 1u);                            // odd: words hold runs (1,2) (3,4) (5,6) (7,8)
-				s1.rw[0] = (sl > 1) ? __ldg(p) : 0u;
-				s1.rw[1] = (sl > 2 + odd) ? __ldg(p + 1) : 0u;
-				s1.rw[2] = (sl > 4 + odd) ? __ldg(p + 2) : 0u;
-				s1.rw[3] = (sl > 6 + odd) ? __ldg(p + 3) : 0u;
-			}
+			if (s1.have) column_take(P, queue + ((qhead + gl) & (RLERC_QCAP - 1)), RLERC_QCAP, g1, s1);
 			qhead = (qhead + n1) & (RLERC_QCAP - 1);
 			qcount -= n1;
 		}
@@ -501,67 +580,10 @@ k_traverse_f(const __grid_constant__ TraverseParams P, int rays)
 		// ---- C2. project the runs of batch s0 (their words were requested one round ago) -------------------------
 		if (s0.nvalid > 0)
 		{
-			const int ycmin = Hs.ycmin;
 			int slen = 0, nr = 0;
 			bool longcol = false;
-			unsigned flags = 0;               // bit r: run r can be seen (z1 > 0); bit 8+r: its bottom too (z2 > 0)
-			if (s0.have)
-			{
-				{	// run words as loaded in C1 -> runs 0..7, two per register (run 0 rides in the map entry)
-					const unsigned first = s0.e1 >> 16;
-					const unsigned a = s0.rw[0], b = s0.rw[1], c = s0.rw[2], d = s0.rw[3];
-					if (!((2u + s0.e0) & 1u)) s0.rw[0] = first | (a & 0xffff0000u);
-					else
-					{
-						s0.rw[0] = first | (a << 16);
-						s0.rw[1] = __funnelshift_r(a, b, 16);
-						s0.rw[2] = __funnelshift_r(b, c, 16);
-						s0.rw[3] = __funnelshift_r(c, d, 16);
-					}
-				}
-				slen = (int)(s0.e1 & 0xffffu);
-				nr = slen < RLERC_RW ? slen : RLERC_RW;
-				longcol = slen > RLERC_RW;
-				int blen = 0;
-				for (int r = 0; r < nr; r++)
-				{
-					const unsigned rw = run_word(s0.rw, r);
-					const int skip = (int)(rw & 1023u), solid = (int)(rw >> 10);
-					const int top = (blen + skip) << g0.cmip;                // sti_general_sti_skip
-					const int bot = top + (solid << g0.cmip);                // sti_general
-					blen += skip + solid;
-					if (solid == 0) continue;
-					const float ft = (float)top, fb = (float)bot;           // Cuda_Render.h:529-560
-					float zz1 = g0.pz, yy1 = g0.py;
-					if (mountain + ft >= 0) { zz1 += g0.czz; yy1 += g0.cyy; }
-					const float z1 = zz1 + pz_add * ft;
-					if (z1 <= 0) continue;
-					flags |= 1u << r;
-					const float y1 = yy1 + py_add * ft;
-					const int sy2 = f2i(res_y2 + y1 / z1);
-					int sy1 = 0;
-					if (sy2 > ycmin)
-					{
-						float zz2 = g0.pz, yy2 = g0.py;
-						if (mountain + fb < 0) { zz2 += g0.czz; yy2 += g0.cyy; }
-						const float z2 = zz2 + pz_add * fb;
-						if (!(z2 <= 0))
-						{
-							flags |= 1u << (8 + r);
-							const float y2 = yy2 + py_add * fb;
-							sy1 = f2i(res_y2 + y2 / z2 - 1);
-						}
-					}
-					proj[r * 32 + gl] = make_int2(sy1, sy2);
-					if (sy2 <= ycmin)
-					{
-						// breaks now, hence under every later (higher) horizon: later runs are dead
-						nr = r + 1; longcol = false;
-						break;
-					}
-				}
-			}
-
+			unsigned flags = 0;
+			if (s0.have) column_project(F, s0, g0, Hs.ycmin, gl, proj, slen, nr, longcol, flags);
 			RLERC_TICK(5);
 			if (PROF) prof[7] += 1ll << 32;
 			// ---- B / B0 / S. consume batch s0 (traverse_common.cuh) ----------------------------------------------
@@ -569,7 +591,7 @@ k_traverse_f(const __grid_constant__ TraverseParams P, int rays)
 			RLERC_TICK(6);
 			if (finished) break;
 		}
-		else if (s1.nvalid == 0 && dda_done && fn == 0 && qcount == 0) break;   // drained (z > z_far, Cuda_Render.h:367)
+		else if (s1.nvalid == 0 && k_next >= k_total && fn == 0 && qcount == 0) break;   // drained (z > z_far, Cuda_Render.h:367)
 
 		s0 = s1; g0 = g1;
 	}
@@ -587,47 +609,89 @@ k_traverse_f(const __grid_constant__ TraverseParams P, int rays)
 		for (int k = 0; k < 8; k++) out[k] = (unsigned long long)prof[k];
 		for (int k = 0; k < 16; k++) out[8 + k] = (unsigned long long)stat[k];
 	}
+	RLERC_EXIT_AFTER_PREPASS();
+}
+
+static int launch_rays(const TraverseParams& p)
+{
+	return (p.slice_n > 1) ? owned_count(p.ray_end, p.slice_block, p.slice_n, p.slice_rank) : p.ray_end - p.ray_begin;
+}
+
+// dynamic shared memory above 48 KB is an opt-in per kernel AND per device
+template <typename K>
+static void opt_in_smem(K kernel, size_t smem, size_t (&configured_on)[64])
+{
+	int dev = 0;
+	cudaGetDevice(&dev);
+	size_t& configured = configured_on[dev & 63];
+	if (smem > configured)
+	{
+		cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		configured = smem;
+	}
+}
+
+size_t traverse_dda_state_bytes(const TraverseParams& p)
+{
+	const int rays = launch_rays(p);
+	return (size_t)(rays > 0 ? rays : 0) * ((p.lod.k_total + 31) >> 5) * 3 * sizeof(float2);
+}
+
+size_t traverse_dda_progress_bytes(const TraverseParams& p)
+{
+	const int rays = launch_rays(p);
+	return (size_t)(rays > 0 ? rays : 0) * sizeof(unsigned long long);
+}
+
+void launch_dda_states(const TraverseParams& p, cudaStream_t st)
+{
+	const int rays = launch_rays(p);
+	if (rays <= 0 || p.lod.k_total <= 0) return;
+	k_dda_states<<<(rays + 63) / 64, 64, 0, st>>>(p, rays);
+}
+
+// launch behind k_dda_states with programmatic stream serialization: the kernel may start while the pre-pass still runs
+template <typename K>
+static void launch_overlapped(K kernel, int blocks, int threads, size_t smem, cudaStream_t st, const TraverseParams& p, int rays)
+{
+	cudaLaunchConfig_t cfg;
+	memset(&cfg, 0, sizeof(cfg));
+	cfg.gridDim = dim3((unsigned)blocks); cfg.blockDim = dim3((unsigned)threads);
+	cfg.dynamicSmemBytes = smem; cfg.stream = st;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attr[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = attr; cfg.numAttrs = 1;
+	cudaLaunchKernelEx(&cfg, kernel, p, rays);
 }
 
 template <bool IDS, bool PROF>
 static void launch_f(const TraverseParams& p, cudaStream_t st)
 {
 	const int wpb = RLERC_F_WPB;
-	const int rays = (p.slice_n > 1) ? owned_count(p.ray_end, p.slice_block, p.slice_n, p.slice_rank) : p.ray_end - p.ray_begin;
+	const int rays = launch_rays(p);
 	if (rays <= 0) return;
 	const int blocks = (rays + wpb - 1) / wpb;
-	const size_t smem = (size_t)wpb * ((RLERC_F_REC + RLERC_F_QUEUE + 16 + RLERC_PS_WORDS + p.mask_words + 3) & ~3) * sizeof(uint32_t);
-	// dynamic shared memory above 48 KB is an opt-in per kernel AND per device
+	const size_t smem = (size_t)wpb * f_words_per_warp(p.mask_words) * sizeof(uint32_t);
 	static size_t configured_on[64] = { 0 };
-	int dev = 0;
-	cudaGetDevice(&dev);
-	size_t& configured = configured_on[dev & 63];
-	if (smem > configured)
-	{
-		cudaFuncSetAttribute(k_traverse_f<IDS, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		configured = smem;
-	}
-	k_traverse_f<IDS, PROF><<<blocks, wpb * 32, smem, st>>>(p, rays);
+	opt_in_smem(k_traverse_f<IDS, PROF>, smem, configured_on);
+	launch_overlapped(k_traverse_f<IDS, PROF>, blocks, wpb * 32, smem, st, p, rays);
 }
 
 
 // ================================================================================================================
 // k_traverse_p (variant 68; picked automatically for launches of at most 12 ray planes per SM, capi.cu pick_lanes):
 // the same algorithm with the two loops of k_traverse_f on TWO warps per
-// ray plane.  Warp F runs the FILTER (DDA, first-run test, pointer-map gather) and pushes the live columns into a ring
-// in shared memory; warp C pops batches of 32, loads and projects their runs and runs consume_batch.  A ray plane's
-// chain becomes max(filter, consume) instead of their sum.  The filter only ever drops provable no-ops under a horizon
-// that can only rise, so a stale y_clip_min (published by C after every batch) lets more columns through but cannot
-// change the result: the picture does not depend on timing.
+// ray plane.  Warp F runs the FILTER (DDA chunks, pointer-map gather, first-run test) and pushes the live columns into
+// a ring in shared memory; warp C pops batches of 32, loads and projects their runs and runs consume_batch.  A ray
+// plane's chain becomes max(filter, consume) instead of their sum.  The filter only ever drops provable no-ops under
+// a horizon that can only rise, so a stale y_clip_min (published by C after every batch) lets more columns through
+// but cannot change the result: the picture does not depend on timing.
 // Protocol (volatile words in shared memory, one writer each): tail (F), head (C), ycmin (C), done (F), closed (C).
 // F waits while the ring has no room for 32 more entries, C waits until 32 entries are there or F is done; both
 // waits are bounded (a broken protocol traps after >= 1 s of polling: a launch error, neither a hang nor a wrong picture).  Waiting is __nanosleep(64)
-// polling by the whole warp; on a full frame the polling loops are up to 30 % of the kernel's instructions (ncu source
-// view).  Tried instead, all bit-exact, all slower (1080p frame 0, full frame / uncontended chain, ms; shipped: 0.86 /
-// 0.36): back-off 128 ns .. 2 us 0.85 / 0.37; back-off 512 ns .. 8 us 0.94 / 0.46; mbarrier.try_wait as "sleep until
-// the partner signals" (one arrive per tail / head update; the phase bookkeeping falls behind when nobody waits, so
-// waits run into their time limit) 1.09 / 0.41; lane 0 polling alone with one vector load of the control words, the
-// other lanes parked at the broadcast shuffle 1.16 / 0.48.
+// polling by the whole warp.  Tried instead in round 1, all bit-exact, all slower: back-off polling, mbarrier.try_wait as
+// "sleep until the partner signals", lane 0 polling alone with the other lanes parked at a shuffle.
 #ifndef RLERC_P_RCAP
 #define RLERC_P_RCAP 128
 #endif
@@ -654,6 +718,11 @@ static_assert(RLERC_P_REG_F == 0 || RLERC_P_REG_F + RLERC_P_REG_C <= 160, "setma
 
 __device__ __noinline__ void pair_protocol_broken() { __trap(); }     // cold: keeps the trap out of the wait loops' code
 
+__host__ __device__ inline int p_words_per_plane(int mask_words)
+{
+	return (RLERC_F_REC + RLERC_P_RING + 8 + 16 + RLERC_PS_WORDS + mask_words + 3) & ~3;
+}
+
 __global__ void __launch_bounds__(RLERC_P_PLANES * 64, RLERC_P_REG_F ? 3 : 2)
 k_traverse_p(const __grid_constant__ TraverseParams P, int rays)
 {
@@ -674,9 +743,8 @@ k_traverse_p(const __grid_constant__ TraverseParams P, int rays)
 	const int x = inrange ? owned_ray(P, ray_i) : P.ray_begin;
 
 	// shared per ray plane: crossing records | ring | ctl | DrawJob | projections + span records | occlusion bits
-	const int per_plane = (RLERC_F_REC + RLERC_P_RING + 8 + 16 + RLERC_PS_WORDS + P.mask_words + 3) & ~3;
-	uint32_t* wbase = smem + (size_t)pl * per_plane;
-	float4* rec = reinterpret_cast<float4*>(wbase);
+	uint32_t* wbase = smem + (size_t)pl * p_words_per_plane(P.mask_words);
+	const RecView rec = rec_view(wbase);
 	uint32_t* ring = wbase + RLERC_F_REC;                            // [8][RCAP]
 	volatile int* ctl = reinterpret_cast<volatile int*>(wbase + RLERC_F_REC + RLERC_P_RING);   // tail, head, ycmin, done, closed
 	DrawJob* job = reinterpret_cast<DrawJob*>(wbase + RLERC_F_REC + RLERC_P_RING + 8);
@@ -685,16 +753,11 @@ k_traverse_p(const __grid_constant__ TraverseParams P, int rays)
 	uint32_t* ymask = wbase + RLERC_F_REC + RLERC_P_RING + 8 + 16 + RLERC_PS_WORDS;
 
 	const int res_y = P.res_y;
-	const float res_y2 = (float)(res_y / 2);
 	uint32_t* row = P.warp + (size_t)x * res_y;
 	RayInit ri;
 	ray_init(P, x, ri);
-	const float ray_x = ri.ray_x, ray_z = ri.ray_z, rx2mr = ri.rx2mr;
-	const bool vertical = ri.vertical;
-	const float sin_x = P.sin_x, cos_x = P.cos_x;
-	const float vpx = P.viewpos[0], mountain = P.viewpos[1], vpz = P.viewpos[2];
-	const float pz_add = sin_x;
-	const float py_add = (vertical ? cos_x : 0.0f) * rx2mr;
+	FilterRay F;
+	filter_ray_init(P, ri, F);
 	const int ymin0 = ri.ycmin, ymax0 = ri.ycmax;
 
 	// control words: C initialises, the named barrier below (both warps of the pair) publishes them
@@ -712,33 +775,22 @@ k_traverse_p(const __grid_constant__ TraverseParams P, int rays)
 #if RLERC_P_REG_F
 		asm volatile("setmaxnreg.dec.sync.aligned.u32 " RLERC_STR(RLERC_P_REG_F) ";");
 #endif
-		if (!active) return;
-		// ================= warp F: DDA -> geometry + gather -> first-run test -> ring ==========================
-		int fixx, fixz;
-		DdaQ Q;
-		{
-			Dda dd;
-			dda_init(P, ray_x, ray_z, dd);
-			fixx = dd.fixx; fixz = dd.fixz;
-			Q.d0 = dd.d0; Q.x0 = dd.i0x; Q.y0 = dd.i0y; Q.nd1 = -dd.d1; Q.x1 = dd.i1x; Q.y1 = dd.i1y;
-			Q.gd0 = dd.gd0; Q.gx0 = dd.g0x; Q.gy0 = dd.g0y; Q.ngd1 = -dd.gd1; Q.gx1 = dd.g1x; Q.gy1 = dd.g1y;
-		}
-		Q.mip = 0; Q.zi = 0; Q.dzi = 1; Q.mapswitch = P.mapswitch0;
-		if (gl == 0) rec[0] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-		int prev_n = 0;
-		__syncwarp();
-		const int zfar_i = P.z_far;
-		const int last_map = P.nummaps - 1;
-		for (float yms = mountain; yms > 512.0f; yms = yms * 0.5f) ddaq_lod_switch(Q, last_map);
+		if (!active) { RLERC_EXIT_AFTER_PREPASS(); return; }
+		// ================= warp F: DDA chunks -> geometry + gather -> first-run test -> ring ====================
+		const int k_total = P.lod.k_total;
+		const float2* const st = P.dda_states + (size_t)ray_i * ((k_total + 31) >> 5) * 3;
+		const unsigned long long* const flag = P.dda_progress + ray_i;
+		int published = 0;
+		float3 carry = make_float3(0.0f, 0.0f, 0.0f);
+		int chunk = -1, bl = RLERC_F_CH, k_next = 0;
 		Geo fg;
 		fg.pz = fg.py = fg.czz = fg.cyy = 0; fg.cmip = 0; fg.cidx = 0;
 		unsigned fe0 = 0, fe1 = 0;
 		bool fhave = false;
 		int fn = 0;
-		bool dda_done = false;
 		int tail = 0;
 		bool closed = false;
-		while (!dda_done || fn > 0)
+		while (k_next < k_total || fn > 0)
 		{
 			// room for 32 more entries?  (head only grows)
 			// (lane 0 reads the control words and broadcasts them: every decision on them is warp-uniform)
@@ -754,89 +806,36 @@ k_traverse_p(const __grid_constant__ TraverseParams P, int rays)
 				if (++spins > RLERC_P_SPIN_MAX) { pair_protocol_broken(); if (gl == 0) ctl[4] = 1; closed = true; break; }
 			}
 			if (closed) break;                                         // ycmin: possibly stale, lower than the truth, never higher
-			int nvalid = 0;
-			if (!dda_done)
+			Geo ng;
+			ng.pz = ng.py = ng.czz = ng.cyy = 0; ng.cmip = 0; ng.cidx = 0;
+			unsigned ne0 = 0, ne1 = 0;
+			bool nhave = false;
+			int nn = 0;
+			if (k_next < k_total)
 			{
-				nvalid = ddaq_batch(Q, rec, prev_n, last_map, zfar_i, gl == 0);
-				prev_n = nvalid;
-				if (nvalid < G) dda_done = true;
+				if (bl == RLERC_F_CH) { dda_chunk(P, st, flag, published, F.ray_x, F.ray_z, ++chunk, gl, rec, carry); bl = 0; }
+				nn = k_total - k_next < G ? k_total - k_next : G;
+				if (gl < nn) nhave = filter_geometry(P, F, rec, carry, bl, gl, ycmin, ng, ne0, ne1);
+				bl++;
+				k_next += nn;
 			}
-			__syncwarp();
 			if (fn > 0)
 			{
-				bool live = false;
-				if (gl < fn && fhave)
-				{
-					const int slen = (int)(fe1 & 0xffffu);
-					const unsigned first = fe1 >> 16;
-					const int solid = (int)(first >> 10), skip = (int)(first & 1023u);
-					if (slen == 0) live = false;
-					else if (solid == 0) live = true;
-					else
-					{
-						const float ft = (float)(skip << fg.cmip);
-						float zz1 = fg.pz, yy1 = fg.py;
-						if (mountain + ft >= 0) { zz1 += fg.czz; yy1 += fg.cyy; }
-						const float z1 = zz1 + pz_add * ft;
-						if (z1 <= 0) live = true;
-						else
-						{
-							const float y1 = yy1 + py_add * ft;
-							live = f2i(res_y2 + y1 / z1) > ycmin;
-						}
-					}
-				}
+				const bool live = gl < fn && fhave && filter_live<false>(F, fg, fe1, ycmin);
 				const unsigned lb = __ballot_sync(FULL, live);
-				if (live)
-				{
-					uint32_t* q = ring + ((tail + __popc(lb & lt_mask)) & (RLERC_P_RCAP - 1));
-					q[0 * RLERC_P_RCAP] = __float_as_uint(fg.pz); q[1 * RLERC_P_RCAP] = __float_as_uint(fg.py);
-					q[2 * RLERC_P_RCAP] = __float_as_uint(fg.czz); q[3 * RLERC_P_RCAP] = __float_as_uint(fg.cyy);
-					q[4 * RLERC_P_RCAP] = (uint32_t)fg.cmip; q[5 * RLERC_P_RCAP] = (uint32_t)fg.cidx;
-					q[6 * RLERC_P_RCAP] = fe0; q[7 * RLERC_P_RCAP] = fe1;
-				}
+				if (live) column_put(ring + ((tail + __popc(lb & lt_mask)) & (RLERC_P_RCAP - 1)), RLERC_P_RCAP, fg, fe0, fe1);
 				tail += __popc(lb);
 				__threadfence_block();
 				__syncwarp();
 				if (gl == 0 && lb) ctl[0] = tail;
 			}
-			fn = nvalid;
-			fhave = false;
-			if (gl < nvalid)
-			{
-				const float4 ra = rec[gl], rb = rec[gl + 1];
-				const float db = fabsf(ra.x), dn = fabsf(rb.x);
-				const int ib = __float_as_int(ra.x) < 0 ? 1 : 0;
-				fg.cmip = __float_as_int(rb.w);
-				const int fix_x = (1 - ib) * fixx, fix_z = ib * fixz;
-				const float ddelta = dn - db;
-				const float vsx = ray_x * db, vsz = ray_z * db;
-				const int voxel_x = f2i(vpx + ra.y) + fix_x;
-				const int voxel_z = f2i(vpz + ra.z) + fix_z;
-				const int gx = P.level[fg.cmip].sx, gz = P.level[fg.cmip].sz;
-				const bool outside = (P.flags & 1) && (voxel_x < 0 || voxel_z < 0 || (voxel_x >> fg.cmip) > gx - 1 || (voxel_z >> fg.cmip) > gz - 1);
-				const int vx = (voxel_x >> fg.cmip) & (gx - 1);
-				const int vz = (voxel_z >> fg.cmip) & (gz - 1);
-				fg.cidx = vx + vz * gx;
-				const float corx = ray_x * ddelta, corz = ray_z * ddelta;
-				fg.pz = cos_x * vsz + sin_x * mountain;
-				fg.py = vertical ? (cos_x * mountain - sin_x * vsz) : vsx;
-				fg.py *= rx2mr;
-				fg.czz = cos_x * corz;
-				fg.cyy = vertical ? (-sin_x * corz) : corx;
-				fg.cyy *= rx2mr;
-				fhave = !outside && (!(fg.pz * res_y2 + fg.py <= fg.pz * (float)ycmin) || !(fg.pz > 0));
-				if (fhave)
-				{
-					const uint2 ent = __ldg(P.level[fg.cmip].map + fg.cidx);
-					fe0 = ent.x; fe1 = ent.y;
-				}
-			}
+			fg = ng; fe0 = ne0; fe1 = ne1; fhave = nhave; fn = nn;
 			__syncwarp();
 		}
 		__threadfence_block();
 		__syncwarp();
 		if (gl == 0 && !closed) { ctl[0] = tail; __threadfence_block(); ctl[3] = 1; }
+		RLERC_EXIT_AFTER_PREPASS();
 		return;
 	}
 
@@ -844,23 +843,16 @@ k_traverse_p(const __grid_constant__ TraverseParams P, int rays)
 #if RLERC_P_REG_F
 	asm volatile("setmaxnreg.inc.sync.aligned.u32 " RLERC_STR(RLERC_P_REG_C) ";");
 #endif
-	if (!active) return;
+	if (!active) { RLERC_EXIT_AFTER_PREPASS(); return; }
 	HorizonState Hs;
 	Hs.ycmin = ri.ycmin; Hs.ycmax = ri.ycmax; Hs.hiw = 0;
 	Counters Cn;
 	memset(&Cn, 0, sizeof(Cn));
 	RayCtx R;
-	R.row = row; R.ymask = ymask; R.ids = nullptr;
-	R.res_y2 = res_y2; R.pz_add = pz_add; R.py_add = py_add; R.mountain = mountain; R.gl = gl;
-	R.stat = nullptr;
-	R.hc_on = (P.flags & 2) ? 1 : 0;
-	R.hc = f2i((4095.0f - mountain) + P.viewpos[1]);
+	ray_ctx_init(P, F, row, ymask, nullptr, nullptr, gl, R);
 	Geo g0;
-	g0.pz = g0.py = g0.czz = g0.cyy = 0; g0.cmip = 0; g0.cidx = 0;
 	Stage s0;
-	s0.nvalid = 0; s0.have = false; s0.e0 = s0.e1 = 0;
-	#pragma unroll
-	for (int k = 0; k < 4; k++) s0.rw[k] = 0;
+	stage_clear(s0, g0);
 	int head = 0;
 	while (true)
 	{
@@ -885,30 +877,11 @@ k_traverse_p(const __grid_constant__ TraverseParams P, int rays)
 		__syncwarp();
 		Stage s1;
 		Geo g1;
+		stage_clear(s1, g1);
 		{
 			const int n1 = avail < 32 ? avail : 32;
 			s1.nvalid = n1; s1.have = gl < n1;
-			s1.e0 = s1.e1 = 0;
-			#pragma unroll
-			for (int k = 0; k < 4; k++) s1.rw[k] = 0;
-			g1.pz = g1.py = g1.czz = g1.cyy = 0; g1.cmip = 0; g1.cidx = 0;
-			if (s1.have)
-			{
-				const uint32_t* q = ring + ((head + gl) & (RLERC_P_RCAP - 1));
-				g1.pz = __uint_as_float(q[0 * RLERC_P_RCAP]); g1.py = __uint_as_float(q[1 * RLERC_P_RCAP]);
-				g1.czz = __uint_as_float(q[2 * RLERC_P_RCAP]); g1.cyy = __uint_as_float(q[3 * RLERC_P_RCAP]);
-				g1.cmip = (int)q[4 * RLERC_P_RCAP]; g1.cidx = (int)q[5 * RLERC_P_RCAP];
-				s1.e0 = q[6 * RLERC_P_RCAP]; s1.e1 = q[7 * RLERC_P_RCAP];
-				const int sl = (int)(s1.e1 & 0xffffu);
-				const unsigned i0 = 2u + s1.e0;
-				const uint32_t* w32 = reinterpret_cast<const uint32_t*>(P.level[g1.cmip].slabs);
-				const uint32_t* p = w32 + ((i0 + (i0 & 1u)) >> 1);
-				const int odd = (int)(i0 & 1u);
-				s1.rw[0] = (sl > 1) ? __ldg(p) : 0u;
-				s1.rw[1] = (sl > 2 + odd) ? __ldg(p + 1) : 0u;
-				s1.rw[2] = (sl > 4 + odd) ? __ldg(p + 2) : 0u;
-				s1.rw[3] = (sl > 6 + odd) ? __ldg(p + 3) : 0u;
-			}
+			if (s1.have) column_take(P, ring + ((head + gl) & (RLERC_P_RCAP - 1)), RLERC_P_RCAP, g1, s1);
 			head += n1;
 			__syncwarp();
 			if (gl == 0 && n1) ctl[1] = head;                          // the slots may be overwritten from now on
@@ -916,61 +889,10 @@ k_traverse_p(const __grid_constant__ TraverseParams P, int rays)
 		// C2. project the runs of batch s0
 		if (s0.nvalid > 0)
 		{
-			const int ycmin = Hs.ycmin;
 			int slen = 0, nr = 0;
 			bool longcol = false;
 			unsigned flags = 0;
-			if (s0.have)
-			{
-				{
-					const unsigned first = s0.e1 >> 16;
-					const unsigned a = s0.rw[0], b = s0.rw[1], c = s0.rw[2], d = s0.rw[3];
-					if (!((2u + s0.e0) & 1u)) s0.rw[0] = first | (a & 0xffff0000u);
-					else
-					{
-						s0.rw[0] = first | (a << 16);
-						s0.rw[1] = __funnelshift_r(a, b, 16);
-						s0.rw[2] = __funnelshift_r(b, c, 16);
-						s0.rw[3] = __funnelshift_r(c, d, 16);
-					}
-				}
-				slen = (int)(s0.e1 & 0xffffu);
-				nr = slen < RLERC_RW ? slen : RLERC_RW;
-				longcol = slen > RLERC_RW;
-				int blen = 0;
-				for (int r = 0; r < nr; r++)
-				{
-					const unsigned rw = run_word(s0.rw, r);
-					const int skip = (int)(rw & 1023u), solid = (int)(rw >> 10);
-					const int top = (blen + skip) << g0.cmip;
-					const int bot = top + (solid << g0.cmip);
-					blen += skip + solid;
-					if (solid == 0) continue;
-					const float ft = (float)top, fb = (float)bot;
-					float zz1 = g0.pz, yy1 = g0.py;
-					if (mountain + ft >= 0) { zz1 += g0.czz; yy1 += g0.cyy; }
-					const float z1 = zz1 + pz_add * ft;
-					if (z1 <= 0) continue;
-					flags |= 1u << r;
-					const float y1 = yy1 + py_add * ft;
-					const int sy2 = f2i(res_y2 + y1 / z1);
-					int sy1 = 0;
-					if (sy2 > ycmin)
-					{
-						float zz2 = g0.pz, yy2 = g0.py;
-						if (mountain + fb < 0) { zz2 += g0.czz; yy2 += g0.cyy; }
-						const float z2 = zz2 + pz_add * fb;
-						if (!(z2 <= 0))
-						{
-							flags |= 1u << (8 + r);
-							const float y2 = yy2 + py_add * fb;
-							sy1 = f2i(res_y2 + y2 / z2 - 1);
-						}
-					}
-					proj[r * 32 + gl] = make_int2(sy1, sy2);
-					if (sy2 <= ycmin) { nr = r + 1; longcol = false; break; }
-				}
-			}
+			if (s0.have) column_project(F, s0, g0, Hs.ycmin, gl, proj, slen, nr, longcol, flags);
 			const bool finished = consume_batch<IDS, PROF>(P, R, Hs, Cn, s0, g0, slen, nr, longcol, flags, proj, shade, job);
 			if (gl == 0) ctl[2] = Hs.ycmin;                            // the filter's (stale) horizon
 			if (finished) break;
@@ -982,24 +904,18 @@ k_traverse_p(const __grid_constant__ TraverseParams P, int rays)
 	if (gl == 0) ctl[4] = 1;                                           // releases a filter warp that is still running
 	for (int y = ymin0 + gl; y <= ymax0; y += G)
 		if (!((ymask[y >> 5] >> (y & 31)) & 1u)) st_warp(row + y, RLERC_SKY);
+	RLERC_EXIT_AFTER_PREPASS();
 }
 
 void launch_traverse_pair(const TraverseParams& p, cudaStream_t st)
 {
-	const int rays = (p.slice_n > 1) ? owned_count(p.ray_end, p.slice_block, p.slice_n, p.slice_rank) : p.ray_end - p.ray_begin;
+	const int rays = launch_rays(p);
 	if (rays <= 0) return;
 	const int blocks = (rays + RLERC_P_PLANES - 1) / RLERC_P_PLANES;
-	const size_t smem = (size_t)RLERC_P_PLANES * ((RLERC_F_REC + RLERC_P_RING + 8 + 16 + RLERC_PS_WORDS + p.mask_words + 3) & ~3) * sizeof(uint32_t);
+	const size_t smem = (size_t)RLERC_P_PLANES * p_words_per_plane(p.mask_words) * sizeof(uint32_t);
 	static size_t configured_on[64] = { 0 };
-	int dev = 0;
-	cudaGetDevice(&dev);
-	size_t& configured = configured_on[dev & 63];
-	if (smem > configured)
-	{
-		cudaFuncSetAttribute(k_traverse_p, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		configured = smem;
-	}
-	k_traverse_p<<<blocks, RLERC_P_PLANES * 64, smem, st>>>(p, rays);
+	opt_in_smem(k_traverse_p, smem, configured_on);
+	launch_overlapped(k_traverse_p, blocks, RLERC_P_PLANES * 64, smem, st, p, rays);
 }
 
 void launch_traverse_filter(const TraverseParams& p, bool ids, cudaStream_t st)

@@ -33,7 +33,7 @@
 #include "kernels.cuh"
 #include "device_common.cuh"
 
-#include "traverse_common.cuh"
+#include "traverse_variants.cuh"
 
 namespace rlerc {
 

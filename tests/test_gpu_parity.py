@@ -25,6 +25,15 @@ def gpu(R):
     r.close()
 
 
+def _variants(R):
+    """The measured-and-rejected kernels of round 1 (lanes 64, 66, 67) are only in a library built with VARIANTS=1."""
+    return bool(R.lib().rlerc_has_variants())
+
+
+def _lanes_list(R, lanes):
+    return [l for l in lanes if l not in (64, 66, 67) or _variants(R)]
+
+
 def _fresh_warp(r, cfg):
     wp = r.warp_buffer(cfg)
     r.upload(wp, np.zeros((cfg.rays_casted, cfg.render_size), np.uint32))
@@ -39,6 +48,8 @@ def _oracle(rb, rm, scene, cfg, ids=False):
 
 @pytest.mark.parametrize("lanes", [0, 68, 66, 67, 65, 64, 32, 8, 1])
 def test_warp_buffer_bit_exact_camera_grid(R, rb, gpu, scene_mid, lanes):
+    if lanes in (64, 66, 67) and not _variants(R):
+        pytest.skip("variant kernels are not in this build (make VARIANTS=1)")
     gpu.all_to_gpu(scene_mid)
     gpu.set_lanes_per_ray(lanes)
     cfg = R.FrameConfig.default(640, 480)
@@ -65,6 +76,8 @@ def test_dda_variants_bit_exact(R, rb, gpu, scene_mid, variant):
     """k_traverse_w can advance the DDA four ways (closed form evaluated lane-parallel, serial recurrence in
     every warp, merge path over the two tracks, dedicated producer blocks + ring in global memory): same warped
     buffer, bit for bit."""
+    if not _variants(R):
+        pytest.skip("variant kernels are not in this build (make VARIANTS=1)")
     gpu.all_to_gpu(scene_mid)
     gpu.set_lanes_per_ray(64)
     gpu.set_dda_mode({"merge": 2, "closed": 3}.get(variant, 0))
@@ -193,7 +206,7 @@ def test_degenerate_scenes_bit_exact(R, rb, gpu):
                 assert abs(c[k] - cnt[k]) <= 0.005 * cnt[k], (name, k, c[k], cnt[k], rot)
                 if name != "noise50":
                     assert c[k] == cnt[k], (name, k, c[k], cnt[k], rot)
-            for lanes in (0, 65, 68, 64, 66, 32, 1):
+            for lanes in _lanes_list(R, (0, 65, 68, 64, 66, 32, 1)):
                 gpu.set_lanes_per_ray(lanes)
                 _fresh_warp(gpu, cfg)
                 gpu.render(rm, cfg)
@@ -503,7 +516,7 @@ def test_core_h_options_clipregion_height_color(R, rb, gpu, scene_small, scene_m
                     assert np.array_equal(got, want), (flags, lanes, wh, pos, int((got != want).sum()))
     cfg = R.FrameConfig.default(512, 384)
     cfg.flags = flags
-    gpu.set_lanes_per_ray(64)
+    gpu.set_lanes_per_ray(32)                      # the simple lane <-> run kernels do not implement the flags
     with pytest.raises(R.RlercError):
         gpu.render(R.RayMap(cfg).get_ray_map(*cams[0]), cfg)
     gpu.set_lanes_per_ray(0)
