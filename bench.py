@@ -3,19 +3,29 @@
 
     python bench.py --gpus N --steps K --warmup W [--workload NAME] [--impl reference]
 
-A step is ONE FRAME of the hot path (frame setup -> traversal kernel -> unwarp kernel [-> NCCL
-compositing for N > 1]) on the scripted fly-through of BASELINE config 2; step i of K renders path
-frame i*1000/K, so any K covers the whole orbit.  One process per GPU (torchrun sets RANK/...).
+A step is ONE FRAME of the hot path (frame setup -> k_dda_states + traversal kernel -> unwarp kernel [-> NCCL
+compositing for N > 1]) on the scripted fly-through of BASELINE config 2; step i of K renders path frame
+i*1000/K, so any K covers the whole orbit.  One process per GPU (torchrun sets RANK/...).
 
-value      pixel-rays/s = W*H*frames/s, scene + buffers resident in HBM, device-timed (CUDA events
-           on the launching stream, summed over the K steps, max over ranks).  L2 is flushed between
-           timed steps by writing a 512 MiB buffer (outside the timed intervals).
-e2e        the same frames through the C ABI with HOST buffers: camera pose in, RGBA frame out in
-           pinned host memory, D2H inside the timed region (pipelined submit/wait, wall clock).
-roofline   traversal kernel: algorithmic bytes per frame (8C + 2(E-C1) + 6P + 4K, DESIGN.md §5, counted
-           by the instrumented kernel on 8 path frames) / its CUDA-event duration, vs the measured HBM peak.
-cpu_baseline / --impl reference: the reference's own render_line compiled for the host (oracle/_ref,
-           OpenMP over ray planes) + the oracle's unwarp, on a bounded sample of the same frames.
+value      pixel-rays/s = W*H*frames/s of the whole K-frame job, scene + buffers resident in HBM, `--inflight` (4)
+           frames in flight per GPU (one stream and one set of frame buffers per slot), device-timed from a CUDA event
+           in front of the first frame to one behind the last, max over ranks.  The job is repeated R times so that the
+           timed region lasts >= 0.6 s (ms_per_step = total / (R*K); per-repeat times in `repeats`).  For N > 1 every
+           frame is split into interleaved ray-plane slices over all GPUs (north-star split) and composited on rank 0
+           with one NCCL reduce; the same method at every N.
+latency    the same frames one at a time, L2 flushed (512 MiB write) before every frame, per-frame CUDA events:
+           the round-1 `value` method, kept for comparison (mean / p50 / p99 / max).
+e2e        the same metric through the C ABI with HOST buffers: camera pose in, RGBA frame out in pinned host memory,
+           copies inside the timed region.  N = 1: rlerc_frame_submit / rlerc_frame_wait; N > 1: slices + NCCL
+           reduce_scatter, every rank copies its own rows of the finished frame into ONE host frame buffer shared by all
+           ranks (no rank-0 funnel).
+roofline   traversal kernel: algorithmic bytes per frame (8C + 2(E-C1) + 6P + 4K, DESIGN.md §5, counted by the
+           instrumented kernel on 8 path frames) / its CUDA-event duration in the latency pass (kernel timed alone:
+           burst peak), vs the measured HBM peak; L2 and DRAM traffic of the same launch from the committed ncu capture.
+parity     frames of THIS workload compared with the reference's render_line compiled for the host (oracle/_ref),
+           outside the timed regions.
+cpu_baseline / --impl reference: the reference's own render_line compiled for the host (oracle/_ref, OpenMP over ray
+           planes) + the oracle's unwarp, on a bounded sample of the same frames.
 """
 import argparse
 import ctypes as C
@@ -38,7 +48,7 @@ WORKLOADS = {
     "tiled4k": (0, (512, 512, 512), 16, (3840, 2160), "BASELINE config 3: 16x16 physical tiling (multi-GB RLE) at 3840x2160"),
     "shortrun4k": (1, (2048, 1024, 2048), 1, (3840, 2160), "BASELINE config 4 (reduced footprint): worst-case short-run band at 3840x2160"),
     "shortrun16k": (2, (16384, 1024, 16384), 1, (3840, 2160), "BASELINE config 4 at full size: 16384 x 1024 x 16384 heightfield + cave floors + worst-case short-run band (rlerc_synth_rle, ~5.5 GB of RLE incl. mips) at 3840x2160"),
-    "view8k": (0, (512, 512, 512), 16, (7680, 4320), "BASELINE config 5: 7680x4320 views of the tiled scene (N > 1, --mp frames: one camera per GPU, NVLink gather to rank 0)"),
+    "view8k": (0, (512, 512, 512), 16, (7680, 4320), "BASELINE config 5: 7680x4320 views of the tiled scene"),
     "small": (0, (256, 256, 256), 1, (1024, 768), "quick functional run"),
 }
 
@@ -77,8 +87,16 @@ def build_scene(R, workload, log):
     return scene, name, sy
 
 
+def make_config(workload, scene_name, cfg):
+    """What identifies the workload: the SAME dict in both arms (the driver compares them)."""
+    _, _, _, (WW, HH), desc = WORKLOADS[workload]
+    return {"workload": workload, "scene": scene_name, "window": [WW, HH], "render_size": cfg.render_size,
+            "rays_casted": cfg.rays_casted, "z_far": cfg.z_far, "description": desc,
+            "steps_are": "frames of the fly-through; step i of K is path frame i*1000/K, the same K frames for every N and both arms"}
+
+
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md); rank 0 only."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -95,7 +113,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.25)
 
     def summary(self):
         self.stop_flag = True
@@ -111,28 +129,13 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
-KERNEL_NAMES = {0: "k_traverse_f", 65: "k_traverse_f", 64: "k_traverse_w", 66: "k_traverse_c<3>", 67: "k_traverse_c<7>"}
-
-
-def measured_ncu(workload, kernel):
-    """What else the committed ncu capture says about that launch (IPC, hit rates, sectors per request)."""
+def committed_capture(workload, kernel):
+    """The committed `ncu --set full` capture of this workload's traversal launch (profiles/traffic.json), if the
+    kernel it profiled is the kernel this run launched."""
     try:
         e = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(workload)
         if e and e.get("kernel") == kernel:
-            return e.get("ncu")
-    except Exception:
-        pass
-    return None
-
-
-def measured_traffic(workload, kernel):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the traversal kernel, from the committed
-    `ncu --set full` capture (profiles/traffic.json; null when there is none for this workload / kernel)."""
-    try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        e = t.get(workload)
-        if e and e.get("kernel") == kernel:
-            return e["dram_bytes_per_launch"]
+            return e
     except Exception:
         pass
     return None
@@ -144,16 +147,26 @@ def traversal_bytes(c):
     return 8 * C_ + 2 * (E - C1) + 6 * P + 4 * K
 
 
-def cpu_frames(R, rb, scene, cfg, poses, threads):
-    """Reference render_line (oracle/_ref when present, else the port) + the oracle's unwarp. Seconds per frame list."""
+COUNTER_NAMES = ["elems_total", "elems_processed", "voxels_processed", "elems_rendered", "pixels", "cols_fetched",
+                 "run_iters", "cols_nonempty", "cleared", "dda_steps"]
+
+
+def oracle_raymap(rb, rm, levels):
+    orm = rb.RayMapGPU()
+    C.memmove(C.byref(orm), C.byref(rm), 896)
+    rb.attach_host_scene(orm, levels)
+    return orm
+
+
+def cpu_frames(R, rb, scene, cfg, poses, threads, keep=False):
+    """Reference render_line (oracle/_ref when present, else the port) + the oracle's unwarp.
+    Returns [(traversal s, unwarp s[, warp, rgba])] per pose and the kind of baseline."""
     levels = [scene.level(m) for m in range(scene.nummaps)]
     use_ref = rb.have_ref()
     out = []
     for pos, rot in poses:
         rm = R.RayMap(cfg).get_ray_map(pos, rot)
-        orm = rb.RayMapGPU()
-        C.memmove(C.byref(orm), C.byref(rm), 896)
-        rb.attach_host_scene(orm, levels)
+        orm = oracle_raymap(rb, rm, levels)
         t0 = time.perf_counter()
         if use_ref:
             warp, _ = rb.ref_render_frame(orm, cfg.render_size, mip_distance=cfg.mip_distance, z_far=cfg.z_far,
@@ -161,10 +174,64 @@ def cpu_frames(R, rb, scene, cfg, poses, threads):
         else:
             warp, _, _ = rb.orc_render(orm, cfg.render_size, cfg.rays_casted, cfg.mip_distance, cfg.z_far, threads=threads)
         t1 = time.perf_counter()
-        rb.orc_unwarp(orm, cfg.width, cfg.height, cfg.render_size, cfg.rays_casted, cfg.rays_casted_res, warp)
+        rgba = rb.orc_unwarp(orm, cfg.width, cfg.height, cfg.render_size, cfg.rays_casted, cfg.rays_casted_res, warp)
         t2 = time.perf_counter()
-        out.append((t1 - t0, t2 - t1))
+        out.append((t1 - t0, t2 - t1, warp, rgba) if keep else (t1 - t0, t2 - t1))
     return out, ("reference" if use_ref else "port")
+
+
+def pipelined_job(torch, pipe, raymaps, K, repeats, barrier):
+    """R x K frames through `pipe`, device-timed as ONE region.  Returns (total ms, [ms per repeat])."""
+    main = torch.cuda.current_stream()
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e0.record(main)
+    pipe.start_after(e0)
+    marks = []
+    for rep in range(repeats):
+        for i in range(K):
+            k = pipe.submit(rep * K + i, raymaps[i])
+        m = torch.cuda.Event(enable_timing=True)
+        m.record(pipe.streams[k])
+        marks.append(m)
+    pipe.drain(main)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e1.record(main)
+    e1.synchronize()
+    barrier()
+    ends = [e0.elapsed_time(m) for m in marks]
+    per = [b - a for a, b in zip([0.0] + ends[:-1], ends)]
+    return e0.elapsed_time(e1), per
+
+
+def sequential_job(torch, pipe, raymaps, frames, flush, timing_r=None):
+    """Frames one at a time on slot 0, L2 flushed before each, per-frame CUDA events (the round-1 `value` method).
+    Returns ([ms per frame], traversal ms sum, unwarp ms sum)."""
+    s = pipe.streams[0]
+    out, trav, unw = [], 0.0, 0.0
+    for i in frames:
+        with torch.cuda.stream(s):
+            if flush is not None:
+                flush.fill_(i & 255)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(s)
+            pipe.submit(i * pipe.depth, raymaps[i])          # always slot 0
+            if pipe.pending[0] is not None:
+                pipe.pending[0].wait()
+                pipe.pending[0] = None
+            b.record(s)
+        b.synchronize()
+        out.append(a.elapsed_time(b))
+        if timing_r is not None:
+            t, u = timing_r.last_kernel_ms()
+            trav += t
+            unw += u
+    return out, trav, unw
+
+
+def dist_stats(xs):
+    xs = sorted(xs)
+    return {"mean": sum(xs) / len(xs), "p50": xs[len(xs) // 2], "p99": xs[min(len(xs) - 1, int(0.99 * len(xs)))], "max": xs[-1]}
 
 
 def main():
@@ -180,15 +247,18 @@ def main():
     ap.add_argument("--workload", default="imrodh1080p", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="rlerc", choices=["rlerc", "reference"])
     ap.add_argument("--lanes", type=int, default=0,
-                    help="traversal kernel variant (rlerc_set_lanes_per_ray): 0 = k_traverse_f (production), 64 = k_traverse_w, "
-                         "66/67 = k_traverse_c, 1..32 = k_traverse<lanes>")
-    ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
+                    help="traversal kernel (rlerc_set_lanes_per_ray): 0 = automatic (k_traverse_f, or k_traverse_p for small launches), "
+                         "65 = k_traverse_f, 68 = k_traverse_p, 1..32 = k_traverse<lanes>")
+    ap.add_argument("--inflight", type=int, default=4, help="frames in flight per GPU in the throughput measurements")
+    ap.add_argument("--min-seconds", type=float, default=0.6, help="the K-frame job is repeated until the timed region lasts this long")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-north-star", action="store_true", help="N > 1: skip the tiled4k slice-scaling block")
     ap.add_argument("--slice-block", type=int, default=32)
-    ap.add_argument("--mp", default="frames", choices=["frames", "slices"],
-                    help="N > 1: deal whole frames to the GPUs (throughput, default) or split every frame into ray-plane slices (latency, north-star mode)")
+    ap.add_argument("--mp", default="slices", choices=["slices", "frames"],
+                    help="N > 1: split every frame into ray-plane slices (north-star split, default) or deal whole frames to the GPUs")
     args = ap.parse_args()
     K, W = max(1, args.steps), max(3, args.warmup)
+    F = max(1, args.inflight)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -206,6 +276,7 @@ def main():
         if rank != 0:
             return 0
         from oracle import refbind as rb
+        R.lib().rlerc_set_host_threads(os.cpu_count() or 1)
         scene, scene_name, sy = build_scene(R, args.workload, log)
         threads = os.cpu_count() or 1
         poses = [path_pose(R, i, K, sy, scene_name == "Imrodh.rle4") for i in range(K)]
@@ -215,15 +286,15 @@ def main():
         wall = time.perf_counter() - t0
         fps = K / wall
         val = WW * HH * fps / 1e6
+        trav = sum(t[0] for t in times) / K
         line = {"impl": "reference", "metric": "Mrays/s", "value": val, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": K, "warmup": W,
                 "ms_per_step": 1e3 * wall / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic" if scene_name != "Imrodh.rle4" else "Imrodh.rle4",
-                "frames_per_s": fps,
-                "config": {"workload": args.workload, "scene": scene_name, "window": [WW, HH], "render_size": cfg.render_size,
-                           "rays_casted": cfg.rays_casted, "description": desc},
+                "frames_per_s": fps, "config": make_config(args.workload, scene_name, cfg),
                 "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": threads, "kind": kindname,
+                                 "traversal_only_ms_per_frame": 1e3 * trav, "traversal_only_value": WW * HH / trav / 1e6,
                                  "sample": "%d fly-through frames: reference render_line (OpenMP over ray planes, %.1f ms/frame) + oracle unwarp (%.1f ms/frame)"
-                                           % (K, 1e3 * sum(t[0] for t in times) / K, 1e3 * sum(t[1] for t in times) / K)},
+                                           % (K, 1e3 * trav, 1e3 * sum(t[1] for t in times) / K)},
                 "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line), file=json_out, flush=True)
         return 0
@@ -238,123 +309,149 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     MG = importlib.import_module("rle-based-voxel-raycasting_b200.multigpu")
-
-    scene, scene_name, sy = build_scene(R, args.workload, log)
-    r = R.Renderer(local)
-    t0 = time.time()
-    r.all_to_gpu(scene)
-    log("replica uploaded in %.1f s" % (time.time() - t0))
-    r.set_lanes_per_ray(args.lanes)
-    frame = MG.SlicedFrame(r, cfg, torch, rank=rank, world=world, dist=dist if world > 1 else None, block=args.slice_block)
-    poses = [path_pose(R, i, K, sy, scene_name == "Imrodh.rle4") for i in range(K)]
-    raymaps = [R.RayMap(cfg).get_ray_map(p, q) for p, q in poses]
-    flush = None if args.no_flush else torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+    D = dist if world > 1 else None
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    farm = MG.FrameFarm(r, cfg, torch, rank, world, dist) if (world > 1 and args.mp == "frames") else None
-    rounds = (K + world - 1) // world
+    def allmax(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.cpu()[0])
 
-    # ---- warm-up (also initialises NCCL's channels: the first collectives take 100+ ms)
-    for i in range(W):
-        frame.render(raymaps[i % K])
-    if farm is not None:
-        for rd in range(max(W, 4)):
-            farm.render_round(rd, raymaps[(rd * world + rank) % K])
-        farm.finish()
-    barrier()
+    def throughput(pipe, raymaps, K_, min_s):
+        """Warm up, calibrate the repeat count, run the timed job.  Returns dict(value-free numbers)."""
+        for i in range(max(W, 2 * pipe.depth)):
+            pipe.submit(i, raymaps[i % K_])
+        pipe.drain()
+        barrier()
+        t1, _ = pipelined_job(torch, pipe, raymaps, K_, 1, barrier)
+        t1 = allmax(t1)
+        reps = int(max(1, min(200, math.ceil(min_s * 1e3 / max(t1, 1e-3)))))
+        tot, per = pipelined_job(torch, pipe, raymaps, K_, reps, barrier)
+        tot = allmax(tot)
+        med = sorted(per)[len(per) // 2]
+        return {"ms_total": tot, "repeats": reps, "ms_per_frame": tot / (reps * K_), "fps": reps * K_ / (tot / 1e3),
+                "per_repeat_ms": {"median": med, "max": max(per), "max_over_median": max(per) / med if med > 0 else None}}
 
-    # ---- timed region: K steps (frames), device time per step from CUDA events on the launching stream
-    sampler = ClockSampler(local)
-    sampler.start()
-    r.set_timing(True)
-    trav_ms, unwarp_ms = 0.0, 0.0
-    ev = []
+    scene, scene_name, sy = build_scene(R, args.workload, log)
+    imrodh = scene_name == "Imrodh.rle4"
+    scene_megabytes = scene.nbytes() / 1e6
+    t0 = time.time()
+    slices = world > 1 and args.mp == "slices"
+    pipe = MG.FramePipe(R, torch, local, scene, cfg, depth=F, rank=rank if slices else 0, world=world if slices else 1,
+                        dist=D if slices else None, block=args.slice_block, lanes=args.lanes, compose="reduce")
+    log("replica uploaded, %d frame slots: %.1f s" % (F, time.time() - t0))
+    r = pipe.r[0]
+    poses = [path_pose(R, i, K, sy, imrodh) for i in range(K)]
+    raymaps = []
+    for p, q in poses:
+        rm = R.RayMapGPU()
+        C.memmove(C.byref(rm), C.byref(R.RayMap(cfg).get_ray_map(p, q)), 896)
+        raymaps.append(rm)
+
+    # ---- the timed region: R x K frames, F in flight per GPU
+    if slices or world == 1:
+        my_maps, myK = raymaps, K
+    else:                       # --mp frames: whole frames dealt round-robin, each stays on the GPU that rendered it
+        my_maps = raymaps[rank::world]
+        myK = len(my_maps)
+    sampler = ClockSampler(local) if rank == 0 else None
+    # warm-up outside the sampled interval (also initialises NCCL's channels: the first collectives take 100+ ms)
+    for i in range(max(W, 2 * F)):
+        pipe.submit(i, my_maps[i % myK])
+    pipe.drain()
     barrier()
+    if sampler:
+        sampler.start()
     wall0 = time.perf_counter()
-    if farm is None:
-        # 1 GPU, or every frame split into ray-plane slices over all GPUs
-        for i in range(K):
-            if flush is not None:
-                flush.fill_(i & 255)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            frame.render(raymaps[i])
-            e1.record()
-            e1.synchronize()
-            ev.append((e0, e1))
-            a, b_ = r.last_kernel_ms()
-            trav_ms += a
-            unwarp_ms += b_
-    else:
-        # whole frames dealt round-robin; the gather of round rd overlaps the rendering of round rd+1
-        for rd in range(rounds):
-            i = rd * world + rank
-            if flush is not None:
-                flush.fill_(rd & 255)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            farm.render_round(rd, raymaps[i] if i < K else None)
-            e1.record()
-            e1.synchronize()
-            ev.append((e0, e1))
-            if i < K:
-                a, b_ = r.last_kernel_ms()
-                trav_ms += a
-                unwarp_ms += b_
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        farm.finish()
-        e1.record()
-        ev.append((e0, e1))
-    barrier()
+    th = throughput(pipe, my_maps, myK, args.min_seconds)
     wall = time.perf_counter() - wall0
-    clocks = sampler.summary()
-    r.set_timing(False)
-    per_step = sorted(s.elapsed_time(e) for s, e in ev[:K if farm is None else rounds])
-    dev_ms = sum(s.elapsed_time(e) for s, e in ev)
-    # frame-time distribution on this rank (mean / p50 / p99); frames mode: per round
-    frame_ms = {"mean": sum(per_step) / len(per_step), "p50": per_step[len(per_step) // 2],
-                "p99": per_step[min(len(per_step) - 1, int(0.99 * len(per_step)))], "max": per_step[-1],
-                "per": "frame" if farm is None else "round of %d frames" % world} if per_step else None
-    t = torch.tensor([dev_ms, trav_ms, unwarp_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, trav_ms_max, unwarp_ms_max = (float(v) for v in t.cpu())
-    fps = K / (dev_ms / 1e3)
+    clocks = sampler.summary() if sampler else None
+    frames_done = th["repeats"] * K
+    if not (slices or world == 1):
+        # every rank did repeats * len(my_maps) frames in ms_total; the job is all ranks' frames
+        t = torch.tensor([th["repeats"] * myK], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t)
+        frames_done = int(t.cpu()[0])
+    fps = frames_done / (th["ms_total"] / 1e3)
     value = WW * HH * fps / 1e6
-    launches_per_rank = (K if farm is None else len(range(rank, K, world)))
-    kernels_timed = launches_per_rank               # traversal launches behind trav_ms on the slowest rank
+    launches = 3 * th["repeats"] * myK                 # k_dda_states + traversal + k_unwarp per frame on this rank
 
-    # ---- warm-L2 variant (no flush), for information
-    warm_ms = None
-    if farm is None:
+    # ---- latency: one frame at a time, L2 flushed before each (the round-1 `value` method)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+    r.set_timing(True)
+    KL = min(K, 200)
+    seq_frames = [int(j * K / KL) for j in range(KL)]
+    lat = trav_ms = unw_ms = None
+    if slices or world == 1:
         barrier()
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0.record()
-        for i in range(K):
-            frame.render(raymaps[i])
-        s1.record()
+        per, trav_ms, unw_ms = sequential_job(torch, pipe, raymaps, seq_frames, flush, r)
         barrier()
-        warm_ms = s0.elapsed_time(s1)
+        tot = allmax(sum(per))
+        lat = dict(dist_stats(per), frames=KL, value=WW * HH * KL / (tot / 1e3) / 1e6, frames_per_s=KL / (tot / 1e3),
+                   how="one frame at a time, 512 MiB L2 flush before each, CUDA events around each frame (%s), this rank; value from the max over ranks of the summed frame times"
+                       % ("traversal slice + unwarp + NCCL reduce" if slices else "k_dda_states + traversal + unwarp"))
+        trav_ms, unw_ms = allmax(trav_ms), allmax(unw_ms)
+    r.set_timing(False)
+    kernel_used = r.last_kernel
+    del flush
 
-    # ---- roofline of the traversal kernel: algorithmic bytes from the instrumented kernel (N=1 semantics)
-    roof = None
-    cpu = None
-    e2e = None
+    # ---- multi-GPU frame == single-GPU frame (rank 0 renders the whole frame itself and compares)
+    composite_identical = None
+    if slices:
+        checks = [0, K // 2]
+        ok = True
+        for i in checks:
+            pipe.submit(0, raymaps[i])
+            pipe.drain()
+            barrier()
+            if rank == 0:
+                got = pipe.image(0).clone()
+                solo = torch.zeros_like(got)
+                r.frame_device(raymaps[i], cfg, 1, 1, 0, solo.data_ptr())
+                torch.cuda.synchronize()
+                ok = ok and bool(torch.equal(got, solo))
+            barrier()
+        composite_identical = ok if rank == 0 else None
+
+    # ---- parity of THIS workload against the reference compiled for the host (outside every timed region)
+    parity = None
     if rank == 0:
+        try:
+            from oracle import refbind as rb
+            nchk = 5 if WW * HH <= 1920 * 1080 else 2
+            idx = sorted(set(int(j * K / nchk) for j in range(nchk)))
+            ref, kindname = cpu_frames(R, rb, scene, cfg, [poses[j] for j in idx], os.cpu_count() or 1, keep=True)
+            warp_same, rgba_max, ident = True, 0, 1.0
+            solo = torch.zeros((HH, WW, 4), dtype=torch.uint8, device="cuda")
+            for j, (_, _, owarp, orgba) in zip(idx, ref):
+                r.frame_device(raymaps[j], cfg, 1, 1, 0, solo.data_ptr())
+                torch.cuda.synchronize()
+                n = raymaps[j].map_line_count
+                warp_same = warp_same and bool(np.array_equal(r.read_warp(cfg)[:n], owarp[:n]))
+                d = np.abs(solo.cpu().numpy().astype(np.int16) - orgba.astype(np.int16))
+                rgba_max = max(rgba_max, int(d.max()))
+                ident = min(ident, float((d.reshape(-1, 4).max(axis=1) == 0).mean()))
+            parity = {"frames_checked": len(idx), "frames": idx, "against": "oracle/_ref (reference render_line compiled for the host)" if kindname == "reference" else "oracle port",
+                      "warp_identical": warp_same, "rgba_max_diff": rgba_max, "rgba_identical_fraction": ident}
+            del solo
+        except Exception as e:                                   # the checker must not take the measurement down
+            parity = {"error": repr(e)[:200]}
+
+    # ---- roofline of the traversal kernel: algorithmic bytes from the instrumented kernel (whole-frame semantics)
+    roof = None
+    if rank == 0 and trav_ms is not None:
         sample_idx = [int(j * K / 8) for j in range(8)] if K >= 8 else list(range(K))
         ids = torch.empty((cfg.rays_casted, cfg.render_size, 2), dtype=torch.int32, device="cuda")
-        tot_bytes, tot_rays = 0, 0
-        agg = {}
+        tot_bytes, tot_rays, agg = 0, 0, {}
         for j in sample_idx:
             r.render_ids(raymaps[j], cfg, ids.data_ptr())
             r.sync()
-            c = dict(zip(["elems_total", "elems_processed", "voxels_processed", "elems_rendered", "pixels", "cols_fetched",
-                          "run_iters", "cols_nonempty", "cleared", "dda_steps"], r.counters()))
+            c = dict(zip(COUNTER_NAMES, r.counters()))
             tot_bytes += traversal_bytes(c)
             tot_rays += raymaps[j].map_line_count
             for k_, v in c.items():
@@ -367,104 +464,207 @@ def main():
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        # per-rank launches traverse 1/world of the ray planes
-        sliced = world > 1 and farm is None
-        per_launch_bytes = bytes_per_frame / (world if sliced else 1)
-        achieved = per_launch_bytes / (trav_ms_max / max(kernels_timed, 1) / 1e3) / 1e9
+        per_launch_bytes = bytes_per_frame / (world if slices else 1)       # a rank's launch traverses 1/world of the ray planes
+        t_launch = trav_ms / KL
+        achieved = per_launch_bytes / (t_launch / 1e3) / 1e9
+        cap = committed_capture(args.workload, kernel_used) if world == 1 else None
+        l2peak = None
+        try:
+            l2peak = json.load(open(os.path.join(ROOT, "profiles", "l2_peak.json")))
+        except Exception:
+            pass
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": measured_traffic(args.workload, KERNEL_NAMES.get(args.lanes, "k_traverse<%d>" % args.lanes)),
-                "kernel": KERNEL_NAMES.get(args.lanes, "k_traverse<%d>" % args.lanes),
-                "ncu": measured_ncu(args.workload, KERNEL_NAMES.get(args.lanes, "k_traverse<%d>" % args.lanes)),
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
+                "traffic": cap["dram_bytes_per_launch"] if cap else None,
+                "kernel": kernel_used + " (+ k_dda_states, overlapped by programmatic dependent launch; both inside the timed interval)",
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured, burst: the kernel is timed alone in the latency pass)" if peaks else "fallback 6650 GB/s",
                 "algorithmic_bytes_per_launch": per_launch_bytes,
-                "traverse_ms_per_launch": trav_ms_max / max(kernels_timed, 1), "unwarp_ms_per_launch": unwarp_ms_max / max(kernels_timed, 1),
-                "unwarp_achieved_gbs": 8.0 * WW * HH / (max(unwarp_ms_max, 1e-9) / max(kernels_timed, 1) / 1e3) / 1e9,
+                "traverse_ms_per_launch": t_launch, "unwarp_ms_per_launch": unw_ms / KL,
+                "unwarp_achieved_gbs": 8.0 * WW * HH / (max(unw_ms, 1e-9) / KL / 1e3) / 1e9,
                 "counters_per_frame": {k_: v / len(sample_idx) for k_, v in agg.items()},
                 "plane_rays_per_frame": tot_rays / len(sample_idx)}
+        if cap:
+            roof["ncu"] = cap.get("ncu")
+            if cap.get("l2_bytes_per_launch") and l2peak:
+                a = cap["l2_bytes_per_launch"] / (cap["ncu_duration_ms"] / 1e3) / 1e9
+                roof["l2"] = {"achieved": a, "peak": l2peak["l2_read_gbs"], "unit": "GB/s", "frac": a / l2peak["l2_read_gbs"],
+                              "traffic": cap["l2_bytes_per_launch"],
+                              "how": "lts__t_sectors x 32 B of the committed ncu capture / its gpu__time_duration; peak = tools/l2_peak.py on this pool's B200 (profiles/l2_peak.json)"}
+            if cap.get("reference_kernel_on_this_gpu"):
+                roof["reference_kernel_on_this_gpu"] = cap["reference_kernel_on_this_gpu"]
 
-    # ---- same-GPU comparator: the reference's own scheme (one THREAD per ray plane, k_traverse<1>) on a few frames
-    if rank == 0 and world == 1 and roof is not None and args.lanes == 0:
-        r.set_lanes_per_ray(1)
-        r.set_timing(True)
-        ms = []
-        for j in ([int(j * K / 3) for j in range(3)] if K >= 3 else list(range(K))):
-            r.render(raymaps[j], cfg)
-            r.sync()
-            ms.append(r.last_kernel_ms()[0])
-        r.set_timing(False)
-        r.set_lanes_per_ray(args.lanes)
-        roof["reference_scheme_on_this_gpu"] = {"kernel": "k_traverse<1>: one thread per ray plane, as cudaRender (R/src/Cuda_Main.cu:150-181)",
-                                                "traverse_ms_per_launch": sum(ms) / len(ms), "frames": len(ms)}
-
-    # ---- e2e through the C ABI with host buffers (pinned), D2H inside the timed region
+    # ---- e2e through the C ABI with host buffers (pinned), copies inside the timed region
     barrier()
-    e2e_wall = None
+    e2e = None
+    sync_latency_ms = None
     if world == 1:
         r2 = R.Renderer(local)
-        r2.all_to_gpu(scene)
+        r2.share_scene(r)
         r2.set_lanes_per_ray(args.lanes)
-        DEPTH = int(os.environ.get("RLERC_E2E_DEPTH", "4"))          # frames in flight (rlerc_frame_submit pipelines up to RLERC_FRAME_SLOTS)
-        pins = [R.PinnedBuffer((HH, WW, 4)) for _ in range(DEPTH)]
+        pins = [R.PinnedBuffer((HH, WW, 4)) for _ in range(F)]
         for i in range(max(W, 8)):      # every frame slot (stream, warped buffer, RGBA buffer) exists before the timed region
-            r2.frame_wait(r2.frame_submit(poses[i % K][0], poses[i % K][1], cfg, pins[i % DEPTH].array))
+            r2.frame_wait(r2.frame_submit(poses[i % K][0], poses[i % K][1], cfg, pins[i % F].array))
         r2.sync()
+        reps = th["repeats"]
         t0 = time.perf_counter()
         tickets = []
-        for i in range(K):
-            if len(tickets) >= DEPTH:
-                r2.frame_wait(tickets.pop(0))
-            tickets.append(r2.frame_submit(poses[i][0], poses[i][1], cfg, pins[i % DEPTH].array))
+        for rep in range(reps):
+            for i in range(K):
+                if len(tickets) >= F:
+                    r2.frame_wait(tickets.pop(0))
+                tickets.append(r2.frame_submit(poses[i][0], poses[i][1], cfg, pins[i % F].array))
         for tk in tickets:
             r2.frame_wait(tk)
         r2.sync()
         e2e_wall = time.perf_counter() - t0
-        checksum = int(pins[(K - 1) % DEPTH].array[::16, ::16].astype(np.uint32).sum())
+        e2e_frames = reps * K
+        checksum = int(pins[(K - 1) % F].array[::16, ::16].astype(np.uint32).sum())
+        # synchronous single frames through rlerc_render_frame (pose in, pixels in host memory when the call returns)
+        ts = []
+        for i in seq_frames[:50]:
+            t1 = time.perf_counter()
+            r2.render_frame(poses[i][0], poses[i][1], cfg, pins[0].array)
+            ts.append(1e3 * (time.perf_counter() - t1))
+        sync_latency_ms = dist_stats(ts)
         for p in pins:
             p.free()
         r2.close()
-    elif farm is None:
-        host = torch.empty((HH, WW, 4), dtype=torch.uint8).pin_memory() if rank == 0 else None
-        barrier()
-        t0 = time.perf_counter()
-        for i in range(K):
-            rm = R.RayMap(cfg).get_ray_map(poses[i][0], poses[i][1])
-            img = frame.render(rm)
-            if rank == 0:
-                host.copy_(img, non_blocking=True)
-        barrier()
-        e2e_wall = time.perf_counter() - t0
-        checksum = int(host[::16, ::16].to(torch.int64).sum()) if rank == 0 else 0
+        how = "pinned host RGBA out, camera pose in; rlerc_frame_submit/wait, %d frames in flight, one stream per frame slot" % F
     else:
-        hosts = [torch.empty((HH, WW, 4), dtype=torch.uint8).pin_memory() for _ in range(world)] if rank == 0 else None
+        # ONE host frame ring shared by all ranks; every rank copies its own part of every frame into it over its own PCIe link
+        rows = MG.band_rows(HH, world) if slices else HH
+        shape = (F if slices else F * world, rows * world if slices else HH, WW, 4)
+        nbytes = int(np.prod(shape))
+        name = [None]
+        if rank == 0:
+            name[0] = "/dev/shm/rlerc_bench_%d_%d" % (os.getpid(), int(time.time()))
+        dist.broadcast_object_list(name, src=0)
+        host = torch.from_file(name[0], shared=True, size=nbytes, dtype=torch.uint8).view(shape)
         barrier()
+        rc = torch.cuda.cudart().cudaHostRegister(host.data_ptr(), nbytes, 0)
+        if int(rc) != 0:
+            log("cudaHostRegister failed (%s): the copies into the shared host frame will be synchronous" % rc)
+        pipe2 = MG.FramePipe(R, torch, local, scene, cfg, depth=F, rank=rank if slices else 0, world=world if slices else 1,
+                             dist=D if slices else None, block=args.slice_block, lanes=args.lanes, compose="bands" if slices else "none",
+                             host=host if slices else host[rank * F:(rank + 1) * F], share_from=r)
+        maps2 = raymaps if slices else raymaps[rank::world]
+        # host-side frame setup (get_ray_map) is inside the timed region, as in the single-GPU e2e
+        for i in range(max(W, 2 * F)):
+            pipe2.submit(i, maps2[i % len(maps2)])
+        pipe2.drain()
+        barrier()
+        reps = th["repeats"]
+        my_poses = poses if slices else poses[rank::world]
         t0 = time.perf_counter()
-        for rd in range(rounds + 1):
-            if rd < rounds:
-                i = rd * world + rank
-                rm = R.RayMap(cfg).get_ray_map(poses[i][0], poses[i][1]) if i < K else None
-                farm.render_round(rd, rm)
-            if rd > 0 and rank == 0:
-                done = farm.wait_round(rd - 1)          # frames of the previous round are on rank 0: D2H them
-                for j in range(world):
-                    if (rd - 1) * world + j < K:
-                        hosts[j].copy_(done[j], non_blocking=True)
-        farm.finish()
+        n = 0
+        for rep in range(reps):
+            for i in range(len(my_poses)):
+                rm = R.RayMap(cfg).get_ray_map(my_poses[i][0], my_poses[i][1])
+                pipe2.submit(n, rm)
+                n += 1
+        pipe2.drain()
         barrier()
-        e2e_wall = time.perf_counter() - t0
-        checksum = int(hosts[(K - 1) % world][::16, ::16].to(torch.int64).sum()) if rank == 0 else 0
-    tt = torch.tensor([e2e_wall], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    e2e_wall = float(tt.cpu()[0])
-    e2e_fps = K / e2e_wall
+        e2e_wall = allmax(time.perf_counter() - t0)
+        e2e_frames = reps * K
+        # the last frame of the job, as it landed in host memory, against rank 0's own single-GPU frame
+        checksum = 0
+        if slices:
+            last = (n - 1) % F
+            if rank == 0:
+                solo = torch.zeros((HH, WW, 4), dtype=torch.uint8, device="cuda")
+                r.frame_device(raymaps[K - 1], cfg, 1, 1, 0, solo.data_ptr())
+                torch.cuda.synchronize()
+                same = bool(torch.equal(host[last, :HH], solo.cpu()))
+                composite_identical = bool(composite_identical) and same
+                checksum = int(host[last, :HH][::16, ::16].to(torch.int64).sum())
+        barrier()
+        pipe2.close()
+        torch.cuda.cudart().cudaHostUnregister(host.data_ptr())
+        del host
+        barrier()
+        if rank == 0:
+            try:
+                os.unlink(name[0])
+            except OSError:
+                pass
+        how = ("per-rank ray-plane slices, NCCL reduce_scatter into row bands, every rank copies its band into ONE host frame shared by all ranks (%d PCIe links), %d frames in flight"
+               % (world, F)) if slices else ("whole frames per rank, every rank copies its frames into the shared host ring itself, %d frames in flight" % F)
+    e2e_fps = e2e_frames / e2e_wall
     e2e = {"value": WW * HH * e2e_fps / 1e6, "unit": "Mrays/s", "frames_per_s": e2e_fps,
-           "h2d_bytes_per_step": 1024 * world, "d2h_bytes_per_step": WW * HH * 4,
-           "how": "pinned host RGBA out, camera pose in; %s" % ("rlerc_frame_submit/wait, %s frames in flight, one stream per frame slot" % os.environ.get("RLERC_E2E_DEPTH", "4") if world == 1
-                                                                 else ("per-rank slices + NCCL reduce + D2H on rank 0" if farm is None
-                                                                       else "whole frames per rank + NCCL gather + D2H of every frame on rank 0")),
-           "checksum": checksum}
+           "h2d_bytes_per_step": 1024 * world, "d2h_bytes_per_step": WW * HH * 4, "how": how, "checksum": checksum,
+           "frames": e2e_frames, "wall_s": e2e_wall}
+    if sync_latency_ms:
+        e2e["synchronous_single_frame_ms"] = dict(sync_latency_ms, how="rlerc_render_frame: pose in, RGBA in pinned host memory when the call returns; wall clock per call, 50 frames")
+
+    # ---- north star: column slices of the 4K tiled scene, N ranks against rank 0 alone, same frames, same run
+    north = None
+    if slices and not args.no_north_star and args.workload != "tiled4k":
+        try:
+            pipe.close()
+            del scene
+            scene4, name4, sy4 = build_scene(R, "tiled4k", log)
+            W4, H4 = WORKLOADS["tiled4k"][3]
+            cfg4 = R.FrameConfig.default(W4, H4)
+            K4 = 24
+            maps4 = []
+            for i in range(K4):
+                p, q = path_pose(R, i, K4, sy4, False)
+                rm = R.RayMapGPU()
+                C.memmove(C.byref(rm), C.byref(R.RayMap(cfg4).get_ray_map(p, q)), 896)
+                maps4.append(rm)
+            pn = MG.FramePipe(R, torch, local, scene4, cfg4, depth=F, rank=rank, world=world, dist=D, block=args.slice_block,
+                              lanes=args.lanes, compose="reduce")
+            tn = throughput(pn, maps4, K4, 0.4)
+            flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+            barrier()
+            per, _, _ = sequential_job(torch, pn, maps4, list(range(K4)), flush)
+            barrier()
+            seq_n = allmax(sum(per)) / K4
+            ident = None
+            pn.submit(0, maps4[0])
+            pn.drain()
+            barrier()
+            if rank == 0:
+                got = pn.image(0).clone()
+                solo = torch.zeros_like(got)
+                pn.r[0].frame_device(maps4[0], cfg4, 1, 1, 0, solo.data_ptr())
+                torch.cuda.synchronize()
+                ident = bool(torch.equal(got, solo))
+                del got, solo
+            barrier()
+            # rank 0 alone on the same frames (the other ranks wait at the barrier)
+            t1 = None
+            seq_1 = None
+            if rank == 0:
+                p1 = MG.FramePipe(R, torch, local, scene4, cfg4, depth=F, rank=0, world=1, dist=None, lanes=args.lanes,
+                                  compose="none", share_from=pn.r[0])
+                nb = (lambda: torch.cuda.synchronize())
+                for i in range(2 * F):
+                    p1.submit(i, maps4[i % K4])
+                p1.drain()
+                nb()
+                a, _ = pipelined_job(torch, p1, maps4, K4, 1, nb)
+                reps1 = int(max(1, math.ceil(400.0 / max(a, 1e-3))))
+                tot1, _ = pipelined_job(torch, p1, maps4, K4, reps1, nb)
+                t1 = tot1 / (reps1 * K4)
+                per1, _, _ = sequential_job(torch, p1, maps4, list(range(K4)), flush)
+                seq_1 = sum(per1) / K4
+                p1.close()
+            barrier()
+            del flush
+            if rank == 0:
+                north = {"workload": "tiled4k", "scene": name4, "scene_mb": scene4.nbytes() / 1e6, "window": [W4, H4], "frames": K4,
+                         "split": "interleaved blocks of %d ray planes over %d GPUs, full replica each, NCCL reduce to rank 0" % (args.slice_block, world),
+                         "throughput": {"frames_in_flight": F, "ms_per_frame_n": tn["ms_per_frame"], "ms_per_frame_1": t1,
+                                        "fps_n": 1e3 / tn["ms_per_frame"], "fps_1": 1e3 / t1, "speedup": t1 / tn["ms_per_frame"]},
+                         "latency": {"ms_per_frame_n": seq_n, "ms_per_frame_1": seq_1, "speedup": seq_1 / seq_n,
+                                     "how": "one frame at a time, L2 flushed before each"},
+                         "composite_identical": ident}
+            pn.close()
+        except Exception as e:
+            north = {"error": repr(e)[:300]}
 
     # ---- CPU baseline on the box's host cores (rank 0, N=1 only), bounded sample
+    cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         from oracle import refbind as rb
         threads = os.cpu_count() or 1
@@ -474,33 +674,41 @@ def main():
         tms, kindname = cpu_frames(R, rb, scene, cfg, sample, threads)
         one, _ = cpu_frames(R, rb, scene, cfg, sample[:2], 1)
         per = sum(a + b for a, b in tms) / len(tms)
+        trav = sum(a for a, _ in tms) / len(tms)
         per1 = sum(a + b for a, b in one) / len(one)
         pern = sum(a + b for a, b in tms[:2]) / 2
         cpu = {"value": WW * HH / per / 1e6, "unit": "Mrays/s", "cores": threads, "kind": kindname,
-               "frames_per_s": 1.0 / per,
+               "frames_per_s": 1.0 / per, "traversal_only_ms_per_frame": 1e3 * trav, "traversal_only_value": WW * HH / trav / 1e6,
                "sample": "%d of the %d fly-through frames: reference render_line compiled for the host (OpenMP, %d threads, %.1f ms/frame) "
                          "+ oracle unwarp (%.1f ms/frame); 1 thread: %.1f ms/frame -> 1->%d thread speed-up %.1fx"
-                         % (len(tms), K, threads, 1e3 * sum(a for a, _ in tms) / len(tms), 1e3 * sum(b for _, b in tms) / len(tms),
-                            1e3 * per1, threads, per1 / pern)}
+                         % (len(tms), K, threads, 1e3 * trav, 1e3 * sum(b for _, b in tms) / len(tms), 1e3 * per1, threads, per1 / pern)}
 
     if rank == 0:
         line = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": K, "warmup": W,
-                "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic" if scene_name != "Imrodh.rle4" else "Imrodh.rle4",
-                "frames_per_s": fps,
-                "config": {"workload": args.workload, "scene": scene_name, "scene_mb": scene.nbytes() / 1e6, "window": [WW, HH],
-                           "steps_are": "frames of the fly-through; the K frames of the job are the same for every N",
-                           "render_size": cfg.render_size, "rays_casted": cfg.rays_casted, "z_far": cfg.z_far,
-                           "description": desc, "l2": "flushed between timed steps (512 MiB write)" if flush is not None else "not flushed",
-                           "warm_l2_value": (WW * HH * (K / (warm_ms / 1e3)) / 1e6) if warm_ms else None, "lanes": args.lanes,
-                           "parallelism": ("1 GPU" if world == 1 else
-                                           ("whole frames dealt round-robin to %d GPUs (full replica each), NCCL gather of finished frames to rank 0, overlapped" % world
-                                            if farm is not None else
-                                            "every frame split into ray-plane slices x%d, interleaved blocks of %d, NCCL reduce to rank 0" % (world, args.slice_block))),
-                           "wall_s_timed_region": wall},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": 2 * K, "frame_ms": frame_ms, "roofline": roof}
+                "ms_per_step": th["ms_per_frame"] if (slices or world == 1) else th["ms_total"] / frames_done,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic" if not imrodh else "Imrodh.rle4",
+                "frames_per_s": fps, "config": make_config(args.workload, scene_name, cfg),
+                "run": {"scene_mb": scene_megabytes, "frames_in_flight": F, "repeats": th["repeats"], "frames_timed": frames_done, "timed_region_ms": th["ms_total"],
+                        "per_repeat_ms": th["per_repeat_ms"], "wall_s_timed_region": wall, "lanes": args.lanes, "kernel": kernel_used,
+                        "l2": "not flushed inside the pipelined job: a frame touches the scene (%.0f MB) + its own warped buffer (%.0f MB) + DDA states, "
+                              "%d such frames are in flight against a 126 MB L2; the flushed, one-frame-at-a-time figure is `latency`"
+                              % (scene_megabytes, cfg.rays_casted * cfg.render_size * 4 / 1e6, F),
+                        "parallelism": ("1 GPU" if world == 1 else
+                                        ("every frame split into ray-plane slices x%d (interleaved blocks of %d), full replica per GPU, one NCCL reduce per frame to rank 0"
+                                         % (world, args.slice_block) if slices else
+                                         "whole frames dealt round-robin to %d GPUs (full replica each); frames stay on the GPU that rendered them" % world))},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "latency": lat, "roofline": roof, "parity": parity}
+        if composite_identical is not None:
+            line["composite_identical"] = composite_identical
+        if north is not None:
+            line["north_star"] = north
         if cpu:
             line["cpu_baseline"] = cpu
+            line["vs_cpu"] = {"e2e_over_cpu": e2e["value"] / cpu["value"],
+                              "traversal_only": {"cpu_ms": cpu["traversal_only_ms_per_frame"], "gpu_ms": roof["traverse_ms_per_launch"] if roof else None,
+                                                 "ratio": cpu["traversal_only_ms_per_frame"] / roof["traverse_ms_per_launch"] if roof else None,
+                                                 "note": "reference render_line on the host vs k_dda_states + traversal kernel, one frame at a time: no builder-authored unwarp on either side"}}
         print(json.dumps(line), file=json_out, flush=True)
     barrier()
     if dist.is_initialized():

@@ -134,6 +134,9 @@ int  rlerc_create(int device, rlerc_ctx** out);
 void rlerc_destroy(rlerc_ctx* c);
 /* RLE4::all_to_gpu / copy_to_gpu (Rle4.cpp:432-448): full replica of every level in HBM. */
 int  rlerc_scene_upload(rlerc_ctx* c, const rlerc_scene* s);
+/* Borrow the replica another context of the SAME device holds (no copy; `src` has to outlive every use of `dst`).
+ * Several contexts = several frames in flight on one GPU (each context has its own stream and frame buffers). */
+int  rlerc_scene_share(rlerc_ctx* dst, const rlerc_ctx* src);
 /* Device-side Map4 table as main.cpp:277-278 copies it into the ray map (all levels). */
 int  rlerc_scene_device_maps(rlerc_ctx* c, rlerc_map4* out16, int* nummaps);
 /* Traversal kernel variant, all bit-identical: 0 = automatic (default): the production kernel k_traverse_f (one warp
@@ -205,6 +208,11 @@ int  rlerc_render_interleaved(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_
                               int block, int nranks, int rank, uint32_t* d_warp);
 int  rlerc_unwarp_interleaved(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_config* cfg,
                               int block, int nranks, int rank, const uint32_t* d_warp, uint8_t* d_rgba);
+
+/* rlerc_render_interleaved + rlerc_unwarp_interleaved on the context's own warped buffer in one call (nranks == 1: the
+ * whole frame); RGBA8 into d_rgba (DEVICE memory, NULL: the context's buffer).  Asynchronous on the context stream. */
+int  rlerc_frame_device(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_config* cfg,
+                        int block, int nranks, int rank, uint8_t* d_rgba);
 
 /* ---- whole frame with HOST buffers (what render_to_pbo + display_pbo pass 1 do) ----- */
 

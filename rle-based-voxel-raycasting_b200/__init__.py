@@ -93,6 +93,8 @@ _SIGS = {
     "rlerc_destroy": (None, [_P]),
     "rlerc_scene_upload": (C.c_int, [_P, _P]),
     "rlerc_scene_device_maps": (C.c_int, [_P, _P, C.POINTER(C.c_int)]),
+    "rlerc_scene_share": (C.c_int, [_P, _P]),
+    "rlerc_frame_device": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "rlerc_set_lanes_per_ray": (C.c_int, [_P, C.c_int]),
     "rlerc_has_variants": (C.c_int, []),
     "rlerc_last_kernel": (C.c_char_p, [_P]),
@@ -309,6 +311,15 @@ class Renderer:
     # RLE4::all_to_gpu (R/src/Rle4.cpp:432-448)
     def all_to_gpu(self, scene):
         _check(lib().rlerc_scene_upload(self._c, scene._h))
+
+    def share_scene(self, other):
+        """Use the replica `other` (a Renderer on the same device) uploaded; `other` has to stay alive."""
+        _check(lib().rlerc_scene_share(self._c, other._c))
+        self._scene_owner = other
+
+    def frame_device(self, raymap_gpu, cfg, block=1, nranks=1, rank=0, d_rgba=None):
+        """Traversal + unwarp of this rank's interleaved slice (the whole frame for nranks == 1), asynchronous."""
+        _check(lib().rlerc_frame_device(self._c, C.byref(raymap_gpu), C.byref(cfg), block, nranks, rank, d_rgba))
 
     def device_maps(self):
         arr = (Map4 * MAX_MAPS)()

@@ -49,7 +49,7 @@ struct rlerc_ctx {
 	LevelDev level[RLERC_MAX_MAPS];
 	int level_sy[RLERC_MAX_MAPS];
 	uint64_t level_slabs[RLERC_MAX_MAPS];
-	std::vector<void*> scene_allocs;
+	std::vector<void*> scene_allocs;    // empty when the replica is borrowed (rlerc_scene_share)
 	// frame resources
 	uint32_t* d_warp = nullptr;
 	size_t warp_bytes = 0;
@@ -339,6 +339,24 @@ int rlerc_scene_upload(rlerc_ctx* c, const rlerc_scene* s)
 	return RLERC_OK;
 }
 
+int rlerc_scene_share(rlerc_ctx* dst, const rlerc_ctx* src)
+{
+	if (!dst || !src || dst == src) { set_error("rlerc_scene_share: bad argument"); return RLERC_ERR_ARG; }
+	if (dst->device != src->device) { set_error("rlerc_scene_share: contexts are on different devices (%d, %d)", dst->device, src->device); return RLERC_ERR_ARG; }
+	if (src->nummaps < 1) { set_error("rlerc_scene_share: the source context has no scene"); return RLERC_ERR_STATE; }
+	int rc = set_dev(dst);
+	if (rc) return rc;
+	free_scene(dst);
+	for (int m = 0; m < src->nummaps; m++)
+	{
+		dst->level[m] = src->level[m];
+		dst->level_sy[m] = src->level_sy[m];
+		dst->level_slabs[m] = src->level_slabs[m];
+	}
+	dst->nummaps = src->nummaps;
+	return RLERC_OK;
+}
+
 int rlerc_scene_device_maps(rlerc_ctx* c, rlerc_map4* out16, int* nummaps)
 {
 	if (!c || !out16) { set_error("rlerc_scene_device_maps: bad argument"); return RLERC_ERR_ARG; }
@@ -536,6 +554,29 @@ int rlerc_debug_lod_sched(int mapswitch0, int z_far, float mountain, int* out)
 	return RLERC_OK;
 }
 
+/* undocumented (tools/l2_peak.py): read bandwidth in GB/s of `iters` passes over a zero-filled buffer of `mbytes` MB
+ * (<= 64 MB: L2-resident after the warm-up pass; >= 1024 MB: HBM) */
+int rlerc_debug_read_gbs(rlerc_ctx* c, int mbytes, int iters, double* gbs)
+{
+	if (!c || !gbs || mbytes < 1 || iters < 1) return RLERC_ERR_ARG;
+	int rc = set_dev(c);
+	if (rc) return rc;
+	const size_t bytes = (size_t)mbytes << 20;
+	void* buf = nullptr;
+	CK(cudaMalloc(&buf, bytes));
+	CK(cudaMemsetAsync(buf, 0, bytes, c->stream));
+	launch_read_u4(buf, bytes, 2, (uint32_t*)c->d_counters, c->stream);       // warm-up: brings the buffer into L2
+	CK(cudaEventRecord(c->ev[0], c->stream));
+	launch_read_u4(buf, bytes, iters, (uint32_t*)c->d_counters, c->stream);
+	CK(cudaEventRecord(c->ev[1], c->stream));
+	CK(cudaEventSynchronize(c->ev[1]));
+	float ms = 0;
+	CK(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
+	cudaFree(buf);
+	*gbs = (double)bytes * iters / (ms * 1e-3) / 1e9;
+	return RLERC_OK;
+}
+
 /* undocumented: raw copy of all 32 debug counter slots (tools/ only) */
 int rlerc_debug_counters(rlerc_ctx* c, uint64_t out[32])
 {
@@ -609,6 +650,14 @@ int rlerc_unwarp_interleaved(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_f
 	int rc = check_slice(block, nranks, rank);
 	if (rc) return rc;
 	return unwarp_impl(c, rm, cfg, d_warp, d_rgba, 0, -1, 0, -1, block, nranks, rank);
+}
+
+int rlerc_frame_device(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_config* cfg, int block, int nranks, int rank, uint8_t* d_rgba)
+{
+	int rc = check_slice(block, nranks, rank);
+	if (rc) return rc;
+	if ((rc = render_impl(c, rm, cfg, 0, -1, nullptr, nullptr, false, block, nranks, rank))) return rc;
+	return unwarp_impl(c, rm, cfg, nullptr, d_rgba, 0, -1, 0, -1, block, nranks, rank);
 }
 
 int rlerc_set_stream(rlerc_ctx* c, void* cuda_stream)

@@ -630,4 +630,28 @@ void launch_fill_u32(uint32_t* p, uint32_t v, size_t n, cudaStream_t st)
 	k_fill_u32<<<148 * 8, 256, 0, st>>>(p, v, n);
 }
 
+// Measurement only (tools/l2_peak.py): `iters` passes of 128-bit loads over a buffer; with the buffer L2-resident this is the
+// L2 -> SM read bandwidth the roofline block quotes, with a buffer far larger than L2 it is the HBM read bandwidth.
+__global__ void __launch_bounds__(512) k_read_u4(const uint4* __restrict__ p, size_t n, int iters, uint32_t* sink)
+{
+	uint32_t acc = 0;
+	const size_t stride = (size_t)gridDim.x * blockDim.x;
+	for (int it = 0; it < iters; it++)
+	{
+		size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+		for (; i + 3 * stride < n; i += 4 * stride)
+		{
+			const uint4 a = __ldcg(p + i), b = __ldcg(p + i + stride), c = __ldcg(p + i + 2 * stride), d = __ldcg(p + i + 3 * stride);
+			acc ^= a.x ^ a.y ^ a.z ^ a.w ^ b.x ^ b.y ^ b.z ^ b.w ^ c.x ^ c.y ^ c.z ^ c.w ^ d.x ^ d.y ^ d.z ^ d.w;
+		}
+		for (; i < n; i += stride) { const uint4 a = __ldcg(p + i); acc ^= a.x ^ a.y ^ a.z ^ a.w; }
+	}
+	if (acc == 0x9e3779b9u) *sink = acc;              // never true for the zero-filled buffer; keeps the loads alive
+}
+
+void launch_read_u4(const void* p, size_t bytes, int iters, uint32_t* sink, cudaStream_t st)
+{
+	k_read_u4<<<148 * 4, 512, 0, st>>>((const uint4*)p, bytes / 16, iters, sink);
+}
+
 } // namespace rlerc

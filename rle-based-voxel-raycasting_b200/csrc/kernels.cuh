@@ -98,5 +98,6 @@ void launch_traverse_chunk(const TraverseParams& p, bool ids, int wpb, cudaStrea
 size_t traverse_ring_bytes(int rays);
 void launch_unwarp(const UnwarpParams& p, cudaStream_t st);
 void launch_fill_u32(uint32_t* p, uint32_t v, size_t n, cudaStream_t st);
+void launch_read_u4(const void* p, size_t bytes, int iters, uint32_t* sink, cudaStream_t st);
 
 } // namespace rlerc

@@ -39,7 +39,7 @@ namespace rlerc {
 #endif
 #define RLERC_F_SLOTS (RLERC_F_CH * 33)     // record slots per chunk: crossing c of the chunk sits in slot c + (c >> 5), so that
                                             // the DDA lanes (stride 33) and the filter lanes (stride 1) are both conflict-free
-#define RLERC_F_REC (3 * RLERC_F_SLOTS + (RLERC_F_SLOTS + 3) / 4)   // words: distance, pos.x, pos.y (float) + mip level (byte) per slot
+#define RLERC_F_REC ((3 * RLERC_F_SLOTS + (RLERC_F_SLOTS + 3) / 4 + 3) & ~3)   // words: distance, pos.x, pos.y (float) + mip level (byte) per slot
 #define RLERC_F_QUEUE (8 * RLERC_QCAP)      // words: 8 fields x QCAP, field-major
 
 static_assert(RLERC_F_CH >= 1 && RLERC_F_CH <= 32, "one lane per batch of a chunk");

@@ -1,12 +1,18 @@
 """Multi-GPU frames: one process per GPU (torch.distributed), full scene replica per GPU, the ray
-planes of every frame dealt out in interleaved blocks, finished pixels composited on rank 0 with one
-reduce over NVLink (NCCL).  Nothing in the reference corresponds to this (it is single-GPU,
-SURVEY.md §2a); the split follows SURVEY.md §8e: ray planes are independent, the only exchange is the
-final compositing, and the multi-GPU frame must equal the single-GPU frame bit for bit.
+planes of every frame dealt out in interleaved blocks ("column slices" of the warped ray buffer), finished
+pixels composited over NVLink with NCCL.  Nothing in the reference corresponds to this (it is single-GPU,
+SURVEY.md §2a); the split follows SURVEY.md §8e: ray planes are independent (R/src/Cuda_Render.h:109: every ray
+plane writes only its own row), the only exchange is the final compositing, and the multi-GPU frame must equal
+the single-GPU frame bit for bit.
 
 Slices are interleaved rather than contiguous because ray cost varies smoothly with the ray index
 (rays toward the horizon walk ~20x more cells than rays toward the ground): dealing blocks of
 `block` consecutive ray planes round-robin gives every GPU the same mix.
+
+Two compositors, both exact (the per-rank images have disjoint support, so a sum is a select):
+  reduce   one NCCL reduce(sum) of the RGBA8 images to rank 0: the finished frame is on GPU 0.
+  bands    one NCCL reduce_scatter(sum): rank r ends up with rows [r*H/N, (r+1)*H/N) of the finished frame and
+           copies them to the host itself, so a frame that is wanted in HOST memory leaves over N PCIe links.
 """
 import ctypes as C
 
@@ -27,12 +33,31 @@ def owned_count(count, block, nranks, rank):
     return owned + max(0, min(rem, block))
 
 
+def band_rows(height, nranks):
+    """Rows per rank of the `bands` compositor (the image is padded to nranks * band_rows rows)."""
+    return (height + nranks - 1) // nranks
+
+
 def composite(image, dist, dst=0):
     """Sum-reduce the per-rank images (uint8 tensors with disjoint support) onto rank `dst`.
     NCCL over NVLink on GPUs; gloo in the CPU tests.  Returns `image` (complete on rank dst)."""
     if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
         dist.reduce(image, dst=dst, op=dist.ReduceOp.SUM)
     return image
+
+
+def composite_bands(image, band, dist):
+    """reduce_scatter(sum) of the per-rank images: `band` (this rank's rows of the finished frame) <- sum over
+    ranks of the matching rows of `image` ([nranks * band_rows, W, 4]).  gloo has no reduce_scatter: the CPU
+    tests go through all_reduce + slicing, the same arithmetic."""
+    world = dist.get_world_size()
+    rank = dist.get_rank()
+    if dist.get_backend() == "nccl":
+        return dist.reduce_scatter_tensor(band, image, op=dist.ReduceOp.SUM, async_op=True)
+    dist.all_reduce(image, op=dist.ReduceOp.SUM)
+    rows = image.shape[0] // world
+    band.copy_(image[rank * rows:(rank + 1) * rows])
+    return None
 
 
 class SlicedFrame:
@@ -54,6 +79,91 @@ class SlicedFrame:
         self.r.render_interleaved(raymap_gpu, self.cfg, self.block, self.world, self.rank)
         self.r.unwarp_interleaved(raymap_gpu, self.cfg, self.block, self.world, self.rank, d_rgba=self.rgba.data_ptr())
         return composite(self.rgba, self.dist)
+
+
+class FramePipe:
+    """`depth` frames in flight on this rank's GPU.  One context per slot (its own stream, warped buffer, DDA states
+    and RGBA image), all sharing ONE scene replica (rlerc_scene_share).  Frame i goes to slot i % depth; with
+    world > 1 every rank renders its interleaved slice of every frame and the compositor runs on the slot's stream
+    order (torch's NCCL stream waits for the slot's kernels; the slot waits for the collective before it is reused),
+    so nothing blocks the host and the collectives are issued in the same order on every rank.
+
+    compose: "reduce" (frame complete on rank 0), "bands" (reduce_scatter, every rank keeps its rows; `host` = a
+    [slots, nranks * band_rows, W, 4] uint8 host tensor shared by all ranks gets every band copied in by its owner),
+    "none" (world == 1, or frames kept where they were rendered)."""
+
+    def __init__(self, R, torch, device, scene, cfg, depth=4, rank=0, world=1, dist=None, block=DEFAULT_BLOCK, lanes=0,
+                 compose="reduce", host=None, share_from=None):
+        self.torch, self.dist, self.cfg = torch, dist, cfg
+        self.rank, self.world, self.block, self.depth = rank, world, block, depth
+        self.compose = compose if world > 1 else "none"
+        dev = torch.device("cuda", device)
+        self.r = [R.Renderer(device) for _ in range(depth)]
+        if share_from is not None:
+            for x in self.r:
+                x.share_scene(share_from)
+        else:
+            self.r[0].all_to_gpu(scene)
+            for x in self.r[1:]:
+                x.share_scene(self.r[0])
+        self.streams = [torch.cuda.Stream(dev) for _ in range(depth)]
+        for x, s in zip(self.r, self.streams):
+            x.set_lanes_per_ray(lanes)
+            x.set_stream(s.cuda_stream)
+        self.rows = band_rows(cfg.height, world) if self.compose == "bands" else cfg.height
+        full = self.rows * world if self.compose == "bands" else cfg.height
+        self.rgba = [torch.zeros((full, cfg.width, 4), dtype=torch.uint8, device=dev) for _ in range(depth)]
+        self.band = [torch.zeros((self.rows, cfg.width, 4), dtype=torch.uint8, device=dev) for _ in range(depth)] \
+            if self.compose == "bands" else None
+        self.pending = [None] * depth
+        self.host = host
+
+    def submit(self, i, raymap_gpu):
+        """Enqueue frame i (asynchronous).  Returns the slot it went to."""
+        k = i % self.depth
+        with self.torch.cuda.stream(self.streams[k]):
+            if self.pending[k] is not None:
+                self.pending[k].wait()              # stream-ordered: the slot's image is free again
+                self.pending[k] = None
+            self.r[k].frame_device(raymap_gpu, self.cfg, self.block, self.world, self.rank, self.rgba[k].data_ptr())
+            if self.compose == "reduce":
+                self.pending[k] = self.dist.reduce(self.rgba[k], dst=0, op=self.dist.ReduceOp.SUM, async_op=True)
+            elif self.compose == "bands":
+                w = composite_bands(self.rgba[k], self.band[k], self.dist)
+                if w is not None:
+                    w.wait()
+                if self.host is not None:
+                    lo = self.rank * self.rows
+                    self.host[k, lo:lo + self.rows].copy_(self.band[k], non_blocking=True)
+            elif self.host is not None:
+                self.host[k].copy_(self.rgba[k], non_blocking=True)
+        return k
+
+    def drain(self, onto=None):
+        """Make `onto` (default: the current stream) wait for everything submitted so far."""
+        cur = onto if onto is not None else self.torch.cuda.current_stream()
+        for k, s in enumerate(self.streams):
+            if self.pending[k] is not None:
+                with self.torch.cuda.stream(s):
+                    self.pending[k].wait()
+                self.pending[k] = None
+            cur.wait_stream(s)
+
+    def start_after(self, event):
+        for s in self.streams:
+            s.wait_event(event)
+
+    def image(self, k):
+        """Slot k's finished frame as the compositor left it on this rank (reduce: complete on rank 0; bands: this
+        rank's rows; none: the whole frame)."""
+        if self.compose == "bands":
+            return self.band[k]
+        return self.rgba[k][:self.cfg.height]
+
+    def close(self):
+        self.torch.cuda.synchronize()
+        for x in reversed(self.r):
+            x.close()
 
 
 class FrameFarm:

@@ -17,13 +17,14 @@ def marks(fname, table):
 
 M = {
     "traverse_filte": marks("traverse_filter.cu", [
-        ("struct DdaQ {", "F1 DDA (serial recurrence, 32 crossings)"), ("#define RLERC_TICK", "set-up / loop / epilogue"),
-        ("// F1. DDA", "F1 DDA (serial recurrence, 32 crossings)"), ("// F2. first-run", "F2 first-run test + queue"),
-        ("// F3. geometry", "F3 geometry + pointer-map gather"), ("// ---- C1.", "C1 run-word loads"),
-        ("// ---- C2.", "C2 run projection"), ("// ---- B / B0", "set-up / loop / epilogue")]),
+        ("struct DdaQ {", "DDA (lane-parallel chunk re-expansion)"), ("// ---- pre-pass:", "DDA (lane-parallel chunk re-expansion)"),
+        ("// ---- FILTER, geometry half", "F geometry + pointer-map gather"), ("// ---- FILTER, test half", "F first-run test + queue"),
+        ("// entry of the live-column queue", "F first-run test + queue"),
+        ("// ---- C1: take a live column", "C1 run-word loads"), ("// ---- C2: project the runs", "C2 run projection"),
+        ("__device__ __forceinline__ void filter_ray_init", "set-up / loop / epilogue")]),
     "traverse_commo": marks("traverse_common.cuh", [
         ("__device__ __noinline__ int coop_span(", "cooperative span shaders"), ("void long_column(", "long_column (lane <-> run)"),
-        ("struct DdaState {", "helpers"), ("// ---- B0. rising-horizon", "B0 rising-horizon path"),
+        ("// ---- B0. rising-horizon", "B0 rising-horizon path"),
         ("// ---- B1. ownership-resolved", "B1 ownership-resolved path"), ("// ---- E. one event-loop iteration", "event loop (owner lane)"),
         ("// ---- S. shade the short spans", "S deferred shading")]),
 }
