@@ -227,6 +227,52 @@ int  rlerc_frame_submit(rlerc_ctx* c, const float pos[3], const float rot[3],
                         const rlerc_frame_config* cfg, uint8_t* host_rgba);
 int  rlerc_frame_wait(rlerc_ctx* c, int ticket);
 
+/* ---- multi-GPU frames (the reference is single-GPU) -------------------- */
+/* N GPUs, a full replica of the scene in each; every frame's ray planes are dealt to the GPUs in interleaved blocks of
+ * `slice_block` (R/src/Cuda_Render.h:109: ray planes are independent); compositing happens inside the unwarp kernel over
+ * NVLink peer memory: GPU r produces rows [r*H/N, (r+1)*H/N) of the window, loading every texel from the warped buffer
+ * of the GPU that traversed its ray plane.  The multi-GPU frame equals the single-GPU frame bit for bit. */
+
+/* (a) all GPUs in ONE process — what a C++ host (the reference's host language) uses in place of rlerc_create. */
+typedef struct rlerc_multi rlerc_multi;
+int  rlerc_create_multi(const int* devices, int n, rlerc_multi** out);                 /* n <= 8 distinct devices */
+void rlerc_multi_destroy(rlerc_multi* m);
+int  rlerc_multi_count(const rlerc_multi* m);
+rlerc_ctx* rlerc_multi_ctx(rlerc_multi* m, int i);                                     /* member i's context (borrowed) */
+/* frames in flight (default 4) and ray planes per interleaved block (default 32); takes effect at the next frame */
+int  rlerc_multi_set_depth(rlerc_multi* m, int depth, int slice_block);
+int  rlerc_multi_scene_upload(rlerc_multi* m, const rlerc_scene* s);                   /* RLE4::all_to_gpu on every GPU */
+/* rlerc_render_frame / rlerc_frame_submit / rlerc_frame_wait on all GPUs: get_ray_map -> traversal slices -> unwarp bands
+ * -> every GPU copies ITS rows into host_rgba over its own PCIe link (host_rgba: width*height*4 bytes, pinned recommended). */
+int  rlerc_multi_render_frame(rlerc_multi* m, const float pos[3], const float rot[3],
+                              const rlerc_frame_config* cfg, uint8_t* host_rgba);
+int  rlerc_multi_frame_submit(rlerc_multi* m, const float pos[3], const float rot[3],
+                              const rlerc_frame_config* cfg, uint8_t* host_rgba);
+int  rlerc_multi_frame_wait(rlerc_multi* m, int ticket);
+
+/* (b) one member per context, members in one process or ONE PROCESS PER GPU (torchrun): create, exchange the
+ * RLERC_GROUP_BLOB_BYTES descriptions (CUDA IPC handles) by any means, connect, then submit the same frames in the same
+ * order on every member. */
+typedef struct rlerc_group rlerc_group;
+#define RLERC_GROUP_BLOB_BYTES 256
+int  rlerc_group_create(rlerc_ctx* c, int rank, int nranks, int depth, int slice_block,
+                        const rlerc_frame_config* cfg, rlerc_group** out);
+void rlerc_group_destroy(rlerc_group* g);
+int  rlerc_group_export(rlerc_group* g, void* blob);
+int  rlerc_group_connect(rlerc_group* g, const void* blobs /* nranks * RLERC_GROUP_BLOB_BYTES, member r at r * BYTES */);
+/* Enqueue this member's part of the next frame (asynchronous; returns its ticket, the same number on every member).
+ * dst_rank >= 0: the finished frame is assembled in member dst_rank's image (pushed there over NVLink);
+ * dst_rank < 0: every member keeps its band of rows.  host_rgba (may be NULL) = start of the WHOLE frame in host memory:
+ * the member that holds the frame (or every member its band) copies it there. */
+int  rlerc_group_submit(rlerc_group* g, const rlerc_raymap* rm, int dst_rank, uint8_t* host_rgba);
+int  rlerc_group_wait(rlerc_group* g, int ticket);
+int  rlerc_group_sync(rlerc_group* g);
+/* Device image of the ticket's slot [height][width][4] and the rows this member produces. */
+int  rlerc_group_image(rlerc_group* g, int ticket, uint8_t** d_rgba, int* row_begin, int* row_end);
+void* rlerc_group_stream(rlerc_group* g, int ticket);                                  /* cudaStream_t of the ticket's slot */
+/* with rlerc_set_timing on the member's context: ms from the first kernel of the ticket's frame to its last barrier */
+int  rlerc_group_last_ms(rlerc_group* g, int ticket, float* ms);
+
 /* ---- plumbing ------------------------------------------------------------------------ */
 int   rlerc_sync(rlerc_ctx* c);
 void* rlerc_stream(rlerc_ctx* c);                    /* cudaStream_t the kernels run on */

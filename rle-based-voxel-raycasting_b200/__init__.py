@@ -122,6 +122,25 @@ _SIGS = {
     "rlerc_host_free": (None, [_P]),
     "rlerc_last_kernel_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "rlerc_set_timing": (C.c_int, [_P, C.c_int]),
+    "rlerc_create_multi": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(_P)]),
+    "rlerc_multi_destroy": (None, [_P]),
+    "rlerc_multi_count": (C.c_int, [_P]),
+    "rlerc_multi_ctx": (_P, [_P, C.c_int]),
+    "rlerc_multi_set_depth": (C.c_int, [_P, C.c_int, C.c_int]),
+    "rlerc_multi_scene_upload": (C.c_int, [_P, _P]),
+    "rlerc_multi_render_frame": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), _P, _P]),
+    "rlerc_multi_frame_submit": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), _P, _P]),
+    "rlerc_multi_frame_wait": (C.c_int, [_P, C.c_int]),
+    "rlerc_group_create": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.POINTER(_P)]),
+    "rlerc_group_destroy": (None, [_P]),
+    "rlerc_group_export": (C.c_int, [_P, _P]),
+    "rlerc_group_connect": (C.c_int, [_P, _P]),
+    "rlerc_group_submit": (C.c_int, [_P, _P, C.c_int, _P]),
+    "rlerc_group_wait": (C.c_int, [_P, C.c_int]),
+    "rlerc_group_sync": (C.c_int, [_P]),
+    "rlerc_group_image": (C.c_int, [_P, C.c_int, C.POINTER(_P), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "rlerc_group_stream": (_P, [_P, C.c_int]),
+    "rlerc_group_last_ms": (C.c_int, [_P, C.c_int, C.POINTER(C.c_float)]),
     "gpu_malloc": (_P, [C.c_int]),
     "gpu_memcpy": (None, [_P, _P, C.c_int]),
     "cpu_memcpy": (None, [_P, _P, C.c_int]),
@@ -416,6 +435,114 @@ class Renderer:
 
     def read_warp(self, cfg):
         return self.download(self.warp_buffer(cfg), (cfg.rays_casted, cfg.render_size), np.uint32)
+
+
+GROUP_BLOB_BYTES = 256
+
+
+class Group:
+    """One member of an N-GPU group (include/rlerc.h "multi-GPU", csrc/group.cu): this GPU traverses its interleaved
+    blocks of ray planes and produces its band of window rows, pulling texels from the other members' warped buffers
+    over NVLink.  Members in other processes are reached through CUDA IPC: exchange export() blobs, then connect()."""
+
+    def __init__(self, renderer, cfg, rank=0, world=1, depth=4, block=32):
+        self._g = C.c_void_p()
+        self.r, self.cfg, self.rank, self.world, self.depth, self.block = renderer, cfg, rank, world, depth, block
+        _check(lib().rlerc_group_create(renderer._c, rank, world, depth, block, C.byref(cfg), C.byref(self._g)))
+
+    def export(self):
+        buf = (C.c_uint8 * GROUP_BLOB_BYTES)()
+        _check(lib().rlerc_group_export(self._g, buf))
+        return bytes(buf)
+
+    def connect(self, blobs):
+        """blobs: the members' export() results concatenated in rank order."""
+        blobs = bytes(blobs)
+        if len(blobs) != self.world * GROUP_BLOB_BYTES:
+            raise RlercError("Group.connect: %d bytes for %d members" % (len(blobs), self.world))
+        _check(lib().rlerc_group_connect(self._g, blobs))
+
+    def connect_distributed(self, torch, dist):
+        """Exchange the descriptions over torch.distributed (one process per GPU) and connect."""
+        if self.world == 1:
+            return
+        mine = torch.frombuffer(bytearray(self.export()), dtype=torch.uint8)
+        if dist.get_backend() == "nccl":
+            mine = mine.cuda(self.r.device)
+        out = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(out, mine)
+        self.connect(b"".join(bytes(t.cpu().numpy().tobytes()) for t in out))
+        dist.barrier()
+
+    def submit(self, raymap_gpu, dst=0, host=None):
+        """Enqueue the next frame (the same call, in the same order, on every member). Returns its ticket."""
+        return _check(lib().rlerc_group_submit(self._g, C.byref(raymap_gpu), dst, _ptr(host) if host is not None else None))
+
+    def wait(self, ticket):
+        _check(lib().rlerc_group_wait(self._g, ticket))
+
+    def sync(self):
+        _check(lib().rlerc_group_sync(self._g))
+
+    def image(self, ticket):
+        """(device pointer of the ticket's [H][W][4] image, first row, one past the last row this member produces)."""
+        p, a, b = C.c_void_p(), C.c_int(), C.c_int()
+        _check(lib().rlerc_group_image(self._g, ticket, C.byref(p), C.byref(a), C.byref(b)))
+        return p.value, a.value, b.value
+
+    def stream(self, ticket):
+        return lib().rlerc_group_stream(self._g, ticket)
+
+    def last_ms(self, ticket):
+        ms = C.c_float()
+        _check(lib().rlerc_group_last_ms(self._g, ticket, C.byref(ms)))
+        return ms.value
+
+    def close(self):
+        if self._g:
+            lib().rlerc_group_destroy(self._g)
+            self._g = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MultiRenderer:
+    """All GPUs of a node behind one object in ONE process (rlerc_create_multi): the multi-GPU drop-in for Renderer's
+    render_frame / frame_submit / frame_wait."""
+
+    def __init__(self, devices, depth=4, block=32):
+        self._m = C.c_void_p()
+        arr = (C.c_int * len(devices))(*devices)
+        _check(lib().rlerc_create_multi(arr, len(devices), C.byref(self._m)))
+        _check(lib().rlerc_multi_set_depth(self._m, depth, block))
+        self.devices = list(devices)
+
+    def all_to_gpu(self, scene):
+        _check(lib().rlerc_multi_scene_upload(self._m, scene._h))
+
+    def render_frame(self, pos, rot, cfg, host_rgba):
+        _check(lib().rlerc_multi_render_frame(self._m, _f3(pos), _f3(rot), C.byref(cfg), _ptr(host_rgba)))
+
+    def frame_submit(self, pos, rot, cfg, host_rgba):
+        return _check(lib().rlerc_multi_frame_submit(self._m, _f3(pos), _f3(rot), C.byref(cfg), _ptr(host_rgba)))
+
+    def frame_wait(self, ticket):
+        _check(lib().rlerc_multi_frame_wait(self._m, ticket))
+
+    def close(self):
+        if self._m:
+            lib().rlerc_multi_destroy(self._m)
+            self._m = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def _ptr(a):

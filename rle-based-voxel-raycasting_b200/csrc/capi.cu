@@ -12,76 +12,11 @@
 #include "kernels.cuh"
 #include "device_common.cuh"
 #include "rlerc_internal.h"
+#include "capi_internal.cuh"
 
 using namespace rlerc;
 
-#define CK(call)                                                                        \
-	do {                                                                                \
-		cudaError_t e_ = (call);                                                        \
-		if (e_ != cudaSuccess) {                                                        \
-			set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
-			return RLERC_ERR_CUDA;                                                      \
-		}                                                                               \
-	} while (0)
-
-namespace {
-
-struct FrameSlot {            // one in-flight frame of the pipelined path
-	uint32_t* d_warp = nullptr;
-	uint8_t* d_rgba = nullptr;
-	float2* d_states = nullptr;      // DDA states of the frame's ray planes (k_dda_states -> k_traverse_f / _p)
-	size_t warp_bytes = 0, rgba_bytes = 0, states_bytes = 0;
-	cudaEvent_t done = nullptr;
-	cudaStream_t stream = nullptr;   // each in-flight frame renders on its own stream: the tail of one
-	                                 // frame's traversal (a few long ray planes) overlaps the next frame
-	uint8_t* host_dst = nullptr;
-	bool busy = false;
-};
-
-} // namespace
-
-struct rlerc_ctx {
-	int device = 0;
-	cudaStream_t stream = nullptr;      // traversal + unwarp
-	cudaStream_t copy_stream = nullptr; // D2H of finished frames
-	// device scene replica
-	int nummaps = 0;
-	LevelDev level[RLERC_MAX_MAPS];
-	int level_sy[RLERC_MAX_MAPS];
-	uint64_t level_slabs[RLERC_MAX_MAPS];
-	std::vector<void*> scene_allocs;    // empty when the replica is borrowed (rlerc_scene_share)
-	// frame resources
-	uint32_t* d_warp = nullptr;
-	size_t warp_bytes = 0;
-	uint8_t* d_rgba = nullptr;
-	size_t rgba_bytes = 0;
-	float2* d_states = nullptr;         // DDA states of the ray planes of the frame on c->stream
-	size_t states_bytes = 0;
-	float2** cur_states = nullptr;      // the states buffer render_impl uses (rlerc_frame_submit points it at the slot's)
-	size_t* cur_states_bytes = nullptr;
-	unsigned int dda_epoch = 0;         // epoch of the last traversal launch (k_dda_states -> traversal hand-over)
-	const char* last_kernel = "";       // traversal kernel of the last launch
-	uint32_t* d_ids_scratch = nullptr;
-	unsigned long long* d_counters = nullptr;
-	int lanes = 0;                      // 0 = auto (pick_lanes)
-	int sm_count = 148;
-	int dda_mode = 0;                   // 0 serial (default: fastest measured), 2 merge path (k_traverse_w)
-	int producer = 0;                   // decoupled DDA producer blocks (k_traverse_w): optional, off by default
-	float4* d_ring = nullptr;
-	size_t ring_bytes = 0;
-	int* d_ring_ctl = nullptr;          // head[rays] | tail[rays] | err
-	size_t ring_ctl_bytes = 0;
-	bool timing = false;
-	bool own_stream = true;
-	cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
-	bool ev_valid[2] = { false, false };
-	// pipeline
-	static const int kSlots = 6;        // frames in flight in rlerc_frame_submit (each on its own stream)
-	FrameSlot slot[kSlots];
-	int next_ticket = 0;
-};
-
-namespace {
+namespace rlerc {
 
 int set_dev(rlerc_ctx* c)
 {
@@ -99,7 +34,7 @@ void free_scene(rlerc_ctx* c)
 // (Re)allocate a device buffer.  A new buffer is zero-filled ON THE STREAM THAT WILL USE IT: the streams here are
 // cudaStreamNonBlocking, which a memset on the legacy default stream does not order with.  zero = false: the buffer is
 // fully written before it is read (DDA states).
-int ensure(void** p, size_t* have, size_t need, cudaStream_t st, bool zero = true)
+int ensure(void** p, size_t* have, size_t need, cudaStream_t st, bool zero)
 {
 	if (*have >= need && *p) return RLERC_OK;
 	if (*p) cudaFree(*p);                                        // synchronises the device: nothing still uses the old buffer
@@ -200,9 +135,10 @@ int fill_traverse(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_config
 }
 
 // Uniforms of the colorize pass exactly as main.cpp:578-603 computes them.
-int fill_unwarp(const rlerc_raymap* rm, const rlerc_frame_config* cfg, const uint32_t* d_warp, uint8_t* d_rgba, UnwarpParams& U)
+int fill_unwarp(const rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_config* cfg, const uint32_t* d_warp, uint8_t* d_rgba, UnwarpParams& U)
 {
 	memset(&U, 0, sizeof(U));
+	U.shade_rgb = c->d_shade_rgb; U.shade_alpha = c->d_shade_alpha;
 	U.warp = d_warp; U.rgba = d_rgba;
 	U.W = cfg->width; U.H = cfg->height;
 	U.RS = cfg->render_size; U.RC = cfg->rays_casted;
@@ -221,6 +157,8 @@ int fill_unwarp(const rlerc_raymap* rm, const rlerc_frame_config* cfg, const uin
 	U.row_begin = 0; U.row_end = cfg->height;
 	U.ray_begin = 0; U.ray_end = -1;
 	U.slice_block = 1; U.slice_n = 1; U.slice_rank = 0;
+	U.peer_n = 0;
+	U.generic = (std::fabs(U.vanish_x) < 1e6f && std::fabs(U.vanish_y) < 1e6f) ? 0 : 1;
 	return RLERC_OK;
 }
 
@@ -233,11 +171,11 @@ int fill_unwarp(const rlerc_raymap* rm, const rlerc_frame_config* cfg, const uin
 int pick_lanes(const rlerc_ctx* c, int rays, bool ids)
 {
 	if (c->lanes != 0) return c->lanes;
-	if (!ids && c->dda_mode != 99 && rays > 0 && rays <= 12 * c->sm_count) return 68;
+	if (!ids && !c->pipelined && c->dda_mode != 99 && rays > 0 && rays <= 12 * c->sm_count) return 68;
 	return 0;
 }
 
-} // namespace
+} // namespace rlerc
 
 extern "C" {
 
@@ -258,6 +196,10 @@ int rlerc_create(int device, rlerc_ctx** out)
 	for (int i = 0; i < 4; i++) CK(cudaEventCreate(&c->ev[i]));
 	for (int i = 0; i < rlerc_ctx::kSlots; i++) CK(cudaEventCreateWithFlags(&c->slot[i].done, cudaEventDisableTiming));
 	CK(cudaMalloc((void**)&c->d_counters, 32 * sizeof(unsigned long long)));
+	CK(cudaMalloc((void**)&c->d_shade_rgb, 65536 * sizeof(uint32_t)));
+	CK(cudaMalloc((void**)&c->d_shade_alpha, 65536));
+	launch_shade_tables(c->d_shade_rgb, c->d_shade_alpha, c->stream);
+	CK(cudaStreamSynchronize(c->stream));
 	*out = c;
 	return RLERC_OK;
 }
@@ -271,6 +213,8 @@ void rlerc_destroy(rlerc_ctx* c)
 	if (c->d_warp) cudaFree(c->d_warp);
 	if (c->d_rgba) cudaFree(c->d_rgba);
 	if (c->d_counters) cudaFree(c->d_counters);
+	if (c->d_shade_rgb) cudaFree(c->d_shade_rgb);
+	if (c->d_shade_alpha) cudaFree(c->d_shade_alpha);
 	if (c->d_states) cudaFree(c->d_states);
 	if (c->d_ring) cudaFree(c->d_ring);
 	if (c->d_ring_ctl) cudaFree(c->d_ring_ctl);
@@ -425,9 +369,10 @@ int rlerc_warp_buffer(rlerc_ctx* c, const rlerc_frame_config* cfg, uint32_t** d_
 	return RLERC_OK;
 }
 
-static int render_impl(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_config* cfg,
+} // extern "C"
+int rlerc::render_impl(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_config* cfg,
                        int ray_begin, int ray_end, uint32_t* d_warp, uint32_t* d_ids, bool ids,
-                       int slice_block = 1, int slice_n = 1, int slice_rank = 0, uint32_t* prof_out = nullptr)
+                       int slice_block, int slice_n, int slice_rank, uint32_t* prof_out)
 {
 	if (!c || !rm) { set_error("rlerc_render: null argument"); return RLERC_ERR_ARG; }
 	int rc = check_cfg(cfg);
@@ -503,6 +448,7 @@ static int render_impl(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_c
 	CK(cudaGetLastError());
 	return RLERC_OK;
 }
+extern "C" {
 
 int rlerc_render(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_config* cfg, int ray_begin, int ray_end, uint32_t* d_warp)
 {
@@ -588,9 +534,10 @@ int rlerc_debug_counters(rlerc_ctx* c, uint64_t out[32])
 	return RLERC_OK;
 }
 
-static int unwarp_impl(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_config* cfg, const uint32_t* d_warp,
+} // extern "C"
+int rlerc::unwarp_impl(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_config* cfg, const uint32_t* d_warp,
                        uint8_t* d_rgba, int row_begin, int row_end, int ray_begin, int ray_end,
-                       int slice_block = 1, int slice_n = 1, int slice_rank = 0)
+                       int slice_block, int slice_n, int slice_rank)
 {
 	if (!c || !rm) { set_error("rlerc_unwarp: null argument"); return RLERC_ERR_ARG; }
 	int rc = check_cfg(cfg);
@@ -608,7 +555,7 @@ static int unwarp_impl(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_c
 		d_rgba = c->d_rgba;
 	}
 	UnwarpParams U;
-	fill_unwarp(rm, cfg, d_warp, d_rgba, U);
+	fill_unwarp(c, rm, cfg, d_warp, d_rgba, U);
 	if (row_end < 0 || row_end > cfg->height) row_end = cfg->height;
 	if (row_begin < 0) row_begin = 0;
 	U.row_begin = row_begin; U.row_end = row_end;
@@ -620,10 +567,25 @@ static int unwarp_impl(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_c
 	CK(cudaGetLastError());
 	return RLERC_OK;
 }
+extern "C" {
 
 int rlerc_unwarp(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_config* cfg, const uint32_t* d_warp, uint8_t* d_rgba, int row_begin, int row_end)
 {
 	return unwarp_impl(c, rm, cfg, d_warp, d_rgba, row_begin, row_end, 0, -1);
+}
+
+/* undocumented (tests): the texel every window pixel samples, uint32[height][width] = ray plane << 16 | position along the ray */
+int rlerc_debug_unwarp_texels(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_config* cfg, uint32_t* d_out)
+{
+	if (!c || !rm || !d_out) return RLERC_ERR_ARG;
+	int rc = check_cfg(cfg);
+	if (rc) return rc;
+	if ((rc = set_dev(c))) return rc;
+	UnwarpParams U;
+	fill_unwarp(c, rm, cfg, nullptr, (uint8_t*)d_out, U);
+	launch_unwarp(U, c->stream, true);
+	CK(cudaGetLastError());
+	return RLERC_OK;
 }
 
 int rlerc_unwarp_slice(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_config* cfg, const uint32_t* d_warp, uint8_t* d_rgba, int ray_begin, int ray_end)
@@ -733,12 +695,15 @@ int rlerc_frame_submit(rlerc_ctx* c, const float pos[3], const float rot[3], con
 	}
 	cudaStream_t const fs = c->stream;
 	c->cur_states = &s.d_states; c->cur_states_bytes = &s.states_bytes;
+	const bool was_pipelined = c->pipelined;
+	c->pipelined = true;                    // frames overlap: throughput-bound, the paired kernel would only add instructions
 	rc = ensure((void**)&s.d_warp, &s.warp_bytes, (size_t)cfg->rays_casted * cfg->render_size * 4, fs);
 	if (!rc) rc = ensure((void**)&s.d_rgba, &s.rgba_bytes, (size_t)cfg->width * cfg->height * 4, fs);
 	if (!rc) rc = render_impl(c, &rm, cfg, 0, -1, s.d_warp, nullptr, false);
 	if (!rc) rc = unwarp_impl(c, &rm, cfg, s.d_warp, s.d_rgba, 0, -1, 0, -1);
 	c->stream = main_stream;
 	c->cur_states = nullptr; c->cur_states_bytes = nullptr;
+	c->pipelined = was_pipelined;
 	if (rc) return rc;
 	// hand the finished frame to the copy stream so the next frame's traversal overlaps the D2H
 	CK(cudaEventRecord(s.done, fs));

@@ -431,11 +431,40 @@ void launch_traverse(const TraverseParams& p, int lanes, bool ids, cudaStream_t 
 }
 
 // ------------------------------------------------------------------------------------------
-// Unwarp + shade.  One thread produces four horizontally adjacent pixels and writes them
+// Unwarp + shade (GLSL pass 1, R/bin/shader/colorize_buddha_soft.frag:12-137, uniforms R/src/main.cpp:578-603).
+// One thread produces a tile of 4 horizontally adjacent pixels x RLERC_UNWARP_ROWS rows and writes every row of it
 // with one 128-bit store.  Pixel (px, py) with GL origin bottom-left; output row 0 = top.
-// The statement order follows colorize_buddha_soft.frag line by line (cites inline) so
-// that the texel chosen is bit-identical to the CPU restatement in oracle/.
-__device__ __forceinline__ float stepf(float edge, float x) { return x >= edge ? 1.0f : 0.0f; }
+//
+// The shader evaluates ~12 IEEE divisions per fragment.  Most of them do not depend on the fragment: here everything
+// that depends only on the column (scx, scx1, left, |scx1|*RESX/RESY, ...) is computed once per thread column and
+// everything that depends only on the row (scy, scy1, upper, fy/RESX, ...) once per thread row; the step() selectors
+// are 0.0 or 1.0, so each `sel * a + (1 - sel) * b` of the shader IS a or b (x*1 + y*0 == x exactly for finite
+// operands), and only the selected branch is evaluated — with the same operations in the same order, so the texel
+// chosen is bit-identical to the CPU restatement in oracle/ (checked per pixel by tests/test_gpu_parity.py through
+// rlerc_debug_unwarp_texels).  One case needs care: the branch that is NOT selected can be non-finite (a division by
+// scy1 == 0 or scx1 == 0) and then poisons x_pre through inf * 0 = NaN; that is reproduced explicitly.
+// c / 255.0f of the four texel bytes comes from a 256-entry table in shared memory (the same IEEE quotient).
+//
+// Multi-GPU "pull" mode (P.peer_n > 1, csrc/group.cu): ray plane iy lives in the warped buffer of GPU
+// (iy / slice_block) % peer_n; the texel is loaded from that GPU's buffer over NVLink (peer mapping), and P.rgba may
+// point into another GPU's frame buffer: unwarp and compositing are one kernel, no collective moves pixel data.
+// Thread <-> pixel mapping: a thread produces 4 horizontally adjacent pixels (one 128-bit store), a WARP a tile of
+// RLERC_UNWARP_QW quads x (32 / QW) rows = 8 pixels x 16 rows, a block RLERC_UNWARP_WARPS such tiles side by side.
+// In the upper / lower segments the texels of vertically adjacent pixels are adjacent along one ray (ix = row + const),
+// in the left / right segments those of horizontally adjacent pixels are: the 128 gathers of a warp tile fall into
+// 16-32 sectors of 32 bytes instead of 128 with a row-by-row order (one load instruction touches 4-16 sectors, the
+// other three mostly hit L1) — fewer L2 requests locally, and what the NVLink pull of the multi-GPU mode pays for.  The
+// stores stay full 32-byte sectors (two lanes per row).
+#ifndef RLERC_UNWARP_QW
+#define RLERC_UNWARP_QW 2
+#endif
+#ifndef RLERC_UNWARP_WARPS
+#define RLERC_UNWARP_WARPS 4
+#endif
+#ifndef RLERC_UNWARP_MINB
+#define RLERC_UNWARP_MINB 12
+#endif
+#define RLERC_UNWARP_TROWS (32 / RLERC_UNWARP_QW)
 
 __device__ __forceinline__ uint32_t quant8(float c)
 {
@@ -443,7 +472,85 @@ __device__ __forceinline__ uint32_t quant8(float c)
 	return (uint32_t)__float2int_rz(c * 255.0f + 0.5f);
 }
 
-__device__ __forceinline__ uint32_t unwarp_pixel(const UnwarpParams& P, int px, int pyg)
+struct UnwarpCol {            // per pixel column (frag:19,24,28-29,42-44)
+	float scx, scx1, axr, Bc, c3;
+	bool left;
+};
+struct UnwarpRow {            // per pixel row (frag:20,25,27,36,38-40)
+	float scy1, ay, A, c2, fyx;
+	bool upper;
+};
+
+__device__ __forceinline__ void unwarp_col(const UnwarpParams& P, int px, UnwarpCol& c)
+{
+	const float RESX = (float)P.W, RESY = (float)P.H;
+	const float fx = (float)px + 0.5f;                               // gl_FragCoord.x
+	c.scx = fx / RESX;                                               // frag:19
+	c.scx1 = c.scx - P.vanish_x;                                     // frag:24
+	c.left = 0.0f >= c.scx1;                                         // frag:28 step(scx1, 0)
+	c.axr = fabsf(c.scx1) * RESX / RESY;                             // frag:29, the column half of ostep
+	const float left = c.left ? 1.0f : 0.0f;
+	c.Bc = fabsf(1 - left - P.vanish_x);                             // frag:42
+	c.c3 = c.left ? (1 - P.vanish_y) : P.vanish_y;                   // frag:43-44: left*(1-vy) + (1-left)*vy
+}
+
+__device__ __forceinline__ void unwarp_row(const UnwarpParams& P, int pyg, UnwarpRow& r)
+{
+	const float RESX = (float)P.W, RESY = (float)P.H;
+	const float fy = (float)pyg + 0.5f;                              // gl_FragCoord.y
+	const float scy = fy / RESY;                                     // frag:20
+	r.scy1 = scy - P.vanish_y;                                       // frag:25
+	r.upper = 0.0f >= r.scy1;                                        // frag:27
+	r.ay = fabsf(r.scy1);
+	const float upper = r.upper ? 1.0f : 0.0f;
+	r.A = fabsf(1 - upper - P.vanish_y);                             // frag:38
+	r.c2 = r.upper ? (1 - P.vanish_x) : P.vanish_x;                  // frag:39-40
+	r.fyx = fy / RESX;                                               // frag:36 for ostep == 0
+}
+
+// texel (iy = ray plane, ix = position along the ray) of one fragment
+__device__ __forceinline__ void unwarp_texel(const UnwarpParams& P, const UnwarpCol& c, const UnwarpRow& r, int& iy, int& ix)
+{
+	const float RESX = (float)P.W, RESY = (float)P.H;
+	const float border = (RESX - RESY) / (RESX * 2);                 // frag:22
+	const bool ostep = 0.0f >= r.ay - c.axr;                          // frag:29
+	float x_pre, o2;
+	if (ostep)
+	{
+		float ang3 = r.scy1 * c.Bc / c.scx1 + c.c3;                  // frag:42-44
+		ang3 = ang3 * RESY / RESX + border;                          // frag:46
+		x_pre = (r.scy1 == 0.0f) ? __int_as_float(0x7fc00000) : ang3;   // frag:53: ang2 = .../scy1 is inf or NaN, times 0: NaN
+		o2 = c.scx;                                                  // frag:36: (1*fx + 0*fy) / RESX
+	}
+	else
+	{
+		const float ang2 = c.scx1 * r.A / r.scy1 + r.c2;             // frag:38-40
+		x_pre = (c.scx1 == 0.0f) ? __int_as_float(0x7fc00000) : ang2;   // frag:53: 0 * ang3 with ang3 = .../scx1 non-finite
+		o2 = r.fyx;
+	}
+	// frag:31-34,56-60: exactly one segment selector is 1
+	float ty;
+	if (!ostep) ty = r.upper ? (P.ofs_add[1] + x_pre) : (P.ofs_add[0] + 1.0f - x_pre);      // seg_dn : seg_up
+	else        ty = c.left ? (P.ofs_add[3] + x_pre) : (P.ofs_add[2] + 1.0f - x_pre);       // seg_lt : seg_rt
+	ty = ty * P.ratio * 0.25f;                                       // frag:62
+	// frag:68-77: rot_x_greater_zero == 0 swaps up <-> dn and rt <-> lt
+	const bool flip = !P.rot_x_gt0;
+	float tx;
+	if (!ostep) tx = ((r.upper != flip) ? (1.0f - (o2 + border)) : (o2 + border));           // seg_dn_x : seg_up_x
+	else        tx = ((c.left != flip) ? (1.0f - o2) : o2);                                  // seg_lt_x : seg_rt_x
+	// GL_NEAREST + CLAMP_TO_EDGE (R/src/GL_Main.cpp:154-157): texel = floor(coord * size), clamped
+	ix = f2i(floorf(tx * (float)P.RS));
+	iy = f2i(floorf(ty * (float)P.RC));
+	ix = ix < 0 ? 0 : (ix >= P.RS ? P.RS - 1 : ix);
+	iy = iy < 0 ? 0 : (iy >= P.RC ? P.RC - 1 : iy);
+}
+
+// The same texel with every statement of the shader evaluated as written (frag:19-77).  Used when the vanishing point is
+// so far out (|vanish| >= 1e6, or not finite: camera pitch within ~1e-6 of level) that the unselected branch of x_pre
+// could overflow to infinity without an exact division by zero — the only case unwarp_texel's shortcut does not cover.
+__device__ __forceinline__ float stepf(float edge, float x) { return x >= edge ? 1.0f : 0.0f; }
+
+__device__ __noinline__ void unwarp_texel_generic(const UnwarpParams& P, int px, int pyg, int& iy, int& ix)
 {
 	const float RESX = (float)P.W, RESY = (float)P.H;
 	const float fx = (float)px + 0.5f, fy = (float)pyg + 0.5f;      // gl_FragCoord
@@ -482,59 +589,119 @@ __device__ __forceinline__ uint32_t unwarp_pixel(const UnwarpParams& P, int px, 
 	               + (seg_dn_x) * (1.0f - (o2 + border))
 	               + (seg_rt_x) * (o2)
 	               + (seg_lt_x) * (1.0f - o2);
-	// GL_NEAREST + CLAMP_TO_EDGE (R/src/GL_Main.cpp:154-157): texel = floor(coord * size), clamped
-	int ix = f2i(floorf(tx * (float)P.RS));
-	int iy = f2i(floorf(ty * (float)P.RC));
+	ix = f2i(floorf(tx * (float)P.RS));
+	iy = f2i(floorf(ty * (float)P.RC));
 	ix = ix < 0 ? 0 : (ix >= P.RS ? P.RS - 1 : ix);
 	iy = iy < 0 ? 0 : (iy >= P.RC ? P.RC - 1 : iy);
-	if (P.ray_end >= 0 && (iy < P.ray_begin || iy >= P.ray_end)) return 0u;   // slice mode
-	if (P.slice_n > 1 && (iy / P.slice_block) % P.slice_n != P.slice_rank) return 0u;
-	const uint32_t t = __ldg(P.warp + (size_t)iy * P.RS + ix);
-	const float cr = (float)(t & 255u) / 255.0f, cg = (float)((t >> 8) & 255u) / 255.0f;
-	const float cb = (float)((t >> 16) & 255u) / 255.0f, ca = (float)(t >> 24) / 255.0f;
-	float r, g, b, fragz = 0.0f;
-	if (cb != 1.0f)                                                   // frag:89-121
-	{
-		const float zz = (cb * (1.0f / 256.0f) + ca);
-		fragz = 0.001f / zz;
-		const float light = (1.0f - cg) * 1.0f + (0.0f + cr) * 0.3f - 0.5f;
-		// pow(max(c, 0), 4) (frag:121) as two squarings: within 1 ulp of powf, a third of k_unwarp's instructions less;
-		// the 8-bit result differs from the oracle's powf in < 1e-4 of the pixels, by 1 LSB (the north star's tolerance)
-		const float lp = fmaxf(light, 0.0f), lp2 = lp * lp;
-		const float pw = 1.2f * (lp2 * lp2);
-		r = light * 1.3f + pw * 1.2f;
-		g = light * 0.9f + pw * 1.2f;
-		b = light * 0.7f + pw * 1.2f;
-	}
-	else { r = 178.0f / 255.0f; g = 204.0f / 255.0f; b = 1.0f; }      // frag:125-126
-	return quant8(r) | (quant8(g) << 8) | (quant8(b) << 16) | (quant8(fragz) << 24);
 }
 
-__global__ void __launch_bounds__(256) k_unwarp(const __grid_constant__ UnwarpParams P)
+// frag:89-136 on the texel's four bytes.  The colour depends on the two attribute bytes only and the smoothing weight
+// (alpha) on the two depth bytes only, so both are tabulated over their full 16-bit domains once per context
+// (k_shade_tables: the formulas below on every input, hence bit-identical to evaluating them per pixel) and a pixel
+// costs two table reads instead of ~60 instructions with five IEEE divisions.
+__device__ __forceinline__ uint32_t shade_rgb(uint32_t lo16)          // lo16 = attribute: byte 0 -> c.r, byte 1 -> c.g
 {
-	const int qx = blockIdx.x * blockDim.x + threadIdx.x;           // group of 4 pixels
-	const int rowi = P.row_begin + blockIdx.y;
-	const int px0 = qx * 4;
-	if (px0 >= P.W || rowi >= P.row_end) return;
-	const int pyg = P.H - 1 - rowi;                                  // GL row
-	uint32_t out[4];
-	#pragma unroll
-	for (int k = 0; k < 4; k++) out[k] = (px0 + k < P.W) ? unwarp_pixel(P, px0 + k, pyg) : 0u;
-	uint32_t* dst = reinterpret_cast<uint32_t*>(P.rgba) + (size_t)rowi * P.W + px0;
-	if (px0 + 3 < P.W && ((P.W & 3) == 0))
-		*reinterpret_cast<uint4*>(dst) = make_uint4(out[0], out[1], out[2], out[3]);
-	else
-		for (int k = 0; k < 4 && px0 + k < P.W; k++) dst[k] = out[k];
+	const float cr = (float)(lo16 & 255u) / 255.0f, cg = (float)((lo16 >> 8) & 255u) / 255.0f;
+	const float light = (1.0f - cg) * 1.0f + (0.0f + cr) * 0.3f - 0.5f;   // frag:90-121
+	// pow(max(c, 0), 4) (frag:121) as two squarings: within 1 ulp of powf; the 8-bit result differs from the
+	// oracle's powf in < 1e-4 of the pixels, by 1 LSB (the north star's tolerance)
+	const float lp = fmaxf(light, 0.0f), lp2 = lp * lp;
+	const float pw = 1.2f * (lp2 * lp2);
+	const float r = light * 1.3f + pw * 1.2f;
+	const float g = light * 0.9f + pw * 1.2f;
+	const float b = light * 0.7f + pw * 1.2f;
+	return quant8(r) | (quant8(g) << 8) | (quant8(b) << 16);
+}
+__device__ __forceinline__ uint32_t shade_alpha(uint32_t hi16)        // hi16 = depth: byte 0 -> c.b, byte 1 -> c.a
+{
+	const float cb = (float)(hi16 & 255u) / 255.0f, ca = (float)(hi16 >> 8) / 255.0f;
+	const float zz = (cb * (1.0f / 256.0f) + ca);                         // frag:89,135
+	return quant8(0.001f / zz);
+}
+#define RLERC_SKY_RGBA (178u | (204u << 8) | (255u << 16))              // frag:125-126: (178, 204, 255) / 255, weight 0
+
+__global__ void k_shade_tables(uint32_t* rgb, uint8_t* alpha)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < 65536u) { rgb[i] = shade_rgb(i); alpha[i] = (uint8_t)shade_alpha(i); }
+}
+void launch_shade_tables(uint32_t* rgb, uint8_t* alpha, cudaStream_t st) { k_shade_tables<<<256, 256, 0, st>>>(rgb, alpha); }
+
+__device__ __forceinline__ uint32_t unwarp_shade(const UnwarpParams& P, uint32_t t)
+{
+	if (((t >> 16) & 255u) == 255u) return RLERC_SKY_RGBA;                // c.b == 1.0: the sky sentinel (frag:89)
+	return __ldg(P.shade_rgb + (t & 0xffffu)) | ((uint32_t)__ldg(P.shade_alpha + (t >> 16)) << 24);
 }
 
-void launch_unwarp(const UnwarpParams& p, cudaStream_t st)
+// TEXELS: write (iy << 16) | ix instead of the colour (rlerc_debug_unwarp_texels: per-pixel texel parity against the oracle)
+template <bool TEXELS>
+__global__ void __launch_bounds__(32 * RLERC_UNWARP_WARPS, RLERC_UNWARP_MINB) k_unwarp(const __grid_constant__ UnwarpParams P)
+{
+	// the tile's column and row invariants, computed once per block
+	constexpr int TW = RLERC_UNWARP_WARPS * RLERC_UNWARP_QW * 4;     // tile width in pixels
+	__shared__ UnwarpCol s_col[TW];
+	__shared__ UnwarpRow s_row[RLERC_UNWARP_TROWS];
+	const int lane = threadIdx.x;
+	const int tid = threadIdx.y * 32 + lane;
+	const int tile_px = (int)blockIdx.x * TW, tile_row = P.row_begin + (int)blockIdx.y * RLERC_UNWARP_TROWS;
+	for (int i = tid; i < TW + RLERC_UNWARP_TROWS; i += 32 * RLERC_UNWARP_WARPS)
+	{
+		if (i < TW) unwarp_col(P, tile_px + i, s_col[i]);
+		else unwarp_row(P, P.H - 1 - (tile_row + i - TW), s_row[i - TW]);     // GL row
+	}
+	__syncthreads();
+	const int cx = ((int)threadIdx.y * RLERC_UNWARP_QW + (lane % RLERC_UNWARP_QW)) * 4;   // first pixel of my group of 4, in the tile
+	const int ry = lane / RLERC_UNWARP_QW;
+	const int px0 = tile_px + cx, rowi = tile_row + ry;
+	if (px0 >= P.W || rowi >= P.row_end) return;
+	const bool vec = (px0 + 3 < P.W) && ((P.W & 3) == 0);
+	const UnwarpRow rw = s_row[ry];
+	uint32_t out[4];
+	const uint32_t* src[4];
+	bool take[4];
+	#pragma unroll
+	for (int k = 0; k < 4; k++)
+	{
+		int iy, ix;
+		if (P.generic) unwarp_texel_generic(P, px0 + k, P.H - 1 - rowi, iy, ix);
+		else unwarp_texel(P, s_col[cx + k], rw, iy, ix);
+		take[k] = px0 + k < P.W;
+		if (P.ray_end >= 0 && (iy < P.ray_begin || iy >= P.ray_end)) take[k] = false;          // slice mode
+		const uint32_t* base = P.warp;
+		if (P.slice_n > 1)
+		{
+			const int owner = (iy / P.slice_block) % P.slice_n;
+			if (P.peer_n > 1) base = P.warp_peer[owner];                                       // pull over NVLink
+			else if (owner != P.slice_rank) take[k] = false;                                   // interleaved slice mode
+		}
+		src[k] = base + (size_t)iy * P.RS + ix;
+		if (TEXELS) out[k] = ((uint32_t)iy << 16) | (uint32_t)ix;
+	}
+	if (!TEXELS)
+	{
+		uint32_t t[4];
+		// all four gathers in flight before the first is used.  Read-only path (L1) also for peer memory: another GPU
+		// rewrites it between frames, never during this kernel, and L1 does not outlive a kernel
+		#pragma unroll
+		for (int k = 0; k < 4; k++) t[k] = take[k] ? __ldg(src[k]) : 0u;
+		#pragma unroll
+		for (int k = 0; k < 4; k++) out[k] = take[k] ? unwarp_shade(P, t[k]) : 0u;
+	}
+	uint32_t* dst = reinterpret_cast<uint32_t*>(P.rgba) + (size_t)rowi * P.W + px0;
+	if (vec) *reinterpret_cast<uint4*>(dst) = make_uint4(out[0], out[1], out[2], out[3]);
+	else for (int k = 0; k < 4 && px0 + k < P.W; k++) dst[k] = out[k];
+}
+
+void launch_unwarp(const UnwarpParams& p, cudaStream_t st, bool texels)
 {
 	const int rows = p.row_end - p.row_begin;
 	if (rows <= 0) return;
 	const int quads = (p.W + 3) / 4;
-	dim3 block(64, 1, 1);
-	dim3 grid((quads + 63) / 64, rows, 1);
-	k_unwarp<<<grid, block, 0, st>>>(p);
+	const int qpb = RLERC_UNWARP_QW * RLERC_UNWARP_WARPS;
+	dim3 block(32, RLERC_UNWARP_WARPS, 1);
+	dim3 grid((quads + qpb - 1) / qpb, (rows + RLERC_UNWARP_TROWS - 1) / RLERC_UNWARP_TROWS, 1);
+	if (texels) k_unwarp<true><<<grid, block, 0, st>>>(p);
+	else k_unwarp<false><<<grid, block, 0, st>>>(p);
 }
 
 

@@ -76,6 +76,13 @@ struct UnwarpParams {
 	int row_begin, row_end;
 	int ray_begin, ray_end;  // slice mode (ray_end < 0: off)
 	int slice_block, slice_n, slice_rank;   // interleaved slice mode (slice_n <= 1: off)
+	// multi-GPU pull mode (csrc/group.cu): peer_n == slice_n > 1, warp_peer[g] = GPU g's warped buffer (peer mapping);
+	// every pixel of the rows is produced, its texel loaded from the GPU that traversed its ray plane
+	int peer_n;
+	const uint32_t* warp_peer[8];
+	const uint32_t* shade_rgb;   // [65536] colour of every attribute value (k_shade_tables)
+	const uint8_t* shade_alpha;  // [65536] smoothing weight of every depth value
+	int generic;             // evaluate the shader's texel arithmetic statement by statement (vanishing point beyond 1e6, kernels.cu)
 };
 
 struct SoftParams {
@@ -96,7 +103,8 @@ size_t traverse_dda_state_bytes(const TraverseParams& p);
 size_t traverse_dda_progress_bytes(const TraverseParams& p);
 void launch_traverse_chunk(const TraverseParams& p, bool ids, int wpb, cudaStream_t st); // traverse_chunk.cu
 size_t traverse_ring_bytes(int rays);
-void launch_unwarp(const UnwarpParams& p, cudaStream_t st);
+void launch_unwarp(const UnwarpParams& p, cudaStream_t st, bool texels = false);
+void launch_shade_tables(uint32_t* rgb, uint8_t* alpha, cudaStream_t st);
 void launch_fill_u32(uint32_t* p, uint32_t v, size_t n, cudaStream_t st);
 void launch_read_u4(const void* p, size_t bytes, int iters, uint32_t* sink, cudaStream_t st);
 

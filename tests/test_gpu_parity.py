@@ -558,3 +558,160 @@ def test_more_ray_planes_than_buffer_rows(R, rb, gpu, scene_small):
     gpu.render(rm, cfg)
     assert np.array_equal(gpu.read_warp(cfg), want)
 
+
+
+def _texels(R, gpu, rm, cfg):
+    import torch
+    out = torch.zeros((cfg.height, cfg.width), dtype=torch.int32, device="cuda")
+    f = R.lib().rlerc_debug_unwarp_texels
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    assert f(gpu._c, C.byref(rm), C.byref(cfg), out.data_ptr()) == 0
+    gpu.sync()
+    t = out.cpu().numpy().view(np.uint32)
+    return np.stack([t >> 16, t & 0xffff], axis=-1).astype(np.int32)
+
+
+@pytest.mark.parametrize("wh", [(1024, 768), (1920, 1080), (3840, 2160), (7680, 4320), (641, 479)])
+def test_unwarp_texel_selection_equals_oracle(R, rb, gpu, scene_small, wh):
+    """k_unwarp evaluates the shader's texel arithmetic with row / column invariants hoisted and only the selected
+    branch of every step() blend (csrc/kernels.cu): the (ray plane, texel) it samples must equal the oracle's
+    statement-by-statement evaluation of colorize_buddha_soft.frag:19-85 at EVERY pixel of every BASELINE window,
+    for cameras in all quadrant configurations, incl. a level camera (vanishing point at infinity: generic path)."""
+    gpu.all_to_gpu(scene_small)
+    cfg = R.FrameConfig.default(*wh)
+    cams = list(camera_grid(-40.0)) if wh[0] <= 1920 else few_cameras(-40.0)
+    cams += [((10000.0, -40.0, 10000.0), (0.0, 0.3, 0.0)), ((10000.0, -40.0, 10000.0), (1e-7, 2.0, 0.0))]
+    warp = np.zeros((cfg.rays_casted, cfg.render_size), np.uint32)
+    for pos, rot in cams:
+        rm = R.RayMap(cfg).get_ray_map(pos, rot)
+        orm = oracle_raymap(rb, rm, scene_small)
+        _, want = rb.orc_unwarp(orm, cfg.width, cfg.height, cfg.render_size, cfg.rays_casted, cfg.rays_casted_res, warp, want_texels=True)
+        got = _texels(R, gpu, rm, cfg)
+        assert np.array_equal(got, want), (wh, rot, int((got != want).any(axis=-1).sum()))
+
+
+def test_unwarp_texel_selection_independent_restatement(R, gpu, scene_small):
+    """A second, independent restatement of the unwarp geometry (written from the shader's MEANING:
+    boolean segment selection, no step() arithmetic; numpy float32) picks the same texel as k_unwarp wherever its own
+    arithmetic is well away from a texel boundary."""
+    cfg = R.FrameConfig.default(1024, 768)
+    W, H, RS, RC, RCR = cfg.width, cfg.height, cfg.render_size, cfg.rays_casted, cfg.rays_casted_res
+    f = np.float32
+    for pos, rot in list(camera_grid(-40.0))[::3]:
+        rm = R.RayMap(cfg).get_ray_map(pos, rot)
+        got = _texels(R, gpu, rm, cfg)
+        vp = rm.vanishing_point_2d
+        vx, vy = f(1) - f(vp.x), (f(1) - f(vp.y) - f(rm.border)) * f(W) / f(H)
+        o1 = f(4) * f(rm.res[0]) / f(RCR); o2_ = o1 + f(4) * f(rm.res[1]) / f(RCR); o3 = o2_ + f(4) * f(rm.res[2]) / f(RCR)
+        ofs = [-f(rm.p_ofs_min[0]), -f(rm.p_ofs_min[1]) + o1, -f(rm.p_ofs_min[2]) + o2_, -f(rm.p_ofs_min[3]) + o3]
+        px, py = np.meshgrid(np.arange(W, dtype=f) + f(0.5), (H - 1 - np.arange(H, dtype=f)) + f(0.5))
+        with np.errstate(all="ignore"):
+            dx, dy = px / f(W) - vx, py / f(H) - vy
+            b = f(W - H) / f(2 * W)
+            upper, left = dy <= 0, dx <= 0
+            horiz = np.abs(dy) - np.abs(dx) * f(W) / f(H) <= 0
+            o2 = np.where(horiz, px, py) / f(W)
+            ang2 = dx * np.abs(f(1) - upper.astype(f) - vy) / dy + np.where(upper, f(1) - vx, vx)
+            ang3 = (dy * np.abs(f(1) - left.astype(f) - vx) / dx + np.where(left, f(1) - vy, vy)) * f(H) / f(W) + b
+            xp = np.where(horiz, ang3, ang2)
+            ty = np.where(~horiz, np.where(upper, ofs[1] + xp, ofs[0] + f(1) - xp), np.where(left, ofs[3] + xp, ofs[2] + f(1) - xp))
+            ty = ty * (f(RCR) / f(RC)) * f(0.25)
+            flip = not (rm.rotation.x > 0)
+            tx = np.where(~horiz, np.where(upper != flip, f(1) - (o2 + b), o2 + b), np.where(left != flip, f(1) - o2, o2))
+            fy, fx = ty * f(RC), tx * f(RS)
+        sure = np.isfinite(fy) & np.isfinite(fx) & (np.abs(fy - np.round(fy)) > 1e-2) & (np.abs(fx - np.round(fx)) > 1e-2)
+        iy = np.clip(np.floor(np.where(sure, fy, 0)), 0, RC - 1).astype(np.int32)
+        ix = np.clip(np.floor(np.where(sure, fx, 0)), 0, RS - 1).astype(np.int32)
+        assert sure.mean() > 0.9
+        assert np.array_equal(got[..., 0][sure], iy[sure]) and np.array_equal(got[..., 1][sure], ix[sure]), rot
+
+
+def _solo_frame(R, r, rm, cfg):
+    import torch
+    solo = torch.zeros((cfg.height, cfg.width, 4), dtype=torch.uint8, device="cuda:%d" % r.device)
+    r.set_lanes_per_ray(0)
+    r.frame_device(rm, cfg, 1, 1, 0, solo.data_ptr())
+    r.sync()
+    return solo.cpu().numpy()
+
+
+def test_group_of_one_and_multi_renderer(R, rb, gpu, scene_mid):
+    """The multi-GPU entry points with ONE member are the plain frame (runs on the single-GPU box): rlerc_group_*
+    with nranks = 1 and rlerc_create_multi([0]); frames in flight keep their order."""
+    gpu.all_to_gpu(scene_mid)
+    cfg = R.FrameConfig.default(640, 480)
+    cams = few_cameras(-100.0)
+    maps = []
+    for pos, rot in cams:
+        rm = R.RayMapGPU()
+        C.memmove(C.byref(rm), C.byref(R.RayMap(cfg).get_ray_map(pos, rot)), 896)
+        maps.append(rm)
+    want = [_solo_frame(R, gpu, rm, cfg) for rm in maps]
+    g = R.Group(gpu, cfg, 0, 1, depth=3)
+    hosts = [R.PinnedBuffer((cfg.height, cfg.width, 4)) for _ in maps]
+    tickets = [g.submit(rm, 0, hosts[i].array) for i, rm in enumerate(maps)]
+    for t in tickets:
+        g.wait(t)
+    g.sync()
+    for i in range(len(maps)):
+        assert np.array_equal(hosts[i].array, want[i]), i
+    g.close()
+    m = R.MultiRenderer([0], depth=2)
+    m.all_to_gpu(scene_mid)
+    for i, (pos, rot) in enumerate(cams):
+        hosts[i].array[:] = 0
+        m.render_frame(pos, rot, cfg, hosts[i].array)
+        assert np.array_equal(hosts[i].array, want[i]), i
+    m.close()
+    for h in hosts:
+        h.free()
+
+
+def test_multi_gpu_frame_in_one_process(R, rb, scene_mid):
+    """rlerc_create_multi on every GPU of the box (>= 2): slices traversed per GPU, bands unwarped per GPU with texels
+    pulled over NVLink, every GPU copies its band to the host: the frame equals the single-GPU frame bit for bit,
+    synchronous and with frames in flight."""
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs two GPUs")
+    r0 = R.Renderer(0)
+    r0.all_to_gpu(scene_mid)
+    for wh in ((1024, 768), (1920, 1080)):
+        cfg = R.FrameConfig.default(*wh)
+        cams = few_cameras(-100.0)
+        want = [_solo_frame(R, r0, R.RayMap(cfg).get_ray_map(p, q), cfg) for p, q in cams]
+        for nd in sorted({2, n}):
+            m = R.MultiRenderer(list(range(nd)), depth=3)
+            m.all_to_gpu(scene_mid)
+            hosts = [R.PinnedBuffer((cfg.height, cfg.width, 4)) for _ in cams]
+            for i, (p, q) in enumerate(cams):
+                m.render_frame(p, q, cfg, hosts[i].array)
+                assert np.array_equal(hosts[i].array, want[i]), (wh, nd, i)
+                hosts[i].array[:] = 0
+            tickets = [m.frame_submit(p, q, cfg, hosts[i].array) for i, (p, q) in enumerate(cams)]
+            for t in tickets:
+                m.frame_wait(t)
+            for i in range(len(cams)):
+                assert np.array_equal(hosts[i].array, want[i]), (wh, nd, i, "pipelined")
+            m.close()
+            for h in hosts:
+                h.free()
+    r0.close()
+
+
+def test_multi_gpu_frame_one_process_per_gpu(R):
+    """The same under torchrun, one process per GPU (CUDA IPC mappings): tools/group_probe.py compares the frame
+    assembled on rank 0 and every rank's band with single-GPU frames and exits non-zero on any difference."""
+    import subprocess
+    import sys
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(HERE)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(root, "tools", "group_probe.py"), "small", "12", "3"]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, (p.stdout[-2000:], p.stderr[-2000:])
+    assert "mismatches 0" in p.stdout
