@@ -11,14 +11,16 @@ value      pixel-rays/s = W*H*frames/s of the whole K-frame job, scene + buffers
            frames in flight per GPU (one stream and one set of frame buffers per slot), device-timed from a CUDA event
            in front of the first frame to one behind the last, max over ranks.  The job is repeated R times so that the
            timed region lasts >= 0.6 s (ms_per_step = total / (R*K); per-repeat times in `repeats`).  For N > 1 every
-           frame is split into interleaved ray-plane slices over all GPUs (north-star split) and composited on rank 0
-           with one NCCL reduce; the same method at every N.
+           frame is split into interleaved ray-plane slices over all GPUs (north-star split); every GPU unwarps its
+           band of rows, pulling texels from the owners' warped buffers over NVLink, and pushes the pixels into rank
+           0's frame (csrc/group.cu; `--compose reduce` = one NCCL reduce of whole images instead); the same
+           method at every N.
 latency    the same frames one at a time, L2 flushed (512 MiB write) before every frame, per-frame CUDA events:
            the round-1 `value` method, kept for comparison (mean / p50 / p99 / max).
 e2e        the same metric through the C ABI with HOST buffers: camera pose in, RGBA frame out in pinned host memory,
-           copies inside the timed region.  N = 1: rlerc_frame_submit / rlerc_frame_wait; N > 1: slices + NCCL
-           reduce_scatter, every rank copies its own rows of the finished frame into ONE host frame buffer shared by all
-           ranks (no rank-0 funnel).
+           copies inside the timed region.  N = 1: rlerc_frame_submit / rlerc_frame_wait; N > 1: rlerc_group_submit,
+           every rank copies the rows it produced into ONE host frame buffer shared by all ranks over its own PCIe
+           link (no rank-0 funnel).
 roofline   traversal kernel: algorithmic bytes per frame (8C + 2(E-C1) + 6P + 4K, DESIGN.md §5, counted by the
            instrumented kernel on 8 path frames) / its CUDA-event duration in the latency pass (kernel timed alone:
            burst peak), vs the measured HBM peak; L2 and DRAM traffic of the same launch from the committed ncu capture.
@@ -205,21 +207,19 @@ def pipelined_job(torch, pipe, raymaps, K, repeats, barrier):
 
 
 def sequential_job(torch, pipe, raymaps, frames, flush, timing_r=None):
-    """Frames one at a time on slot 0, L2 flushed before each, per-frame CUDA events (the round-1 `value` method).
+    """Frames one at a time, L2 flushed before each, CUDA events around each frame (the round-1 `value` method).
     Returns ([ms per frame], traversal ms sum, unwarp ms sum)."""
-    s = pipe.streams[0]
+    main = torch.cuda.current_stream()
     out, trav, unw = [], 0.0, 0.0
     for i in frames:
-        with torch.cuda.stream(s):
-            if flush is not None:
-                flush.fill_(i & 255)
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(s)
-            pipe.submit(i * pipe.depth, raymaps[i])          # always slot 0
-            if pipe.pending[0] is not None:
-                pipe.pending[0].wait()
-                pipe.pending[0] = None
-            b.record(s)
+        if flush is not None:
+            flush.fill_(i & 255)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(main)
+        pipe.start_after(a)
+        k = pipe.submit(i, raymaps[i])
+        pipe.finish_slot(k)
+        b.record(pipe.streams[k])
         b.synchronize()
         out.append(a.elapsed_time(b))
         if timing_r is not None:
@@ -249,18 +249,23 @@ def main():
     ap.add_argument("--lanes", type=int, default=0,
                     help="traversal kernel (rlerc_set_lanes_per_ray): 0 = automatic (k_traverse_f, or k_traverse_p for small launches), "
                          "65 = k_traverse_f, 68 = k_traverse_p, 1..32 = k_traverse<lanes>")
-    ap.add_argument("--inflight", type=int, default=4, help="frames in flight per GPU in the throughput measurements")
+    ap.add_argument("--inflight", type=int, default=0,
+                    help="frames in flight per GPU in the throughput measurements (0 = 4 on one GPU, 2 per GPU from 2 GPUs up: a slice of a frame "
+                         "is bound by its longest ray planes, not by the GPU, so the GPUs are kept busy by more frames in flight)")
     ap.add_argument("--min-seconds", type=float, default=0.6, help="the K-frame job is repeated until the timed region lasts this long")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-north-star", action="store_true", help="N > 1: skip the tiled4k slice-scaling block")
     ap.add_argument("--slice-block", type=int, default=32)
+    ap.add_argument("--compose", default="pull", choices=["pull", "reduce"],
+                    help="N > 1, slices: pull = unwarp bands with texels pulled over NVLink peer memory (csrc/group.cu, default); "
+                         "reduce = every GPU unwarps its own pixels of the whole window, one NCCL reduce(sum) to rank 0")
     ap.add_argument("--mp", default="slices", choices=["slices", "frames"],
                     help="N > 1: split every frame into ray-plane slices (north-star split, default) or deal whole frames to the GPUs")
     args = ap.parse_args()
     K, W = max(1, args.steps), max(3, args.warmup)
-    F = max(1, args.inflight)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    F = args.inflight if args.inflight > 0 else max(4, min(16, 2 * world))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     log = (lambda m: print("[bench r%d] %s" % (rank, m), file=sys.stderr, flush=True))
 
@@ -342,8 +347,14 @@ def main():
     scene_megabytes = scene.nbytes() / 1e6
     t0 = time.time()
     slices = world > 1 and args.mp == "slices"
-    pipe = MG.FramePipe(R, torch, local, scene, cfg, depth=F, rank=rank if slices else 0, world=world if slices else 1,
-                        dist=D if slices else None, block=args.slice_block, lanes=args.lanes, compose="reduce")
+    def make_pipe(scene_, cfg_, rank_, world_, dist_, dst=0, host=None, share_from=None):
+        if args.compose == "reduce" and world_ > 1:
+            return MG.FramePipe(R, torch, local, scene_, cfg_, depth=F, rank=rank_, world=world_, dist=dist_, block=args.slice_block,
+                                lanes=args.lanes, compose="reduce" if dst >= 0 else "bands", host=host, share_from=share_from)
+        return MG.GroupPipe(R, torch, local, scene_, cfg_, depth=F, rank=rank_, world=world_, dist=dist_, block=args.slice_block,
+                            lanes=args.lanes, dst=dst, host=host, share_from=share_from)
+
+    pipe = make_pipe(scene, cfg, rank if slices else 0, world if slices else 1, D if slices else None)
     log("replica uploaded, %d frame slots: %.1f s" % (F, time.time() - t0))
     r = pipe.r[0]
     poses = [path_pose(R, i, K, sy, imrodh) for i in range(K)]
@@ -379,7 +390,8 @@ def main():
         frames_done = int(t.cpu()[0])
     fps = frames_done / (th["ms_total"] / 1e3)
     value = WW * HH * fps / 1e6
-    launches = 3 * th["repeats"] * myK                 # k_dda_states + traversal + k_unwarp per frame on this rank
+    # k_dda_states + traversal + k_unwarp per frame on this rank (+ two k_group_barrier with the peer-memory compositor)
+    launches = (5 if (slices and args.compose == "pull") else 3) * th["repeats"] * myK
 
     # ---- latency: one frame at a time, L2 flushed before each (the round-1 `value` method)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
@@ -394,7 +406,7 @@ def main():
         tot = allmax(sum(per))
         lat = dict(dist_stats(per), frames=KL, value=WW * HH * KL / (tot / 1e3) / 1e6, frames_per_s=KL / (tot / 1e3),
                    how="one frame at a time, 512 MiB L2 flush before each, CUDA events around each frame (%s), this rank; value from the max over ranks of the summed frame times"
-                       % ("traversal slice + unwarp + NCCL reduce" if slices else "k_dda_states + traversal + unwarp"))
+                       % (("traversal slice + barrier + unwarp band with NVLink pull + barrier" if args.compose == "pull" else "traversal slice + unwarp + NCCL reduce") if slices else "k_dda_states + traversal + unwarp"))
         trav_ms, unw_ms = allmax(trav_ms), allmax(unw_ms)
     r.set_timing(False)
     kernel_used = r.last_kernel
@@ -406,15 +418,16 @@ def main():
         checks = [0, K // 2]
         ok = True
         for i in checks:
-            pipe.submit(0, raymaps[i])
+            k_ = pipe.submit(0, raymaps[i])
+            pipe.finish_slot(k_)
             pipe.drain()
             barrier()
             if rank == 0:
-                got = pipe.image(0).clone()
-                solo = torch.zeros_like(got)
+                got, _, _ = pipe.image_numpy(k_)
+                solo = torch.zeros((HH, WW, 4), dtype=torch.uint8, device="cuda")
                 r.frame_device(raymaps[i], cfg, 1, 1, 0, solo.data_ptr())
                 torch.cuda.synchronize()
-                ok = ok and bool(torch.equal(got, solo))
+                ok = ok and bool(np.array_equal(got, solo.cpu().numpy()))
             barrier()
         composite_identical = ok if rank == 0 else None
 
@@ -531,8 +544,9 @@ def main():
         how = "pinned host RGBA out, camera pose in; rlerc_frame_submit/wait, %d frames in flight, one stream per frame slot" % F
     else:
         # ONE host frame ring shared by all ranks; every rank copies its own part of every frame into it over its own PCIe link
-        rows = MG.band_rows(HH, world) if slices else HH
-        shape = (F if slices else F * world, rows * world if slices else HH, WW, 4)
+        pull = args.compose == "pull"
+        rows = HH if (pull or not slices) else MG.band_rows(HH, world) * world
+        shape = (F if slices else F * world, rows, WW, 4)
         nbytes = int(np.prod(shape))
         name = [None]
         if rank == 0:
@@ -543,9 +557,8 @@ def main():
         rc = torch.cuda.cudart().cudaHostRegister(host.data_ptr(), nbytes, 0)
         if int(rc) != 0:
             log("cudaHostRegister failed (%s): the copies into the shared host frame will be synchronous" % rc)
-        pipe2 = MG.FramePipe(R, torch, local, scene, cfg, depth=F, rank=rank if slices else 0, world=world if slices else 1,
-                             dist=D if slices else None, block=args.slice_block, lanes=args.lanes, compose="bands" if slices else "none",
-                             host=host if slices else host[rank * F:(rank + 1) * F], share_from=r)
+        pipe2 = make_pipe(scene, cfg, rank if slices else 0, world if slices else 1, D if slices else None, dst=-1,
+                          host=host if slices else host[rank * F:(rank + 1) * F], share_from=r)
         maps2 = raymaps if slices else raymaps[rank::world]
         # host-side frame setup (get_ray_map) is inside the timed region, as in the single-GPU e2e
         for i in range(max(W, 2 * F)):
@@ -556,10 +569,11 @@ def main():
         my_poses = poses if slices else poses[rank::world]
         t0 = time.perf_counter()
         n = 0
+        last_slot = 0
         for rep in range(reps):
             for i in range(len(my_poses)):
                 rm = R.RayMap(cfg).get_ray_map(my_poses[i][0], my_poses[i][1])
-                pipe2.submit(n, rm)
+                last_slot = pipe2.submit(n, rm)
                 n += 1
         pipe2.drain()
         barrier()
@@ -568,14 +582,13 @@ def main():
         # the last frame of the job, as it landed in host memory, against rank 0's own single-GPU frame
         checksum = 0
         if slices:
-            last = (n - 1) % F
             if rank == 0:
                 solo = torch.zeros((HH, WW, 4), dtype=torch.uint8, device="cuda")
                 r.frame_device(raymaps[K - 1], cfg, 1, 1, 0, solo.data_ptr())
                 torch.cuda.synchronize()
-                same = bool(torch.equal(host[last, :HH], solo.cpu()))
+                same = bool(torch.equal(host[last_slot, :HH], solo.cpu()))
                 composite_identical = bool(composite_identical) and same
-                checksum = int(host[last, :HH][::16, ::16].to(torch.int64).sum())
+                checksum = int(host[last_slot, :HH][::16, ::16].to(torch.int64).sum())
         barrier()
         pipe2.close()
         torch.cuda.cudart().cudaHostUnregister(host.data_ptr())
@@ -586,7 +599,8 @@ def main():
                 os.unlink(name[0])
             except OSError:
                 pass
-        how = ("per-rank ray-plane slices, NCCL reduce_scatter into row bands, every rank copies its band into ONE host frame shared by all ranks (%d PCIe links), %d frames in flight"
+        how = (("rlerc_group_submit: per-rank ray-plane slices, every rank unwarps its band of rows (texels pulled over NVLink) and copies it into ONE host frame shared by all ranks (%d PCIe links), %d frames in flight"
+                if pull else "per-rank ray-plane slices, NCCL reduce_scatter into row bands, every rank copies its band into ONE host frame shared by all ranks (%d PCIe links), %d frames in flight")
                % (world, F)) if slices else ("whole frames per rank, every rank copies its frames into the shared host ring itself, %d frames in flight" % F)
     e2e_fps = e2e_frames / e2e_wall
     e2e = {"value": WW * HH * e2e_fps / 1e6, "unit": "Mrays/s", "frames_per_s": e2e_fps,
@@ -611,8 +625,7 @@ def main():
                 rm = R.RayMapGPU()
                 C.memmove(C.byref(rm), C.byref(R.RayMap(cfg4).get_ray_map(p, q)), 896)
                 maps4.append(rm)
-            pn = MG.FramePipe(R, torch, local, scene4, cfg4, depth=F, rank=rank, world=world, dist=D, block=args.slice_block,
-                              lanes=args.lanes, compose="reduce")
+            pn = make_pipe(scene4, cfg4, rank, world, D)
             tn = throughput(pn, maps4, K4, 0.4)
             flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
             barrier()
@@ -620,23 +633,23 @@ def main():
             barrier()
             seq_n = allmax(sum(per)) / K4
             ident = None
-            pn.submit(0, maps4[0])
+            k_ = pn.submit(0, maps4[0])
+            pn.finish_slot(k_)
             pn.drain()
             barrier()
             if rank == 0:
-                got = pn.image(0).clone()
-                solo = torch.zeros_like(got)
+                got, _, _ = pn.image_numpy(k_)
+                solo = torch.zeros((H4, W4, 4), dtype=torch.uint8, device="cuda")
                 pn.r[0].frame_device(maps4[0], cfg4, 1, 1, 0, solo.data_ptr())
                 torch.cuda.synchronize()
-                ident = bool(torch.equal(got, solo))
+                ident = bool(np.array_equal(got, solo.cpu().numpy()))
                 del got, solo
             barrier()
             # rank 0 alone on the same frames (the other ranks wait at the barrier)
             t1 = None
             seq_1 = None
             if rank == 0:
-                p1 = MG.FramePipe(R, torch, local, scene4, cfg4, depth=F, rank=0, world=1, dist=None, lanes=args.lanes,
-                                  compose="none", share_from=pn.r[0])
+                p1 = make_pipe(scene4, cfg4, 0, 1, None, share_from=pn.r[0])
                 nb = (lambda: torch.cuda.synchronize())
                 for i in range(2 * F):
                     p1.submit(i, maps4[i % K4])
@@ -653,7 +666,7 @@ def main():
             del flush
             if rank == 0:
                 north = {"workload": "tiled4k", "scene": name4, "scene_mb": scene4.nbytes() / 1e6, "window": [W4, H4], "frames": K4,
-                         "split": "interleaved blocks of %d ray planes over %d GPUs, full replica each, NCCL reduce to rank 0" % (args.slice_block, world),
+                         "split": "interleaved blocks of %d ray planes over %d GPUs, full replica each, %s" % (args.slice_block, world, "unwarp bands with NVLink pull, frame assembled on rank 0" if args.compose == "pull" else "NCCL reduce to rank 0"),
                          "throughput": {"frames_in_flight": F, "ms_per_frame_n": tn["ms_per_frame"], "ms_per_frame_1": t1,
                                         "fps_n": 1e3 / tn["ms_per_frame"], "fps_1": 1e3 / t1, "speedup": t1 / tn["ms_per_frame"]},
                          "latency": {"ms_per_frame_n": seq_n, "ms_per_frame_1": seq_1, "speedup": seq_1 / seq_n,
@@ -695,8 +708,9 @@ def main():
                               "%d such frames are in flight against a 126 MB L2; the flushed, one-frame-at-a-time figure is `latency`"
                               % (scene_megabytes, cfg.rays_casted * cfg.render_size * 4 / 1e6, F),
                         "parallelism": ("1 GPU" if world == 1 else
-                                        ("every frame split into ray-plane slices x%d (interleaved blocks of %d), full replica per GPU, one NCCL reduce per frame to rank 0"
-                                         % (world, args.slice_block) if slices else
+                                        ("every frame split into ray-plane slices x%d (interleaved blocks of %d), full replica per GPU, %s"
+                                         % (world, args.slice_block, "every GPU unwarps its band of rows with texels pulled from the owners over NVLink peer memory and pushes the pixels into rank 0's frame; flag barriers in peer memory, no collective moves pixel data"
+                                            if args.compose == "pull" else "one NCCL reduce per frame to rank 0") if slices else
                                          "whole frames dealt round-robin to %d GPUs (full replica each); frames stay on the GPU that rendered them" % world))},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "latency": lat, "roofline": roof, "parity": parity}
         if composite_identical is not None:

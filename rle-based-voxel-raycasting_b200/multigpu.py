@@ -139,6 +139,16 @@ class FramePipe:
                 self.host[k].copy_(self.rgba[k], non_blocking=True)
         return k
 
+    def finish_slot(self, k):
+        """Make slot k's stream wait for its compositing collective."""
+        if self.pending[k] is not None:
+            with self.torch.cuda.stream(self.streams[k]):
+                self.pending[k].wait()
+            self.pending[k] = None
+
+    def image_numpy(self, k):
+        return self.image(k).cpu().numpy(), 0, self.cfg.height
+
     def drain(self, onto=None):
         """Make `onto` (default: the current stream) wait for everything submitted so far."""
         cur = onto if onto is not None else self.torch.cuda.current_stream()
@@ -164,6 +174,64 @@ class FramePipe:
         self.torch.cuda.synchronize()
         for x in reversed(self.r):
             x.close()
+
+
+class GroupPipe:
+    """`depth` frames in flight through the library's own multi-GPU path (csrc/group.cu, include/rlerc.h "multi-GPU"):
+    every rank traverses its interleaved ray-plane slices and produces its band of window rows with the texels pulled
+    from the owners' warped buffers over NVLink; flag barriers in peer memory; no collective moves pixel data.
+    Same interface as FramePipe.  dst >= 0: the finished frame is assembled on rank dst; dst = -1: every rank keeps
+    its band (and copies it into `host`, a [slots, H, W, 4] uint8 host tensor shared by all ranks, when given)."""
+
+    def __init__(self, R, torch, device, scene, cfg, depth=4, rank=0, world=1, dist=None, block=DEFAULT_BLOCK, lanes=0,
+                 dst=0, host=None, share_from=None):
+        import numpy as np
+        self.np, self.torch, self.dist, self.cfg = np, torch, dist, cfg
+        self.rank, self.world, self.block, self.depth, self.dst, self.host = rank, world, block, depth, dst, host
+        r = R.Renderer(device)
+        if share_from is not None:
+            r.share_scene(share_from)
+        else:
+            r.all_to_gpu(scene)
+        r.set_lanes_per_ray(lanes)
+        self.r = [r]
+        self.g = R.Group(r, cfg, rank, world, depth=depth, block=block)
+        if world > 1:
+            self.g.connect_distributed(torch, dist)
+        dev = torch.device("cuda", device)
+        self.streams = [torch.cuda.ExternalStream(self.g.stream(k), device=dev) for k in range(depth)]
+        self.pending = [None] * depth
+        self.last_ticket = -1
+
+    def submit(self, i, raymap_gpu):
+        """Enqueue the next frame (asynchronous; `i` is ignored: frames go to the slots in turn). Returns its slot."""
+        host = None
+        if self.host is not None:
+            host = self.host[(self.last_ticket + 1) % self.depth].data_ptr()
+        self.last_ticket = self.g.submit(raymap_gpu, self.dst, host)
+        return self.last_ticket % self.depth
+
+    def finish_slot(self, k):
+        pass                                     # barriers and copies are stream-ordered inside the slot
+
+    def drain(self, onto=None):
+        cur = onto if onto is not None else self.torch.cuda.current_stream()
+        for s in self.streams:
+            cur.wait_stream(s)
+
+    def start_after(self, event):
+        for s in self.streams:
+            s.wait_event(event)
+
+    def image_numpy(self, k):
+        """Slot k's [H][W][4] image on this rank as numpy, and the rows this rank produced."""
+        ptr, a, b = self.g.image(k)
+        return self.r[0].download(ptr, (self.cfg.height, self.cfg.width, 4), self.np.uint8), a, b
+
+    def close(self):
+        self.torch.cuda.synchronize()
+        self.g.close()
+        self.r[0].close()
 
 
 class FrameFarm:

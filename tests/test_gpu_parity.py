@@ -713,5 +713,5 @@ def test_multi_gpu_frame_one_process_per_gpu(R):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1",
            "--master-port", "29533", os.path.join(root, "tools", "group_probe.py"), "small", "12", "3"]
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
-    assert p.returncode == 0, (p.stdout[-2000:], p.stderr[-2000:])
+    assert p.returncode == 0, (p.stdout[-3000:], p.stderr[-1500:])
     assert "mismatches 0" in p.stdout

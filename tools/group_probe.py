@@ -13,6 +13,11 @@ rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_S
 workload = sys.argv[1] if len(sys.argv) > 1 else "small"
 K = int(sys.argv[2]) if len(sys.argv) > 2 else 24
 depth = int(sys.argv[3]) if len(sys.argv) > 3 else 4
+import traceback
+def _excepthook(t, v, tb):
+    print("rank %d FAILED: %s" % (rank, "".join(traceback.format_exception(t, v, tb))[-1500:]), flush=True)
+    sys.__excepthook__(t, v, tb)
+sys.excepthook = _excepthook
 torch.cuda.set_device(local)
 if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -60,7 +65,9 @@ def run(n_rep, dst):
     g.sync(); barrier()
     return (time.perf_counter() - t0) / (n_rep * K)
 run(1, 0)
-reps = max(1, int(0.5 / max(run(1, 0) * K, 1e-4)))
+reps_t = torch.tensor([max(1, int(0.5 / max(run(1, 0) * K, 1e-4)))], device="cuda")
+if world > 1: dist.all_reduce(reps_t, op=dist.ReduceOp.MAX)       # every member has to submit the SAME frames
+reps = int(reps_t.cpu()[0])
 ms_push = 1e3 * run(reps, 0); ms_band = 1e3 * run(reps, -1)
 # ---- parity again after many generations of every slot (stale data in any cache would show here)
 for i in (1, K - 1):
