@@ -250,7 +250,7 @@ def main():
                     help="traversal kernel (rlerc_set_lanes_per_ray): 0 = automatic (k_traverse_f, or k_traverse_p for small launches), "
                          "65 = k_traverse_f, 68 = k_traverse_p, 1..32 = k_traverse<lanes>")
     ap.add_argument("--inflight", type=int, default=0,
-                    help="frames in flight per GPU in the throughput measurements (0 = 4 on one GPU, 2 per GPU from 2 GPUs up: a slice of a frame "
+                    help="frames in flight per GPU in the throughput measurements (0 = 8 up to four GPUs, 2 per GPU beyond: a slice of a frame "
                          "is bound by its longest ray planes, not by the GPU, so the GPUs are kept busy by more frames in flight)")
     ap.add_argument("--min-seconds", type=float, default=0.6, help="the K-frame job is repeated until the timed region lasts this long")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -265,7 +265,7 @@ def main():
     K, W = max(1, args.steps), max(3, args.warmup)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    F = args.inflight if args.inflight > 0 else max(4, min(16, 2 * world))
+    F = args.inflight if args.inflight > 0 else max(8, min(16, 2 * world))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     log = (lambda m: print("[bench r%d] %s" % (rank, m), file=sys.stderr, flush=True))
 

@@ -66,7 +66,7 @@ struct rlerc_ctx {
 	cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
 	bool ev_valid[2] = { false, false };
 	// pipeline
-	static const int kSlots = 6;        // frames in flight in rlerc_frame_submit (each on its own stream)
+	static const int kSlots = 8;        // frames in flight in rlerc_frame_submit (each on its own stream)
 	FrameSlot slot[kSlots];
 	int next_ticket = 0;
 };
