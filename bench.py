@@ -502,8 +502,16 @@ def main():
                 roof["l2"] = {"achieved": a, "peak": l2peak["l2_read_gbs"], "unit": "GB/s", "frac": a / l2peak["l2_read_gbs"],
                               "traffic": cap["l2_bytes_per_launch"],
                               "how": "lts__t_sectors x 32 B of the committed ncu capture / its gpu__time_duration; peak = tools/l2_peak.py on this pool's B200 (profiles/l2_peak.json)"}
-            if cap.get("reference_kernel_on_this_gpu"):
-                roof["reference_kernel_on_this_gpu"] = cap["reference_kernel_on_this_gpu"]
+        # same-GPU comparator: the reference's own cudaRender compiled for sm_100a (oracle/_ref/libref_cuda.so), config 1
+        if world == 1 and args.workload.startswith("imrodh"):
+            try:
+                from oracle import refbind as rb_
+                if rb_.have_ref_cuda():
+                    sys.path.insert(0, os.path.join(ROOT, "tools"))
+                    import ref_cuda_kernel
+                    roof["reference_kernel_on_this_gpu"] = ref_cuda_kernel.compare(R, r, sy, imrodh)
+            except Exception as e:
+                roof["reference_kernel_on_this_gpu"] = {"error": repr(e)[:200]}
 
     # ---- e2e through the C ABI with host buffers (pinned), copies inside the timed region
     barrier()

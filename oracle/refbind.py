@@ -58,6 +58,23 @@ def have_ref():
                for n in ("libref_render.so", "libref_render_bench.so", "libref_host.so"))
 
 
+def have_ref_cuda():
+    """The reference's own CUDA kernel compiled for sm_100a (oracle/ref_cuda_tu.cu): the same-GPU comparator."""
+    return os.path.exists(os.path.join(REF_DIR, "libref_cuda.so"))
+
+
+def ref_cuda_frame(rm_device_maps, d_out, repeats=5, nofma=False):
+    """cudaRender (R/src/Cuda_Main.cu:150-181,183-271) on the current CUDA device.  rm_device_maps: RayMapGPU whose
+    map4_gpu hold DEVICE pointers; d_out: device pointer of 4096 x 1024 uint32.  Returns (ms kernel, ms whole call)."""
+    lib = _load("libref_cuda_nofma.so" if nofma else "libref_cuda.so")
+    lib.refcuda_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    k, c = C.c_float(), C.c_float()
+    rc = lib.refcuda_frame(C.byref(rm_device_maps), d_out, repeats, C.byref(k), C.byref(c))
+    if rc:
+        raise RuntimeError("refcuda_frame rc=%d" % rc)
+    return k.value, c.value
+
+
 _libs = {}
 
 

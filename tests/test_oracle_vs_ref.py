@@ -181,3 +181,19 @@ def test_more_ray_planes_than_buffer_rows(R, rb, need_ref, scene_small):
     ref, port, ids, cnt = _both(R, rb, scene_small, cfg, pos, rot)
     assert ref.shape == port.shape == (cfg.rays_casted, cfg.render_size)
     assert np.array_equal(ref, port) and cnt["pixels"] > 0
+
+
+def test_reference_cuda_kernel_comparator_builds(rb, have_ref):
+    """oracle/_ref/libref_cuda*.so: the reference's own cudaRender compiled for sm_100a from the sources in place
+    (oracle/Makefile refcuda); here only that it was built and exports its entry points (it needs a GPU to run:
+    tools/ref_cuda_kernel.py, bench.py roofline.reference_kernel_on_this_gpu)."""
+    import ctypes as C
+    import os
+    if not have_ref:
+        pytest.skip("oracle/_ref not built (no /root/reference)")
+    assert rb.have_ref_cuda()
+    for name in ("libref_cuda.so", "libref_cuda_nofma.so"):
+        lib = C.CDLL(os.path.join(rb.REF_DIR, name))
+        assert lib.refcuda_render_size() == 1024 and lib.refcuda_rays_casted() == 4096      # R/src/core.h:5-6 as shipped
+        assert lib.refcuda_sizeof_render() > 896 + 4096 * 20                               # RayMap_GPU + perf[RAYS_CASTED]
+        assert hasattr(lib, "refcuda_frame")
