@@ -162,16 +162,18 @@ int fill_unwarp(const rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_co
 	return RLERC_OK;
 }
 
-// 0 = automatic: the production kernel k_traverse_f (one warp per ray plane), except for launches whose ray planes are
-// all resident at once in the paired kernel (12 per SM: filter warp + consume warp per ray plane, k_traverse_p).
-// Such a launch is bound by the serial chain of its slowest ray planes, which the pair shortens (measured on B200:
-// 1/4 of a 4K frame 0.79 -> 0.67 ms, 1/8 0.79 -> 0.59 ms; a full frame is throughput-bound and 15-30 % slower on
-// the pair).  That is the multi-GPU slice mode from 4 GPUs up and small windows.  65 = k_traverse_f always,
-// 68 = k_traverse_p always, 64 = k_traverse_w, 66/67 = k_traverse_c, else k_traverse<lanes>.
+// 0 = automatic: the production kernel k_traverse_f (one warp per ray plane), except for launches so small that every
+// ray plane is resident at once with warps to spare (at most 5 per SM): such a launch is bound by the serial chain of its
+// slowest ray planes, which the four-role kernel k_traverse_q (filter / project / resolve / shade warps per ray plane)
+// shortens (measured on B200, round 2: 1/8 of a 1080p frame 0.42 -> 0.34 ms, 1/8 of a 4K frame 0.64 -> 0.56 ms, 1/16
+// 0.66 -> 0.48 ms; a full frame is throughput-bound and 1.7x slower on it).  That is the multi-GPU slice mode at 8 GPUs,
+// one frame at a time, and small windows.  Never when frames overlap (pipelined): then the GPU is throughput-bound.
+// 65 = k_traverse_f always, 68 = k_traverse_p (two warps per ray plane), 69 = k_traverse_q always, 64 = k_traverse_w,
+// 66/67 = k_traverse_c, else k_traverse<lanes>.
 int pick_lanes(const rlerc_ctx* c, int rays, bool ids)
 {
 	if (c->lanes != 0) return c->lanes;
-	if (!ids && !c->pipelined && c->dda_mode != 99 && rays > 0 && rays <= 12 * c->sm_count) return 68;
+	if (!ids && !c->pipelined && c->dda_mode != 99 && rays > 0 && rays <= 5 * c->sm_count) return 69;
 	return 0;
 }
 
@@ -320,9 +322,9 @@ int rlerc_has_variants(void) { return RLERC_VARIANTS ? 1 : 0; }
 
 int rlerc_set_lanes_per_ray(rlerc_ctx* c, int lanes)
 {
-	if (!c || !(lanes == 0 || lanes == 1 || lanes == 2 || lanes == 4 || lanes == 8 || lanes == 16 || lanes == 32 || (lanes >= 64 && lanes <= 68)))
+	if (!c || !(lanes == 0 || lanes == 1 || lanes == 2 || lanes == 4 || lanes == 8 || lanes == 16 || lanes == 32 || (lanes >= 64 && lanes <= 69)))
 	{
-		set_error("lanes per ray must be 0,1,2,4,8,16,32 or a kernel code 64..68");
+		set_error("lanes per ray must be 0,1,2,4,8,16,32 or a kernel code 64..69");
 		return RLERC_ERR_ARG;
 	}
 	if (!RLERC_VARIANTS && (lanes == 64 || lanes == 66 || lanes == 67))
@@ -386,7 +388,7 @@ int rlerc::render_impl(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_c
 	}
 	TraverseParams P;
 	if ((rc = fill_traverse(c, rm, cfg, ray_begin, ray_end, d_warp, P))) return rc;
-	if (cfg->flags != 0 && !(c->lanes == 0 || c->lanes == 65 || c->lanes == 68))
+	if (cfg->flags != 0 && !(c->lanes == 0 || c->lanes == 65 || c->lanes == 68 || c->lanes == 69))
 	{
 		set_error("frame config flags (CLIPREGION / HEIGHT_COLOR) are implemented by the production traversal kernels only (lanes_per_ray = 0, 65, 68)");
 		return RLERC_ERR_ARG;
@@ -415,7 +417,7 @@ int rlerc::render_impl(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_c
 #endif
 	const int launch_rays = (P.slice_n > 1) ? owned_count(P.ray_end, P.slice_block, P.slice_n, P.slice_rank) : P.ray_end - P.ray_begin;
 	const int lanes = pick_lanes(c, launch_rays, ids);
-	const bool production = lanes == 0 || lanes == 65 || lanes == 68;
+	const bool production = lanes == 0 || lanes == 65 || lanes == 68 || lanes == 69;
 	if (production)
 	{
 		// DDA states of this launch's ray planes: sized for the most ray planes a launch of this configuration can have,
@@ -443,7 +445,7 @@ int rlerc::render_impl(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_c
 	if (production) launch_dda_states(P, c->stream);
 	launch_traverse(P, lanes, ids, c->stream);
 	if (c->timing) { CK(cudaEventRecord(c->ev[1], c->stream)); c->ev_valid[0] = true; }
-	c->last_kernel = (lanes == 0 || lanes == 65) ? (ids ? "k_traverse_f<ids>" : "k_traverse_f") : lanes == 68 ? (ids ? "k_traverse_f<ids>" : "k_traverse_p")
+	c->last_kernel = (lanes == 0 || lanes == 65) ? (ids ? "k_traverse_f<ids>" : "k_traverse_f") : lanes == 68 ? (ids ? "k_traverse_f<ids>" : "k_traverse_p") : lanes == 69 ? (ids ? "k_traverse_f<ids>" : "k_traverse_q")
 	               : lanes == 64 ? "k_traverse_w" : lanes == 66 ? "k_traverse_c<3>" : lanes == 67 ? "k_traverse_c<7>" : "k_traverse<G>";
 	CK(cudaGetLastError());
 	return RLERC_OK;
@@ -478,6 +480,8 @@ int rlerc_debug_profile_rays(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_f
 	if (!c || !d_out) return RLERC_ERR_ARG;
 	const int saved_mode = c->dda_mode, saved_lanes = c->lanes;
 	c->dda_mode = 99; c->lanes = 0;
+	// RLERC_PROF_Q=1: the four-role kernel's own timers (a library built with -DRLERC_Q_PROF=1, tools/quad_profile.py)
+	if (getenv("RLERC_PROF_Q")) { c->dda_mode = saved_mode; c->lanes = 69; }
 	// RLERC_PROF_SLICE=k: only every k-th ray plane (the uncontended chain: every warp has an SM sub-partition to itself)
 	const char* sl = getenv("RLERC_PROF_SLICE");
 	const int k = sl ? atoi(sl) : 1;

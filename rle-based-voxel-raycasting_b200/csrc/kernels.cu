@@ -415,6 +415,7 @@ void launch_traverse(const TraverseParams& p, int lanes, bool ids, cudaStream_t 
 {
 	if (lanes == 0 || lanes == 65) { launch_traverse_filter(p, ids, st); return; }
 	if (lanes == 68) { if (ids) launch_traverse_filter(p, ids, st); else launch_traverse_pair(p, st); return; }
+	if (lanes == 69) { if (ids) launch_traverse_filter(p, ids, st); else launch_traverse_quad(p, st); return; }
 #if RLERC_VARIANTS
 	if (lanes == 64) { launch_traverse_warp(p, ids, st); return; }
 	if (lanes == 66 || lanes == 67) { launch_traverse_chunk(p, ids, lanes == 67 ? 7 : 3, st); return; }

@@ -98,6 +98,7 @@ void launch_traverse(const TraverseParams& p, int lanes_per_ray, bool ids, cudaS
 void launch_traverse_warp(const TraverseParams& p, bool ids, cudaStream_t st);   // traverse_warp.cu
 void launch_traverse_filter(const TraverseParams& p, bool ids, cudaStream_t st); // traverse_filter.cu
 void launch_traverse_pair(const TraverseParams& p, cudaStream_t st);              // traverse_filter.cu (k_traverse_p, variant 68)
+void launch_traverse_quad(const TraverseParams& p, cudaStream_t st);              // traverse_filter.cu (k_traverse_q, variant 69)
 void launch_dda_states(const TraverseParams& p, cudaStream_t st);                 // traverse_filter.cu (k_dda_states, before either of the two)
 size_t traverse_dda_state_bytes(const TraverseParams& p);
 size_t traverse_dda_progress_bytes(const TraverseParams& p);

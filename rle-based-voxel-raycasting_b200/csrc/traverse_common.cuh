@@ -308,11 +308,13 @@ struct Counters {                                  // instrumented build: per-la
 	unsigned long long dbg[11];                    // fast-path statistics
 };
 
+// RESOLVE: everything of a batch that touches the occlusion state (which rows go to which span, the horizon, the long
+// spans); the short spans it assigns are left as records in `shade`, one bit per run in shade_runs_out, for shade_batch.
 // Returns true when the ray plane is finished (y_clip_min >= y_clip_max, Cuda_Render.h:370).
 template <bool IDS, bool STATS = false>
-__device__ __forceinline__ bool consume_batch(const TraverseParams& P, const RayCtx& R, HorizonState& H, Counters& C,
+__device__ __forceinline__ bool resolve_batch(const TraverseParams& P, const RayCtx& R, HorizonState& H, Counters& C,
                                               const Stage& s0, const Geo& g0, int slen, int nr, bool longcol, unsigned flags,
-                                              const int2* proj, uint32_t* shade, DrawJob* job)
+                                              const int2* proj, uint32_t* shade, DrawJob* job, unsigned& shade_runs_out)
 {
 	const unsigned FULL = 0xffffffffu;
 	const int gl = R.gl;
@@ -724,7 +726,22 @@ __device__ __forceinline__ bool consume_batch(const TraverseParams& P, const Ray
 	}   // while (todo)
 
 	if (STATS) { const long long now_ = clock64(); R.stat[14] += now_ - stick; stick = now_; }
-	// ---- S. shade the short spans of this batch: every lane its own column, side by side -------
+	H.ycmin = ycmin; H.ycmax = ycmax; H.hiw = hiw;
+	shade_runs_out = shade_runs;
+	return finished;
+}
+
+// SHADE (S): the short spans resolve_batch assigned, every lane its own column, side by side.  Touches neither the
+// occlusion mask nor the horizon: it may run later, or on another warp (k_traverse_q).
+template <bool IDS, bool STATS = false>
+__device__ __forceinline__ void shade_batch(const TraverseParams& P, const RayCtx& R, Counters& C, const Stage& s0, const Geo& g0,
+                                            int slen, int nr, unsigned shade_runs, const uint32_t* shade)
+{
+	uint32_t* const row = R.row;
+	const int gl = R.gl;
+	const float res_y2 = R.res_y2, pz_add = R.pz_add, py_add = R.py_add;
+	unsigned long long& c_pix = C.c_pix;
+	long long stick = STATS ? clock64() : 0;
 	if (shade_runs)
 	{
 		int blen = 0, btex = 0;
@@ -794,7 +811,17 @@ __device__ __forceinline__ bool consume_batch(const TraverseParams& P, const Ray
 		}
 	}
 	if (STATS) { const long long now_ = clock64(); R.stat[15] += now_ - stick; stick = now_; }
-	H.ycmin = ycmin; H.ycmax = ycmax; H.hiw = hiw;
+}
+
+// resolve + shade on one warp (k_traverse_f, k_traverse_p, k_traverse_w)
+template <bool IDS, bool STATS = false>
+__device__ __forceinline__ bool consume_batch(const TraverseParams& P, const RayCtx& R, HorizonState& H, Counters& C,
+                                              const Stage& s0, const Geo& g0, int slen, int nr, bool longcol, unsigned flags,
+                                              const int2* proj, uint32_t* shade, DrawJob* job)
+{
+	unsigned shade_runs = 0;
+	const bool finished = resolve_batch<IDS, STATS>(P, R, H, C, s0, g0, slen, nr, longcol, flags, proj, shade, job, shade_runs);
+	shade_batch<IDS, STATS>(P, R, C, s0, g0, slen, nr, shade_runs, shade);
 	return finished;
 }
 

@@ -170,13 +170,17 @@ k_dda_states(const __grid_constant__ TraverseParams P, int rays)
 
 // ---- the crossing records of one chunk, in shared memory -----------------------------------------------------------
 struct RecView {
-	float* d; float* x; float* y; uint8_t* m;        // [RLERC_F_SLOTS] each
+	float* d; float* x; float* y; uint8_t* m;        // [CH * 33] each
 };
+// words of the record area for chunks of CH batches
+__host__ __device__ constexpr int rec_words(int ch) { return (3 * ch * 33 + (ch * 33 + 3) / 4 + 3) & ~3; }
+static_assert(rec_words(RLERC_F_CH) == RLERC_F_REC, "record area");
+template <int CH = RLERC_F_CH>
 __device__ __forceinline__ RecView rec_view(uint32_t* base)
 {
 	RecView v;
-	v.d = reinterpret_cast<float*>(base); v.x = v.d + RLERC_F_SLOTS; v.y = v.x + RLERC_F_SLOTS;
-	v.m = reinterpret_cast<uint8_t*>(v.y + RLERC_F_SLOTS);
+	v.d = reinterpret_cast<float*>(base); v.x = v.d + CH * 33; v.y = v.x + CH * 33;
+	v.m = reinterpret_cast<uint8_t*>(v.y + CH * 33);
 	return v;
 }
 
@@ -186,18 +190,19 @@ __device__ __forceinline__ RecView rec_view(uint32_t* base)
 #define RLERC_DDA_SPIN_MAX (1 << 22)          // x 100 ns: the pre-pass never came; fail loudly (launch error), never a wrong picture
 __device__ __noinline__ void dda_states_missing() { __trap(); }
 
+template <int CH = RLERC_F_CH>
 __device__ __forceinline__ void dda_chunk(const TraverseParams& P, const float2* st, const unsigned long long* flag, int& published,
                                           float ray_x, float ray_z, int chunk, int gl, const RecView& rec, float3& carry)
 {
 	if (chunk > 0)
 	{
-		const int last = RLERC_F_CH * 33 - 2;                        // slot of crossing CH * 32 - 1
+		const int last = CH * 33 - 2;                                // slot of crossing CH * 32 - 1
 		carry = make_float3(rec.d[last], rec.x[last], rec.y[last]);
 	}
 	// the states of this chunk's batches have to be published (k_dda_states runs concurrently, normally far ahead)
 	{
 		const int nb = (P.lod.k_total + 31) >> 5;
-		int need = (chunk + 1) * RLERC_F_CH;
+		int need = (chunk + 1) * CH;
 		need = need < nb ? need : nb;
 		int spins = 0;
 		while (published < need)                                     // warp-uniform: every lane reads the same word
@@ -210,9 +215,9 @@ __device__ __forceinline__ void dda_chunk(const TraverseParams& P, const float2*
 		}
 	}
 	__syncwarp();
-	const int b = chunk * RLERC_F_CH + gl;
+	const int b = chunk * CH + gl;
 	const int k0 = b << 5;
-	if (gl < RLERC_F_CH && k0 < P.lod.k_total)
+	if (gl < CH && k0 < P.lod.k_total)
 	{
 		const float2* s = st + (size_t)b * 3;
 		const float2 a0 = __ldcg(s), a1 = __ldcg(s + 1), a2 = __ldcg(s + 2);   // L2: written by a kernel that is still running
@@ -916,6 +921,434 @@ void launch_traverse_pair(const TraverseParams& p, cudaStream_t st)
 	static size_t configured_on[64] = { 0 };
 	opt_in_smem(k_traverse_p, smem, configured_on);
 	launch_overlapped(k_traverse_p, blocks, RLERC_P_PLANES * 64, smem, st, p, rays);
+}
+
+// ================================================================================================================
+// k_traverse_q (variant 69): FOUR warps per ray plane, one per stage of the traversal, for launches that are bound by the
+// serial chain of their longest ray planes (single frames, multi-GPU slices).  Measured in round 2 on the sky ray planes of
+// a 4K frame: of the ~1.3 M cycles of such a chain the filter is 30 %, run loads + projection 16 %, the occlusion
+// machinery 28 % and the deferred shading 26 %; only the machinery (which row goes to which span, the horizon) is a true
+// recurrence from column to column.  So:
+//   F  filter    DDA chunks -> geometry + pointer-map gather -> first-run test -> live columns into a ring   (as warp F of k_traverse_p)
+//   P  project   per 32 live columns: run-word loads (one batch early), projection of up to RW runs to screen rows
+//   R  resolve   resolve_batch (traverse_common.cuh): rising-horizon / ownership-resolved / event-loop paths, long spans; owns
+//                the occlusion mask and the horizon, publishes y_clip_min for F and P
+//   S  shade     shade_batch: the short spans R assigned (interpolants, attribute gathers, pixel stores)
+// The chain of a ray plane becomes max(F, P, R, S) instead of their sum.  F and P work under a STALE horizon (the last
+// one R published): the filter only drops columns that are no-ops under any later horizon and the projection only stops
+// at a run that breaks under any later horizon, R re-tests everything under the exact state — the picture does not
+// depend on timing (same argument as k_traverse_p).  Batches travel through three buffers per ray plane that go round
+// P -> R -> S -> P; hand-over is by mbarrier (arrive.release / try_wait.acquire, one arrival per hand-over after a
+// __syncwarp), so a waiting warp sleeps in hardware instead of polling.  Roles are by warpgroup (4 ray planes per block of
+// 16 warps) so that setmaxnreg can move registers to where they are needed: launch cap 64, F 40, P 56, R 104, S 56.
+#define RLERC_Q_CH 8                        // DDA chunk of the filter warp (8 x 32 crossings: half the record area of k_traverse_f)
+#define RLERC_Q_RING 128                    // live-column ring, four quarters of 32 (one hand-over each)
+#define RLERC_Q_BUFS 3
+#define RLERC_Q_PLANES 4
+#define RLERC_Q_STAGE 12                    // words per lane of a batch buffer's column record
+#define RLERC_Q_DEPTH 0                     // (stash of a deeper gather pipeline in the filter warp: measured slower, not used)
+#define RLERC_Q_BUF_WORDS (RLERC_Q_STAGE * 32 + RLERC_PS_WORDS + 8)      // column records | projections + span records | header
+#ifndef RLERC_Q_REG_F
+#define RLERC_Q_REG_F 64
+#endif
+#ifndef RLERC_Q_REG_P
+#define RLERC_Q_REG_P 48
+#endif
+#ifndef RLERC_Q_REG_R
+#define RLERC_Q_REG_R 96
+#endif
+#ifndef RLERC_Q_REG_S
+#define RLERC_Q_REG_S 48
+#endif
+static_assert(RLERC_Q_REG_F + RLERC_Q_REG_P + RLERC_Q_REG_R + RLERC_Q_REG_S <= 4 * 64, "setmaxnreg: the roles share the block's launch allocation");
+#define RLERC_Q_SPIN_MAX (1 << 21)          // try_wait rounds (each blocks for up to the hardware's time limit): the protocol is broken; fail loudly
+
+__device__ __forceinline__ void mbar_init(uint64_t* b, int count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"((uint32_t)__cvta_generic_to_shared(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b)
+{
+	asm volatile("{ .reg .b64 t; mbarrier.arrive.release.cta.shared::cta.b64 t, [%0]; }" :: "r"((uint32_t)__cvta_generic_to_shared(b)) : "memory");
+}
+__device__ __noinline__ void quad_protocol_broken() { __trap(); }
+// all lanes wait for the completion of the phase with this parity
+__device__ __forceinline__ void mbar_wait(uint64_t* b, unsigned parity)
+{
+	const uint32_t a = (uint32_t)__cvta_generic_to_shared(b);
+	for (int spins = 0;; spins++)
+	{
+		unsigned ok;
+		asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+		             : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+		if (ok) return;
+		if (spins > RLERC_Q_SPIN_MAX) { quad_protocol_broken(); return; }
+	}
+}
+
+// RLERC_Q_PROF (tools/quad_profile.py, an A/B build only): per ray plane and role {cycles from start to exit, cycles spent in
+// mbar_wait, hand-overs}, unsigned long long[24] per ray plane in the buffer passed as P.ids: [role * 4 + {0, 1, 2}]
+#ifndef RLERC_Q_PROF
+#define RLERC_Q_PROF 0
+#endif
+#if RLERC_Q_PROF
+#define QPROF_DECL long long qp_t0 = clock64(), qp_wait = 0, qp_n = 0
+#define QPROF_WAIT(stmt) do { const long long a_ = clock64(); stmt; qp_wait += clock64() - a_; } while (0)
+#define QPROF_ITEM() (qp_n++)
+#define QPROF_END(role_) do { if (gl == 0 && P.ids) { unsigned long long* o_ = reinterpret_cast<unsigned long long*>(P.ids) + (size_t)x * 24 + (role_) * 4; \
+	o_[0] = (unsigned long long)(clock64() - qp_t0); o_[1] = (unsigned long long)qp_wait; o_[2] = (unsigned long long)qp_n; } } while (0)
+#else
+#define QPROF_DECL
+#define QPROF_WAIT(stmt) stmt
+#define QPROF_ITEM()
+#define QPROF_END(role_)
+#endif
+
+struct QPlane {                              // shared memory of one ray plane (word offsets from its base)
+	uint32_t* base;
+	int mask_words;
+	__device__ __forceinline__ uint32_t* rec() const { return base; }
+	__device__ __forceinline__ uint32_t* ring() const { return base + rec_words(RLERC_Q_CH); }                     // [8][RING]
+	__device__ __forceinline__ uint32_t* buf(int i) const { return ring() + 8 * RLERC_Q_RING + i * RLERC_Q_BUF_WORDS; }
+	__device__ __forceinline__ DrawJob* job() const { return reinterpret_cast<DrawJob*>(buf(RLERC_Q_BUFS)); }
+	__device__ __forceinline__ volatile int* ctl() const { return reinterpret_cast<volatile int*>(buf(RLERC_Q_BUFS) + 16); }   // ycmin, closed, f_total
+	__device__ __forceinline__ uint64_t* bars() const { return reinterpret_cast<uint64_t*>(buf(RLERC_Q_BUFS) + 16 + 8); }     // 8-byte aligned
+	__device__ __forceinline__ uint32_t* stash() const { return buf(RLERC_Q_BUFS) + 16 + 8 + 2 * 20; }                       // [DEPTH][5][32]
+	__device__ __forceinline__ uint32_t* ymask() const { return stash() + RLERC_Q_DEPTH * 160; }
+};
+// mbarriers of a ray plane: ring_full[4] ring_empty[4] p_full[3] r_full[3] s_free[3]
+#define QB_RING_FULL 0
+#define QB_RING_EMPTY 4
+#define QB_P_FULL 8
+#define QB_R_FULL 11
+#define QB_S_FREE 14
+#define QB_COUNT 17
+
+__host__ __device__ inline int q_words_per_plane(int mask_words)
+{
+	return (rec_words(RLERC_Q_CH) + 8 * RLERC_Q_RING + RLERC_Q_BUFS * RLERC_Q_BUF_WORDS + 16 + 8 + 2 * 20 + RLERC_Q_DEPTH * 160 + mask_words + 3) & ~3;
+}
+
+// column record of a batch buffer, field-major: e0 rw0 rw1 rw2 rw3 pz py czz cyy meta slen shade_runs
+// meta = cmip | nr << 8 | longcol << 12 | have << 13 | flags << 16
+__device__ __forceinline__ void qbuf_put(uint32_t* b, int gl, const Stage& s, const Geo& g, int slen, int nr, bool longcol, unsigned flags)
+{
+	b[0 * 32 + gl] = s.e0;
+	b[1 * 32 + gl] = s.rw[0]; b[2 * 32 + gl] = s.rw[1]; b[3 * 32 + gl] = s.rw[2]; b[4 * 32 + gl] = s.rw[3];
+	b[5 * 32 + gl] = __float_as_uint(g.pz); b[6 * 32 + gl] = __float_as_uint(g.py);
+	b[7 * 32 + gl] = __float_as_uint(g.czz); b[8 * 32 + gl] = __float_as_uint(g.cyy);
+	b[9 * 32 + gl] = (uint32_t)g.cmip | ((uint32_t)nr << 8) | ((longcol ? 1u : 0u) << 12) | ((s.have ? 1u : 0u) << 13) | (flags << 16);
+	b[10 * 32 + gl] = (uint32_t)slen;
+}
+__device__ __forceinline__ void qbuf_get(const uint32_t* b, int gl, Stage& s, Geo& g, int& slen, int& nr, bool& longcol, unsigned& flags)
+{
+	s.e0 = b[0 * 32 + gl];
+	s.rw[0] = b[1 * 32 + gl]; s.rw[1] = b[2 * 32 + gl]; s.rw[2] = b[3 * 32 + gl]; s.rw[3] = b[4 * 32 + gl];
+	g.pz = __uint_as_float(b[5 * 32 + gl]); g.py = __uint_as_float(b[6 * 32 + gl]);
+	g.czz = __uint_as_float(b[7 * 32 + gl]); g.cyy = __uint_as_float(b[8 * 32 + gl]);
+	const uint32_t meta = b[9 * 32 + gl];
+	g.cmip = (int)(meta & 255u); g.cidx = 0;
+	nr = (int)((meta >> 8) & 15u); longcol = (meta >> 12) & 1u; s.have = (meta >> 13) & 1u; flags = meta >> 16;
+	slen = (int)b[10 * 32 + gl];
+	s.e1 = (uint32_t)slen | (s.rw[0] << 16);                         // n_runs | first run << 16 (column_project left run 0 in the low half of rw[0])
+}
+
+__global__ void __launch_bounds__(RLERC_Q_PLANES * 128, 2)
+k_traverse_q(const __grid_constant__ TraverseParams P, int rays)
+{
+	extern __shared__ __align__(16) uint32_t smem[];
+	constexpr int G = 32;
+	const int gl = threadIdx.x & 31;
+	const int wid = threadIdx.x >> 5;
+	const int role = wid / RLERC_Q_PLANES;                           // 0 F, 1 P, 2 R, 3 S (one warpgroup each)
+	const int pl = wid % RLERC_Q_PLANES;
+	const unsigned FULL = 0xffffffffu;
+	const unsigned lt_mask = (1u << gl) - 1u;
+
+	const int ray_i = (int)blockIdx.x * RLERC_Q_PLANES + pl;         // launch-local ray index
+	// no early return before setmaxnreg (every warp of a warpgroup has to execute it)
+	const bool inrange = ray_i < rays && owned_ray(P, ray_i) < P.ray_end;
+	const int x = inrange ? owned_ray(P, ray_i) : P.ray_begin;
+
+	QPlane Q;
+	Q.base = smem + (size_t)pl * q_words_per_plane(P.mask_words);
+	Q.mask_words = P.mask_words;
+	volatile int* const ctl = Q.ctl();
+	uint64_t* const bars = Q.bars();
+	uint32_t* const ymask = Q.ymask();
+
+	const int res_y = P.res_y;
+	uint32_t* row = P.warp + (size_t)x * res_y;
+	RayInit ri;
+	ray_init(P, x, ri);
+	const bool active = inrange && !ri.skip;
+
+	if (role == 2)
+	{
+		if (inrange) clear_outside<G>(row, res_y, ri, gl);
+		for (int w = gl; w < P.mask_words; w += G) ymask[w] = 0;
+		if (gl == 0)
+		{
+			ctl[0] = ri.ycmin; ctl[1] = 0; ctl[2] = -1;
+			for (int k = 0; k < QB_COUNT; k++) mbar_init(bars + k, 1);
+		}
+	}
+	__syncthreads();
+
+	if (role == 0)
+	{
+		// ================= F: DDA chunks -> geometry + gather -> first-run test -> ring =========================
+		asm volatile("setmaxnreg.dec.sync.aligned.u32 " RLERC_STR(RLERC_Q_REG_F) ";");
+		if (!active) { RLERC_EXIT_AFTER_PREPASS(); return; }
+		FilterRay F;
+		filter_ray_init(P, ri, F);
+		const RecView rec = rec_view<RLERC_Q_CH>(Q.rec());
+		uint32_t* const ring = Q.ring();
+		const int k_total = P.lod.k_total;
+		const float2* const st = P.dda_states + (size_t)ray_i * ((k_total + 31) >> 5) * 3;
+		const unsigned long long* const flag = P.dda_progress + ray_i;
+		int published = 0;
+		float3 carry = make_float3(0.0f, 0.0f, 0.0f);
+		int chunk = -1, bl = RLERC_Q_CH, k_next = 0;
+		// one batch of 32 crossings is in flight between its pointer-map gather and the first-run test that needs the result
+		// (a deeper pipeline was measured: the filter warp is bound by its own instruction stream, ~400 dependent instructions
+		// per step, not by the gather; four batches in flight made a step 20 % slower)
+		Geo fg;
+		fg.pz = fg.py = fg.czz = fg.cyy = 0; fg.cmip = 0; fg.cidx = 0;
+		unsigned fe0 = 0, fe1 = 0;
+		bool fhave = false;
+		int fn = 0;
+		int tail = 0;                       // entries written
+		int acquired = 0, filled = 0;       // quarters this warp may write / has handed over
+		QPROF_DECL;
+		while (k_next < k_total || fn > 0)
+		{
+			if (ctl[1]) break;                                           // R closed the ray plane
+			const int ycmin = ctl[0];                                    // possibly stale: lower than the truth, never higher
+			QPROF_ITEM();
+			// room for 32 more entries
+			while (((tail + 63) >> 5) > acquired)
+			{
+				QPROF_WAIT(mbar_wait(bars + QB_RING_EMPTY + (acquired & 3), ((acquired >> 2) & 1) ^ 1));
+				acquired++;
+			}
+			Geo ng;
+			ng.pz = ng.py = ng.czz = ng.cyy = 0; ng.cmip = 0; ng.cidx = 0;
+			unsigned ne0 = 0, ne1 = 0;
+			bool nhave = false;
+			int nn = 0;
+			if (k_next < k_total)
+			{
+				if (bl == RLERC_Q_CH) { dda_chunk<RLERC_Q_CH>(P, st, flag, published, F.ray_x, F.ray_z, ++chunk, gl, rec, carry); bl = 0; }
+				nn = k_total - k_next < G ? k_total - k_next : G;
+				if (gl < nn) nhave = filter_geometry(P, F, rec, carry, bl, gl, ycmin, ng, ne0, ne1);
+				bl++;
+				k_next += nn;
+			}
+			if (fn > 0)
+			{
+				const bool live = gl < fn && fhave && filter_live<false>(F, fg, fe1, ycmin);
+				const unsigned lb = __ballot_sync(FULL, live);
+				if (live)
+				{
+					column_put(ring + ((tail + __popc(lb & lt_mask)) & (RLERC_Q_RING - 1)), RLERC_Q_RING, fg, fe0, fe1);
+					// P will want the column's run words: start them on their way into this SM's L1 now
+					if ((fe1 & 0xffffu) > 1u)
+						asm volatile("prefetch.global.L1 [%0];" :: "l"(P.level[fg.cmip].slabs + 2 + (size_t)fe0 + 1));
+				}
+				tail += __popc(lb);
+				__syncwarp();
+				while ((filled + 1) * 32 <= tail)
+				{
+					if (gl == 0) mbar_arrive(bars + QB_RING_FULL + (filled & 3));
+					filled++;
+				}
+			}
+			fg = ng; fe0 = ne0; fe1 = ne1; fhave = nhave; fn = nn;
+		}
+		// end of the stream: the total, then one more hand-over (the last, partial or empty, quarter); its barrier must
+		// not be signalled before P has consumed the quarter that used it last
+		while (acquired <= filled)
+		{
+			QPROF_WAIT(mbar_wait(bars + QB_RING_EMPTY + (acquired & 3), ((acquired >> 2) & 1) ^ 1));
+			acquired++;
+		}
+		__syncwarp();
+		if (gl == 0)
+		{
+			ctl[2] = tail;
+			mbar_arrive(bars + QB_RING_FULL + (filled & 3));
+		}
+		QPROF_END(0);
+		RLERC_EXIT_AFTER_PREPASS();
+		return;
+	}
+
+	if (role == 1)
+	{
+		// ================= P: ring -> run words -> projection -> batch buffer ==================================
+		asm volatile("setmaxnreg.dec.sync.aligned.u32 " RLERC_STR(RLERC_Q_REG_P) ";");
+		if (!active) { RLERC_EXIT_AFTER_PREPASS(); return; }
+		FilterRay F;
+		filter_ray_init(P, ri, F);
+		const uint32_t* const ring = Q.ring();
+		Stage s0;
+		Geo g0;
+		stage_clear(s0, g0);
+		bool s0_valid = false, s0_last = false;
+		bool ended = false;
+		int k = 0, b = 0;
+		QPROF_DECL;
+		while (true)
+		{
+			// C1: the next quarter of the ring
+			Stage s1;
+			Geo g1;
+			stage_clear(s1, g1);
+			bool s1_valid = false, s1_last = false;
+			if (!ended)
+			{
+				QPROF_WAIT(mbar_wait(bars + QB_RING_FULL + (k & 3), (k >> 2) & 1));
+				const int ft = ctl[2];
+				int n = 32;
+				if (ft >= 0 && ft - k * 32 < 32) { n = ft - k * 32; s1_last = true; ended = true; }
+				s1.nvalid = n; s1.have = gl < n;
+				if (s1.have) column_take(P, ring + ((k * 32 + gl) & (RLERC_Q_RING - 1)), RLERC_Q_RING, g1, s1);
+				s1_valid = true;
+				__syncwarp();
+				if (gl == 0) mbar_arrive(bars + QB_RING_EMPTY + (k & 3));
+				k++;
+			}
+			// C2: project s0 into the next batch buffer
+			if (s0_valid)
+			{
+				QPROF_WAIT(mbar_wait(bars + QB_S_FREE + (b % RLERC_Q_BUFS), ((b / RLERC_Q_BUFS) & 1) ^ 1));
+				QPROF_ITEM();
+				uint32_t* const bw = Q.buf(b % RLERC_Q_BUFS);
+				int2* const proj = reinterpret_cast<int2*>(bw + RLERC_Q_STAGE * 32);
+				int slen = 0, nr = 0;
+				bool longcol = false;
+				unsigned flags = 0;
+				const bool closed = ctl[1] != 0;
+				if (!closed && s0.have) column_project(F, s0, g0, ctl[0], gl, proj, slen, nr, longcol, flags);
+				qbuf_put(bw, gl, s0, g0, slen, nr, longcol, flags);
+				if (gl == 0) { bw[RLERC_Q_STAGE * 32 + RLERC_PS_WORDS] = closed ? 0u : (uint32_t)s0.nvalid; bw[RLERC_Q_STAGE * 32 + RLERC_PS_WORDS + 1] = s0_last ? 1u : 0u; }
+				__syncwarp();
+				if (gl == 0) mbar_arrive(bars + QB_P_FULL + (b % RLERC_Q_BUFS));
+				b++;
+				if (s0_last) break;
+			}
+			s0 = s1; g0 = g1; s0_valid = s1_valid; s0_last = s1_last;
+		}
+		QPROF_END(1);
+		RLERC_EXIT_AFTER_PREPASS();
+		return;
+	}
+
+	if (role == 2)
+	{
+		// ================= R: resolve — the occlusion state of the ray plane ===================================
+		asm volatile("setmaxnreg.inc.sync.aligned.u32 " RLERC_STR(RLERC_Q_REG_R) ";");
+		if (!active) { RLERC_EXIT_AFTER_PREPASS(); return; }
+		FilterRay F;
+		filter_ray_init(P, ri, F);
+		const int ymin0 = ri.ycmin, ymax0 = ri.ycmax;
+		HorizonState Hs;
+		Hs.ycmin = ri.ycmin; Hs.ycmax = ri.ycmax; Hs.hiw = 0;
+		Counters Cn;
+		memset(&Cn, 0, sizeof(Cn));
+		RayCtx R;
+		ray_ctx_init(P, F, row, ymask, nullptr, nullptr, gl, R);
+		bool finished = false;
+		QPROF_DECL;
+		for (int b = 0;; b++)
+		{
+			QPROF_WAIT(mbar_wait(bars + QB_P_FULL + (b % RLERC_Q_BUFS), (b / RLERC_Q_BUFS) & 1));
+			QPROF_ITEM();
+			uint32_t* const bw = Q.buf(b % RLERC_Q_BUFS);
+			const int nvalid = (int)bw[RLERC_Q_STAGE * 32 + RLERC_PS_WORDS];
+			const bool last = bw[RLERC_Q_STAGE * 32 + RLERC_PS_WORDS + 1] != 0;
+			unsigned shade_runs = 0;
+			if (nvalid > 0 && !finished)
+			{
+				const int2* const proj = reinterpret_cast<const int2*>(bw + RLERC_Q_STAGE * 32);
+				uint32_t* const shade = bw + RLERC_Q_STAGE * 32 + RLERC_RW * 64;
+				Stage s0;
+				Geo g0;
+				int slen, nr;
+				bool longcol;
+				unsigned flags;
+				qbuf_get(bw, gl, s0, g0, slen, nr, longcol, flags);
+				s0.nvalid = nvalid;
+				// P projected under an older horizon: a run that breaks under the current one ends the column here
+				// (Cuda_Render.h:542-543), which also settles a column P had to leave open as "long"
+				if (s0.have)
+					for (int r = 0; r < nr; r++)
+						if (((flags >> r) & 1u) && proj[r * 32 + gl].y <= Hs.ycmin) { nr = r + 1; longcol = false; break; }
+				finished = resolve_batch<false, false>(P, R, Hs, Cn, s0, g0, slen, nr, longcol, flags, proj, shade, Q.job(), shade_runs);
+				if (Hs.ycmin >= Hs.ycmax) finished = true;               // Cuda_Render.h:370
+				if (gl == 0) { ctl[0] = Hs.ycmin; if (finished) ctl[1] = 1; }
+			}
+			bw[11 * 32 + gl] = shade_runs;
+			__syncwarp();
+			if (gl == 0) mbar_arrive(bars + QB_R_FULL + (b % RLERC_Q_BUFS));
+			if (last) break;
+		}
+		__syncwarp();
+		// sky sentinel on every pixel of the clip range that no run covered
+		for (int y = ymin0 + gl; y <= ymax0; y += G)
+			if (!((ymask[y >> 5] >> (y & 31)) & 1u)) st_warp(row + y, RLERC_SKY);
+		QPROF_END(2);
+		RLERC_EXIT_AFTER_PREPASS();
+		return;
+	}
+
+	// ===================== S: shade the short spans R assigned ===================================================
+	asm volatile("setmaxnreg.dec.sync.aligned.u32 " RLERC_STR(RLERC_Q_REG_S) ";");
+	if (!active) { RLERC_EXIT_AFTER_PREPASS(); return; }
+	{
+		FilterRay F;
+		filter_ray_init(P, ri, F);
+		Counters Cn;
+		memset(&Cn, 0, sizeof(Cn));
+		RayCtx R;
+		ray_ctx_init(P, F, row, ymask, nullptr, nullptr, gl, R);
+		QPROF_DECL;
+		for (int b = 0;; b++)
+		{
+			QPROF_WAIT(mbar_wait(bars + QB_R_FULL + (b % RLERC_Q_BUFS), (b / RLERC_Q_BUFS) & 1));
+			QPROF_ITEM();
+			uint32_t* const bw = Q.buf(b % RLERC_Q_BUFS);
+			const bool last = bw[RLERC_Q_STAGE * 32 + RLERC_PS_WORDS + 1] != 0;
+			const unsigned shade_runs = bw[11 * 32 + gl];
+			if (__any_sync(FULL, shade_runs != 0))
+			{
+				Stage s0;
+				Geo g0;
+				int slen, nr;
+				bool longcol;
+				unsigned flags;
+				qbuf_get(bw, gl, s0, g0, slen, nr, longcol, flags);
+				shade_batch<false, false>(P, R, Cn, s0, g0, slen, nr, shade_runs, bw + RLERC_Q_STAGE * 32 + RLERC_RW * 64);
+			}
+			__syncwarp();
+			if (gl == 0) mbar_arrive(bars + QB_S_FREE + (b % RLERC_Q_BUFS));
+			if (last) break;
+		}
+		QPROF_END(3);
+	}
+	RLERC_EXIT_AFTER_PREPASS();
+}
+
+void launch_traverse_quad(const TraverseParams& p, cudaStream_t st)
+{
+	const int rays = launch_rays(p);
+	if (rays <= 0) return;
+	const int blocks = (rays + RLERC_Q_PLANES - 1) / RLERC_Q_PLANES;
+	const size_t smem = (size_t)RLERC_Q_PLANES * q_words_per_plane(p.mask_words) * sizeof(uint32_t);
+	static size_t configured_on[64] = { 0 };
+	opt_in_smem(k_traverse_q, smem, configured_on);
+	launch_overlapped(k_traverse_q, blocks, RLERC_Q_PLANES * 128, smem, st, p, rays);
 }
 
 void launch_traverse_filter(const TraverseParams& p, bool ids, cudaStream_t st)

@@ -88,7 +88,7 @@ def test_config2_imrodh1080p_all_driver_frames(R, rb, gpu):
 
 
 def test_config2_imrodh1080p_both_production_kernels(R, rb, gpu):
-    _check_frames(R, rb, gpu, "imrodh1080p", (0, 7, 13), 20, lanes=(65, 68), rgba=False)
+    _check_frames(R, rb, gpu, "imrodh1080p", (0, 7, 13), 20, lanes=(65, 68, 69), rgba=False)
 
 
 def test_config3_tiled4k(R, rb, gpu):

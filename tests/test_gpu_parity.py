@@ -46,7 +46,7 @@ def _oracle(rb, rm, scene, cfg, ids=False):
     return orm, warp, oid, cnt
 
 
-@pytest.mark.parametrize("lanes", [0, 68, 66, 67, 65, 64, 32, 8, 1])
+@pytest.mark.parametrize("lanes", [0, 69, 68, 66, 67, 65, 64, 32, 8, 1])
 def test_warp_buffer_bit_exact_camera_grid(R, rb, gpu, scene_mid, lanes):
     if lanes in (64, 66, 67) and not _variants(R):
         pytest.skip("variant kernels are not in this build (make VARIANTS=1)")
@@ -206,7 +206,7 @@ def test_degenerate_scenes_bit_exact(R, rb, gpu):
                 assert abs(c[k] - cnt[k]) <= 0.005 * cnt[k], (name, k, c[k], cnt[k], rot)
                 if name != "noise50":
                     assert c[k] == cnt[k], (name, k, c[k], cnt[k], rot)
-            for lanes in _lanes_list(R, (0, 65, 68, 64, 66, 32, 1)):
+            for lanes in _lanes_list(R, (0, 65, 68, 69, 64, 66, 32, 1)):
                 gpu.set_lanes_per_ray(lanes)
                 _fresh_warp(gpu, cfg)
                 gpu.render(rm, cfg)
@@ -508,7 +508,7 @@ def test_core_h_options_clipregion_height_color(R, rb, gpu, scene_small, scene_m
                 rm = R.RayMap(cfg).get_ray_map(pos, rot)
                 orm = oracle_raymap(rb, rm, scene)
                 want, _, _ = rb.orc_render(orm, cfg.render_size, cfg.rays_casted, cfg.mip_distance, cfg.z_far, flags=flags)
-                for lanes in (0, 65, 68):          # automatic choice, k_traverse_f, k_traverse_p
+                for lanes in (0, 65, 68, 69):      # automatic choice, k_traverse_f, k_traverse_p, k_traverse_q
                     gpu.set_lanes_per_ray(lanes)
                     _fresh_warp(gpu, cfg)
                     gpu.render(rm, cfg)

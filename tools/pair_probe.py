@@ -14,7 +14,7 @@ def same(scene, cfg, pos, rot, tag):
     global bad
     rm = R.RayMap(cfg).get_ray_map(pos, rot)
     out = []
-    for code in (65, 68):
+    for code in (65, 68, 69):
         r.set_lanes_per_ray(code)
         r.upload(r.warp_buffer(cfg), np.zeros((cfg.rays_casted, cfg.render_size), np.uint32))
         r.render(rm, cfg); r.sync()
@@ -42,7 +42,7 @@ for t in (0, 250, 750):
     same(scene, cfg, pos, rot, workload)
     rm = R.RayMap(cfg).get_ray_map(pos, rot)
     line = "t %3d rays %5d |" % (t, rm.map_line_count)
-    for code in (65, 68):
+    for code in [int(c) for c in os.environ.get("PAIR_CODES", "65,68,69").split(",")]:
         r.set_lanes_per_ray(code)
         for k in (1, 2, 4, 8, 16):
             best = 1e9
