@@ -11,6 +11,9 @@
 //
 // usage: headless (--scene FILE.rle4 | --synth N) [--size W H] [--pos X Y Z] [--rot X Y Z] [--out PREFIX]
 //                 [--frames K]   (K > 1: additionally times K frames of the scripted fly-through, pipelined)
+//                 [--gpus N]     (N > 1: the same frame and fly-through on N GPUs through rlerc_create_multi — ray-plane slices per
+//                                 GPU, bands of rows unwarped per GPU with the texels pulled over NVLink, every GPU copies its
+//                                 band to the host; the multi-GPU frame has to equal the single-GPU frame byte for byte)
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -34,7 +37,7 @@ static void write_file(const std::string& path, const void* data, size_t bytes, 
 int main(int argc, char** argv)
 {
 	std::string scene_path, out = "frame";
-	int synth = 0, W = 1024, H = 768, frames = 1;            // core.h:3-4 SCREEN_SIZE_X/Y
+	int synth = 0, W = 1024, H = 768, frames = 1, gpus = 1;  // core.h:3-4 SCREEN_SIZE_X/Y
 	vec3f pos(10000.0f, -818.0f, 10000.0f);                   // main.cpp:316-320,344-347
 	vec3f rot(0.40f, (float)(0.30 + 1.57079632679489661923), 0.0f);
 	bool pos_given = false;
@@ -48,9 +51,10 @@ int main(int argc, char** argv)
 		else if (a == "--rot" && i + 3 < argc) { rot.x = (float)std::atof(argv[++i]); rot.y = (float)std::atof(argv[++i]); rot.z = (float)std::atof(argv[++i]); }
 		else if (a == "--out" && i + 1 < argc) out = argv[++i];
 		else if (a == "--frames" && i + 1 < argc) frames = std::atoi(argv[++i]);
+		else if (a == "--gpus" && i + 1 < argc) gpus = std::atoi(argv[++i]);
 		else
 		{
-			std::fprintf(stderr, "usage: %s (--scene FILE.rle4 | --synth N) [--size W H] [--pos X Y Z] [--rot X Y Z] [--out PREFIX] [--frames K]\n", argv[0]);
+			std::fprintf(stderr, "usage: %s (--scene FILE.rle4 | --synth N) [--size W H] [--pos X Y Z] [--rot X Y Z] [--out PREFIX] [--frames K] [--gpus N]\n", argv[0]);
 			return 2;
 		}
 	}
@@ -146,6 +150,50 @@ int main(int argc, char** argv)
 			std::printf("fly-through: %d frames in %.3f s = %.1f frames/s, %.1f Mrays/s (host buffers, %d frames in flight)\n",
 			            frames, s, frames / s, (double)W * H * frames / s / 1e6, DEPTH);
 			for (int k = 0; k < DEPTH; k++) rlerc_host_free(pin[k]);
+		}
+		// ---- the same on N GPUs behind one object (rlerc_create_multi) ------------------------------------------
+		if (gpus > 1)
+		{
+			std::vector<int> devices(gpus);
+			for (int g = 0; g < gpus; g++) devices[g] = g;
+			rlerc_multi* multi = nullptr;
+			check(rlerc_create_multi(devices.data(), gpus, &multi), "rlerc_create_multi");
+			check(rlerc_multi_set_depth(multi, 2 * gpus < 8 ? 8 : 2 * gpus, 32), "rlerc_multi_set_depth");
+			check(rlerc_multi_scene_upload(multi, rle4.handle()), "rlerc_multi_scene_upload");      // a full replica per GPU
+			uint8_t* mrgba = nullptr;
+			check(rlerc_host_alloc((void**)&mrgba, (size_t)W * H * 4), "rlerc_host_alloc");
+			const float p0[3] = { pos.x, pos.y, pos.z }, r0[3] = { rot.x, rot.y, rot.z };
+			check(rlerc_multi_render_frame(multi, p0, r0, &cfg, mrgba), "rlerc_multi_render_frame");
+			const bool same = std::memcmp(mrgba, rgba, (size_t)W * H * 4) == 0;
+			std::printf("%d GPUs: frame %s the single-GPU frame\n", gpus, same ? "is byte-identical to" : "DIFFERS from");
+			if (frames > 1)
+			{
+				const int DEPTH = 2 * gpus < 8 ? 8 : 2 * gpus;
+				std::vector<uint8_t*> pin(DEPTH);
+				for (int k = 0; k < DEPTH; k++) check(rlerc_host_alloc((void**)&pin[k], (size_t)W * H * 4), "rlerc_host_alloc");
+				const float sy = (float)rle4.map[0].sy;
+				std::vector<int> tickets;
+				const auto t0 = std::chrono::steady_clock::now();
+				for (int i = 0; i < frames; i++)
+				{
+					const float a = 6.28318530717958647692f * (float)i / (float)frames;
+					const float p[3] = { 10000.0f + 4000.0f * std::sin(a), scene_path.empty() ? -(0.15f + 0.08f * std::sin(2 * a)) * sy : -818.0f + 300.0f * std::sin(2 * a),
+					                     10000.0f + 4000.0f * std::cos(a) };
+					const float r[3] = { 0.35f + 0.3f * std::sin(3 * a), a + 1.57079632679489661923f, 0.0f };
+					if ((int)tickets.size() >= DEPTH) { check(rlerc_multi_frame_wait(multi, tickets.front()), "rlerc_multi_frame_wait"); tickets.erase(tickets.begin()); }
+					const int t = rlerc_multi_frame_submit(multi, p, r, &cfg, pin[i % DEPTH]);
+					if (t < 0) check(t, "rlerc_multi_frame_submit");
+					tickets.push_back(t);
+				}
+				for (size_t k = 0; k < tickets.size(); k++) check(rlerc_multi_frame_wait(multi, tickets[k]), "rlerc_multi_frame_wait");
+				const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+				std::printf("fly-through on %d GPUs: %d frames in %.3f s = %.1f frames/s, %.1f Mrays/s (host buffers, %d frames in flight)\n",
+				            gpus, frames, s, frames / s, (double)W * H * frames / s / 1e6, DEPTH);
+				for (int k = 0; k < DEPTH; k++) rlerc_host_free(pin[k]);
+			}
+			rlerc_host_free(mrgba);
+			rlerc_multi_destroy(multi);
+			if (!same) { rlerc_host_free(rgba); return 4; }
 		}
 		rlerc_host_free(rgba);
 	}

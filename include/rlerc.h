@@ -299,6 +299,8 @@ extern int cpu_to_gpu_delta;                           /* always 0: no mirrored 
  * pboUnregister keep their signatures. raymap is the reference's RayMap_GPU (== rlerc_raymap).
  * Uses the process-default context created by rlerc_legacy_init(). */
 int   rlerc_legacy_init(int device, const rlerc_scene* scene, const rlerc_frame_config* cfg);
+/* ... or make an existing context (scene already uploaded) the one the legacy entry points use; it stays the caller's. */
+int   rlerc_legacy_adopt(rlerc_ctx* c, const rlerc_frame_config* cfg);
 int   rlerc_pbo_bind(int pbo, void* device_ptr);
 void  pboRegister(int pbo);
 void  pboUnregister(int pbo);

@@ -9,7 +9,8 @@
 //     ray_map.nummaps = rle4.nummaps;
 //     ray_map.set_border(0.125f); ray_map.set_ray_limit(RAYS_CASTED_RES);     // main.cpp:774-776
 //     ray_map.get_ray_map(pos, rot);                                          // main.cpp:777
-//     cuda_main_render2(pbo, RENDER_SIZE, RENDER_SIZE, &ray_map);             // main.cpp:466
+//     rlerc_pbo_bind(pbo, device_buffer);                                     // no GL here: a "pbo" is a handle bound to device memory
+//     cuda_main_render2(pbo, RENDER_SIZE, RENDER_SIZE, &ray_map);             // main.cpp:466 (renders with the context all_to_gpu filled)
 //
 //   reference                                     here
 //   struct Map4          R/src/Rle4.h:7-21        rlerc::Map4   (= rlerc_map4, field order kept, LP64)
@@ -123,13 +124,17 @@ struct RLE4 {                            // R/src/Rle4.h:25-52
 		scene_ = s;
 		adopt();
 	}
-	void all_to_gpu(int device = 0)      // Rle4.cpp:432-438: every level, full replica in HBM
+	// Rle4.cpp:432-438: every level, full replica in HBM.  The context that holds it becomes the one the reference's own
+	// entry point cuda_main_render2 renders with (cfg: the constants of R/src/core.h it was compiled with; default: as shipped).
+	void all_to_gpu(int device = 0, const Config* cfg = nullptr)
 	{
 		need_scene();
 		rlerc_ctx* c = Device::get(device).ctx();
 		check(rlerc_scene_upload(c, scene_), "rlerc_scene_upload");
 		int n = 0;
 		check(rlerc_scene_device_maps(c, mapgpu, &n), "rlerc_scene_device_maps");
+		const Config shipped = window(1024, 768);
+		check(rlerc_legacy_adopt(c, cfg ? cfg : &shipped), "rlerc_legacy_adopt");
 	}
 	rlerc_scene* handle() const { return scene_; }
 

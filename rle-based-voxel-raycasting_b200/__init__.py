@@ -145,6 +145,7 @@ _SIGS = {
     "gpu_memcpy": (None, [_P, _P, C.c_int]),
     "cpu_memcpy": (None, [_P, _P, C.c_int]),
     "rlerc_legacy_init": (C.c_int, [C.c_int, _P, _P]),
+    "rlerc_legacy_adopt": (C.c_int, [_P, _P]),
     "rlerc_pbo_bind": (C.c_int, [C.c_int, _P]),
     "pboRegister": (None, [C.c_int]),
     "pboUnregister": (None, [C.c_int]),

@@ -265,15 +265,16 @@ int rlerc_scene_upload(rlerc_ctx* c, const rlerc_scene* s)
 		const Level& lv = s->levels[m];
 		void *dm = nullptr, *ds = nullptr;
 		// +64 bytes of zero padding behind the slabs: a column's "first run" style look-ahead
-		// and vector loads may read a few words past the last column
-		const size_t mbytes = lv.map.size() * 4, sbytes = lv.slabs.size() * 2;
+		// and vector loads may read a few words past the last column; + what the attribute gathers of
+		// columns with inconsistent counts can reach (scene.cpp validate_columns)
+		const size_t mbytes = lv.map.size() * 4, sbytes = lv.slabs.size() * 2, pad = 64 + (size_t)lv.gather_pad * 2;
 		CK(cudaMalloc(&dm, mbytes));
 		c->scene_allocs.push_back(dm);
-		CK(cudaMalloc(&ds, sbytes + 64));
+		CK(cudaMalloc(&ds, sbytes + pad));
 		c->scene_allocs.push_back(ds);
 		CK(cudaMemcpy(dm, lv.map.data(), mbytes, cudaMemcpyHostToDevice));
 		CK(cudaMemcpy(ds, lv.slabs.data(), sbytes, cudaMemcpyHostToDevice));
-		CK(cudaMemset((char*)ds + sbytes, 0, 64));
+		CK(cudaMemset((char*)ds + sbytes, 0, pad));
 		c->level[m].map = (const uint2*)dm;
 		c->level[m].slabs = (const uint16_t*)ds;
 		c->level[m].sx = lv.sx;
@@ -789,12 +790,14 @@ int rlerc_last_kernel_ms(rlerc_ctx* c, float out[2])
 int cpu_to_gpu_delta = 0;
 
 static rlerc_ctx* g_legacy = nullptr;
+static bool g_legacy_owned = false;
 static rlerc_frame_config g_legacy_cfg;
 static std::map<int, void*>* g_pbo = nullptr;
 
 void* gpu_malloc(int size)
 {
 	void* p = nullptr;
+	if (g_legacy) cudaSetDevice(g_legacy->device);
 	if (cudaMalloc(&p, (size_t)size) != cudaSuccess) { set_error("gpu_malloc(%d) failed", size); return nullptr; }
 	return p;
 }
@@ -805,9 +808,24 @@ int rlerc_legacy_init(int device, const rlerc_scene* scene, const rlerc_frame_co
 {
 	int rc = check_cfg(cfg);
 	if (rc) return rc;
-	if (g_legacy) { rlerc_destroy(g_legacy); g_legacy = nullptr; }
+	if (g_legacy && g_legacy_owned) rlerc_destroy(g_legacy);
+	g_legacy = nullptr;
 	if ((rc = rlerc_create(device, &g_legacy))) return rc;
+	g_legacy_owned = true;
 	if ((rc = rlerc_scene_upload(g_legacy, scene))) return rc;
+	g_legacy_cfg = *cfg;
+	if (!g_pbo) g_pbo = new std::map<int, void*>();
+	return RLERC_OK;
+}
+
+int rlerc_legacy_adopt(rlerc_ctx* c, const rlerc_frame_config* cfg)
+{
+	int rc = check_cfg(cfg);
+	if (rc) return rc;
+	if (!c) { set_error("rlerc_legacy_adopt: null context"); return RLERC_ERR_ARG; }
+	if (g_legacy && g_legacy_owned && g_legacy != c) rlerc_destroy(g_legacy);
+	g_legacy = c;
+	g_legacy_owned = false;
 	g_legacy_cfg = *cfg;
 	if (!g_pbo) g_pbo = new std::map<int, void*>();
 	return RLERC_OK;
@@ -826,7 +844,13 @@ void pboUnregister(int pbo) { if (g_pbo) g_pbo->erase(pbo); }
 // buffer behind `pbo_out` and returns once the kernel has finished (Cuda_Main.cu:241).
 void cuda_main_render2(int pbo_out, int width, int height, rlerc_raymap* raymap)
 {
-	if (pbo_out == 0 || !g_legacy || !g_pbo || !raymap) return;         // Cuda_Main.cu:187
+	if (pbo_out == 0) return;                                            // Cuda_Main.cu:187
+	if (!g_legacy || !g_pbo || !raymap)
+	{
+		// the reference would dereference garbage here; say what is missing instead of rendering nothing silently
+		set_error("cuda_main_render2: no context (call RLE4::all_to_gpu / rlerc_legacy_init / rlerc_legacy_adopt first)");
+		return;
+	}
 	auto it = g_pbo->find(pbo_out);
 	if (it == g_pbo->end() || !it->second) { set_error("cuda_main_render2: pbo %d has no device buffer", pbo_out); return; }
 	rlerc_frame_config cfg = g_legacy_cfg;

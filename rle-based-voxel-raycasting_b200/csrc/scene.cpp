@@ -10,6 +10,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <new>
 #ifdef _OPENMP
 #include <omp.h>
 #endif
@@ -51,6 +52,41 @@ int build_pointer_map(Level& lv)
 		ofs += (uint64_t)n_runs + n_vox + 2;
 	}
 	if (ofs > n) { set_error("slab stream shorter than its columns claim"); return RLERC_ERR_FORMAT; }
+	return RLERC_OK;
+}
+
+// Scenes that come from outside (a file, caller-provided Map4 arrays) are not trusted: every column's header, runs and
+// attributes have to lie inside the slab stream, and its map entry has to agree with the stream.  A column whose runs
+// claim more solid voxels than its attribute count (n_vox) is NOT an error — the reference's compressor leaves the mip
+// levels narrower than 8 voxels undefined and its own files have to load — but the traversal's
+// attribute gather send[u], u < sum of the solid counts (Cuda_Render.h:498-499,707-713), would then read past the column;
+// gather_pad is the number of ushorts by which such a read can leave the STREAM, and the device copy is padded by it.
+int validate_columns(Level& lv)
+{
+	const uint64_t ncol = (uint64_t)lv.sx * (uint64_t)lv.sz;
+	const uint64_t n = lv.slabs.size();
+	if (lv.map.size() != ncol * 2) { set_error("pointer map has %llu words for %llu columns", (unsigned long long)lv.map.size(), (unsigned long long)ncol); return RLERC_ERR_FORMAT; }
+	const uint16_t* s = lv.slabs.data();
+	uint64_t pad = 0;
+	int bad = 0;
+	#pragma omp parallel for schedule(static) reduction(max : pad) reduction(+ : bad)
+	for (long long c = 0; c < (long long)ncol; c++)
+	{
+		const uint64_t ofs = lv.map[c * 2];
+		if (ofs + 2 > n) { bad++; continue; }
+		const uint64_t n_runs = s[ofs], n_vox = s[ofs + 1];
+		if ((lv.map[c * 2 + 1] & 0xffffu) != n_runs || ofs + 2 + n_runs + n_vox > n) { bad++; continue; }
+		if (n_runs > 0 && (lv.map[c * 2 + 1] >> 16) != s[ofs + 2]) { bad++; continue; }
+		uint64_t solid = 0;
+		for (uint64_t r = 0; r < n_runs; r++) solid += s[ofs + 2 + r] >> 10;
+		if (solid > n_vox)
+		{
+			const uint64_t end = ofs + 2 + n_runs + solid;               // one past the farthest attribute the runs can address
+			if (end > n && end - n > pad) pad = end - n;
+		}
+	}
+	if (bad) { set_error("%d columns of a %d x %d level point outside the slab stream or disagree with it", bad, lv.sx, lv.sz); return RLERC_ERR_FORMAT; }
+	lv.gather_pad = pad;
 	return RLERC_OK;
 }
 
@@ -368,7 +404,13 @@ int rlerc_scene_load(const char* path, rlerc_scene** out)
 		set_error("%s: bad level count %d", path, nummaps);
 		return RLERC_ERR_FORMAT;
 	}
-	rlerc_scene* s = new rlerc_scene();
+	// the header's sizes are claims: compare them with what is left of the file before allocating anything
+	fseeko(f, 0, SEEK_END);
+	const uint64_t file_bytes = (uint64_t)ftello(f);
+	fseeko(f, 4, SEEK_SET);
+	rlerc_scene* s = nullptr;
+	try {
+	s = new rlerc_scene();
 	s->levels.resize(nummaps);
 	for (int m = 0; m < nummaps; m++)
 	{
@@ -385,10 +427,22 @@ int rlerc_scene_load(const char* path, rlerc_scene** out)
 			set_error("%s: level %d has implausible header %d x %d x %d, %llu slabs", path, m, hdr[0], hdr[1], hdr[2], (unsigned long long)n);
 			return RLERC_ERR_FORMAT;
 		}
+		if ((uint64_t)ftello(f) + 2 * n > file_bytes)
+		{
+			fclose(f); delete s;
+			set_error("%s: truncated slabs of level %d (header claims %llu, the file has %llu bytes left)", path, m, (unsigned long long)(2 * n), (unsigned long long)(file_bytes - (uint64_t)ftello(f)));
+			return RLERC_ERR_IO;
+		}
 		lv.slabs.resize(n);
 		if (fread(lv.slabs.data(), 2, n, f) != n) { fclose(f); delete s; set_error("%s: truncated slabs of level %d", path, m); return RLERC_ERR_IO; }
 		int rc = build_pointer_map(lv);
+		if (rc == RLERC_OK) rc = validate_columns(lv);
 		if (rc != RLERC_OK) { fclose(f); delete s; return rc; }
+	}
+	} catch (const std::bad_alloc&) {
+		fclose(f); delete s;
+		set_error("%s: out of host memory", path);
+		return RLERC_ERR_NOMEM;
 	}
 	fclose(f);
 	*out = s;
@@ -418,7 +472,10 @@ int rlerc_scene_save(const rlerc_scene* s, const char* path)
 int rlerc_scene_from_maps(const rlerc_map4* maps, int nummaps, rlerc_scene** out)
 {
 	if (!maps || !out || nummaps < 1 || nummaps > RLERC_MAX_MAPS) { set_error("rlerc_scene_from_maps: bad argument"); return RLERC_ERR_ARG; }
-	rlerc_scene* s = new rlerc_scene();
+	*out = nullptr;
+	rlerc_scene* s = nullptr;
+	try {
+	s = new rlerc_scene();
 	s->levels.resize(nummaps);
 	for (int m = 0; m < nummaps; m++)
 	{
@@ -428,6 +485,13 @@ int rlerc_scene_from_maps(const rlerc_map4* maps, int nummaps, rlerc_scene** out
 		lv.sx = src.sx; lv.sy = src.sy; lv.sz = src.sz;
 		lv.map.assign(src.map, src.map + (size_t)src.sx * src.sz * 2);
 		lv.slabs.assign(src.slabs, src.slabs + (size_t)(uint32_t)src.slabs_size);
+		const int rc = validate_columns(lv);                             // the caller's pointer map is a claim too
+		if (rc != RLERC_OK) { delete s; return rc; }
+	}
+	} catch (const std::bad_alloc&) {
+		delete s;
+		set_error("rlerc_scene_from_maps: out of host memory");
+		return RLERC_ERR_NOMEM;
 	}
 	*out = s;
 	return RLERC_OK;

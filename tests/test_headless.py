@@ -92,3 +92,19 @@ def test_headless_frame_against_the_oracle(R, rb, scene_mid, tmp_path, size):
     orgba = rb.orc_unwarp(orm, W, H, cfg.render_size, cfg.rays_casted, cfg.rays_casted_res, owarp)
     dmax, same = rgb_parity(rgb, orgba[:, :, :3])
     assert dmax <= 1 and same >= 0.999, (dmax, same)         # north star: <= 1 LSB per channel, >= 99.9 % identical
+
+
+@pytest.mark.gpu
+def test_headless_multi_gpu_cpp_host(R, scene_mid, tmp_path):
+    """The multi-GPU frame from a C++ host (rlerc_create_multi, include/rlerc.h): examples/headless --gpus N renders the
+    same frame on every GPU of the box and exits non-zero unless it is byte-identical to its single-GPU frame."""
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs two GPUs")
+    path = str(tmp_path / "scene.rle4")
+    scene_mid.save(path)
+    r = subprocess.run([EXE, "--scene", path, "--size", "1024", "768", "--pos", "10000", "-40", "10000", "--out", str(tmp_path / "m"),
+                        "--frames", "64", "--gpus", str(n)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.stdout, r.stderr)
+    assert "is byte-identical to the single-GPU frame" in r.stdout and "fly-through on %d GPUs" % n in r.stdout

@@ -191,3 +191,45 @@ def test_direct_rle_scene(R, rb, scene_rle, tmp_path):
     assert per_col * 16384.0 * 16384.0 < 2.0 ** 31
     with pytest.raises(R.RlercError):
         R.RLE4.synth_rle(100, 256, 256)
+
+
+def test_untrusted_scenes_are_validated(R, scene_small, tmp_path):
+    """a header may claim any size, a pointer map any offset.  The loader compares the claim with the
+    file before allocating, from_maps checks every column against the stream, and a column whose runs claim more solid
+    voxels than it has attributes (the reference's undefined tiny mip levels) loads, with the device copy padded."""
+    import struct
+    p = str(tmp_path / "a.rle4")
+    scene_small.save(p)
+    raw = bytearray(open(p, "rb").read())
+    # level 0 claims 2^31 - 1 slabs: refused from the file length, no 4 GiB allocation
+    huge = bytearray(raw)
+    struct.pack_into("<i", huge, 4 + 12, 0x7fffffff)
+    q = str(tmp_path / "huge.rle4")
+    open(q, "wb").write(huge)
+    with pytest.raises(R.RlercError, match="truncated"):
+        R.RLE4.load(q)
+    # a pointer map that points outside the stream
+    m4, n = scene_small.map4(0)
+    sx, sy, sz, mp, sl = scene_small.level(0)
+    bad_map = mp.copy()
+    bad_map[2 * 7] = n + 5
+    maps = [scene_small.map4(m)[0] for m in range(scene_small.nummaps)]
+    maps[0].map = bad_map.ctypes.data
+    with pytest.raises(R.RlercError, match="outside the slab stream"):
+        R.RLE4.from_maps(maps)
+    # a column whose voxel count is smaller than its runs claim: loads (as in the reference's own files)
+    sx, sy, sz, mp, sl = scene_small.level(scene_small.nummaps - 1)
+    ofs = int(mp[0])
+    assert sl[ofs] >= 1
+    body = bytearray(raw)
+    # find that level in the file: walk the headers
+    pos = 4
+    for m in range(scene_small.nummaps - 1):
+        nsl = struct.unpack_from("<I", body, pos + 12)[0]
+        pos += 16 + 2 * nsl
+    first_run = struct.unpack_from("<H", body, pos + 16 + 2 * (ofs + 2))[0]
+    struct.pack_into("<H", body, pos + 16 + 2 * (ofs + 2), (first_run & 1023) | (63 << 10))     # 63 solid voxels claimed
+    z = str(tmp_path / "inconsistent.rle4")
+    open(z, "wb").write(body)
+    s = R.RLE4.load(z)
+    assert s.nummaps == scene_small.nummaps
