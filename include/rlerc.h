@@ -83,7 +83,10 @@ typedef struct rlerc_frame_config {
 #define RLERC_FLAG_CLIPREGION   1
 /* R/src/core.h:22 HEIGHT_COLOR: the low attribute byte is scaled by the camera height (R/src/Cuda_Render.h:674-676,716-722). */
 #define RLERC_FLAG_HEIGHT_COLOR 2
-/* Both are implemented by the production traversal kernels (lanes_per_ray = 0, 65, 68) only. */
+/* Both are implemented by the production traversal kernels (lanes_per_ray = 0, 65, 68, 69) only. */
+/* R/src/core.h:12 ANTIALIAS: pass 1 is R/bin/shader/colorize_buddha_soft_2xAA.frag instead of colorize_buddha_soft.frag
+ * (R/src/main.cpp:510-522): same texel geometry, its own shading (5:5:5 normal, point light, sky gradient).  rlerc_unwarp only. */
+#define RLERC_FLAG_SHADER_2XAA  4
 
 /* Defaults exactly as R/src/core.h for a W x H window: render_size=W, rays=4W,
  * z_far=80000, mip_distance=W, border=(1-H/W)/2 (=0.125 for 1024x768, main.cpp:774-776). */

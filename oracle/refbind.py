@@ -245,14 +245,16 @@ def orc_render(rm, res, rays_casted, mip_distance=None, z_far=80000, want_ids=Fa
     return warp, ids, dict(zip(COUNTER_NAMES, list(cnt)))
 
 
-def orc_unwarp(rm, W, H, RS, RC, rays_res, warp, ray_begin=0, ray_end=-1, want_texels=False):
+def orc_unwarp(rm, W, H, RS, RC, rays_res, warp, ray_begin=0, ray_end=-1, want_texels=False, shader=0):
     """RGBA8 [H][W][4] (row 0 = top); with want_texels also int32[H][W][2] = (ray row, texel) sampled."""
     warp = np.ascontiguousarray(warp, dtype=np.uint32)
     rgba = np.zeros((H, W, 4), np.uint8)
     tex = np.zeros((H, W, 2), np.int32) if want_texels else None
     port().orc_unwarp_set_texel_output.argtypes = [C.c_void_p]
     port().orc_unwarp_set_texel_output(tex.ctypes.data if want_texels else None)
+    port().orc_unwarp_set_shader(shader)          # 0: colorize_buddha_soft.frag, 1: colorize_buddha_soft_2xAA.frag
     port().orc_unwarp(C.byref(rm), W, H, RS, RC, rays_res, warp.ctypes.data, rgba.ctypes.data, ray_begin, ray_end)
+    port().orc_unwarp_set_shader(0)
     port().orc_unwarp_set_texel_output(None)
     return (rgba, tex) if want_texels else rgba
 

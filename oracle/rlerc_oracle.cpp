@@ -453,6 +453,11 @@ int orc_render_flags(const void* raymap, int res, int mip_distance, int z_far, u
  * quantisation of the GL_RGBA8 FBO it renders into (R/src/GL_Main.h:151): round(clamp(c)*255). */
 static int32_t* g_texel_out = 0;   /* optional int32[H][W][2] = {ray row iy, texel ix} chosen per pixel */
 void orc_unwarp_set_texel_output(int32_t* p) { g_texel_out = p; }
+/* 0: colorize_buddha_soft.frag (the shipped configuration); 1: colorize_buddha_soft_2xAA.frag (the -DANTIALIAS build,
+ * R/src/main.cpp:510-522): the same texel geometry without the RAYS_CASTED_RES / RAYS_CASTED factor (frag:62), its own
+ * shading (frag:79-139: 5:5:5 normal from the attribute, point light, two-term tone curve, vertical sky gradient). */
+static int g_shader = 0;
+void orc_unwarp_set_shader(int s) { g_shader = s; }
 
 int orc_unwarp(const void* raymap, int W, int H, int RS, int RC, int rays_casted_res, const uint32_t* warp, uint8_t* rgba,
                int ray_begin, int ray_end)
@@ -489,7 +494,7 @@ int orc_unwarp(const void* raymap, int W, int H, int RS, int RC, int rays_casted
 			const float x_pre = (ostep * ang3 + ang2 * (1 - ostep));                     /* frag:53 */
 			float ty = seg_dn * (ofs_add[1] + x_pre) + seg_up * (ofs_add[0] + 1.0f - x_pre) +
 			           seg_lt * (ofs_add[3] + x_pre) + seg_rt * (ofs_add[2] + 1.0f - x_pre);   /* frag:56-60 */
-			ty = ty * ratio * 0.25f;                                                     /* frag:62 */
+			ty = (g_shader == 1) ? ty * 0.25f : ty * ratio * 0.25f;                      /* frag:62 (2xAA frag:62: no ratio) */
 			const float seg_up_x = rg * seg_up + (1.0f - rg) * seg_dn;                   /* frag:68-71 */
 			const float seg_dn_x = rg * seg_dn + (1.0f - rg) * seg_up;
 			const float seg_rt_x = rg * seg_rt + (1.0f - rg) * seg_lt;
@@ -506,6 +511,30 @@ int orc_unwarp(const void* raymap, int W, int H, int RS, int RC, int rays_casted
 			const float cr = (float)(t & 255u) / 255.0f, cg = (float)((t >> 8) & 255u) / 255.0f;
 			const float cb = (float)((t >> 16) & 255u) / 255.0f, ca = (float)(t >> 24) / 255.0f;
 			float r, g, b, fragz = 0.0f;
+			if (g_shader == 1)                                                           /* colorize_buddha_soft_2xAA.frag:79-139 */
+			{
+				const int x1 = f2i(cr * 255.0f);                                         /* 2xAA frag:84-88: int(c.r*255.0) truncates */
+				const int x2 = f2i(cg * 255.0f) * 256 + x1;
+				const float col16b = float(x2 & 31) / 31.0f, col16g = float((x2 >> 5) & 31) / 31.0f, col16r = float((x2 >> 10) & 31) / 31.0f;
+				if (cb != 1.0f)
+				{
+					const float z = (cb * (1.0f / 256.0f) + ca);                          /* :103-106 */
+					fragz = 0.001f / z;
+					const float pos3dx = z * (scx * 2.0f - 1.0f), pos3dy = z * (scy * 2.0f - 1.0f);
+					const float nx = 2.0f * col16r - 1.0f, ny = 2.0f * col16g - 1.0f, nz = 2.0f * col16b - 1.0f;   /* :108-113 */
+					float lx = pos3dx - 10.0f, ly = pos3dy + 5.0f, lz = z;               /* :115-121 */
+					const float inv = 1.0f / sqrtf(lx * lx + ly * ly + lz * lz);         /* normalize = v * (1/sqrt(dot)) */
+					lx *= inv; ly *= inv; lz *= inv;
+					const float light = nx * lx + ny * ly + nz * lz;                     /* :123 */
+					r = light * 0.9f + light * light * 0.5f;                              /* :131 */
+					g = light * 0.6f + light * light * 0.4f;
+					b = light * 0.3f + light * light * 0.3f;
+				}
+				else { r = 0.3f * (1.0f - scy) + 0.8f * scy; g = r; b = r; }              /* :134 */
+				r = r * 1.1f; g = g * 1.1f; b = b * 1.1f;                                 /* :136 */
+				o[0] = (uint8_t)quant8(r); o[1] = (uint8_t)quant8(g); o[2] = (uint8_t)quant8(b); o[3] = (uint8_t)quant8(fragz);
+				continue;
+			}
 			if (cb != 1.0f)                                                              /* frag:89-121 */
 			{
 				const float zz = (cb * (1.0f / 256.0f) + ca);

@@ -59,7 +59,7 @@ class FrameConfig(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("render_size", C.c_int32),
                 ("rays_casted", C.c_int32), ("rays_casted_res", C.c_int32), ("z_far", C.c_int32),
                 ("mip_distance", C.c_int32), ("border", C.c_float), ("flags", C.c_int32)]
-    CLIPREGION, HEIGHT_COLOR = 1, 2      # R/src/core.h:18,22 as run-time switches
+    CLIPREGION, HEIGHT_COLOR, SHADER_2XAA = 1, 2, 4      # R/src/core.h:18,22,12 as run-time switches
 
     @classmethod
     def default(cls, width, height):

@@ -78,7 +78,7 @@ int check_cfg(const rlerc_frame_config* cfg)
 	if (!cfg) { set_error("null frame config"); return RLERC_ERR_ARG; }
 	if (cfg->width < 4 || cfg->height < 1 || cfg->render_size < 32 || cfg->render_size > 16384 ||
 	    cfg->rays_casted < 4 || cfg->rays_casted_res < 4 || cfg->z_far < 1 || cfg->mip_distance < 1 ||
-	    (cfg->flags & ~(RLERC_FLAG_CLIPREGION | RLERC_FLAG_HEIGHT_COLOR)) != 0)
+	    (cfg->flags & ~(RLERC_FLAG_CLIPREGION | RLERC_FLAG_HEIGHT_COLOR | RLERC_FLAG_SHADER_2XAA)) != 0)
 	{
 		set_error("frame config out of range");
 		return RLERC_ERR_ARG;
@@ -153,6 +153,8 @@ int fill_unwarp(const rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_co
 	U.ofs_add[2] = -rm->p_ofs_min[2] + ofs2;
 	U.ofs_add[3] = -rm->p_ofs_min[3] + ofs3;
 	U.ratio = float(cfg->rays_casted_res) / float(cfg->rays_casted);
+	U.shader = (cfg->flags & RLERC_FLAG_SHADER_2XAA) ? 1 : 0;
+	if (U.shader == 1) U.ratio = 1.0f;                                  // colorize_buddha_soft_2xAA.frag:62 has no ratio factor (x * 1.0f is exact)
 	U.rot_x_gt0 = (rm->rotation.x > 0) ? 1 : 0;
 	U.row_begin = 0; U.row_end = cfg->height;
 	U.ray_begin = 0; U.ray_end = -1;
@@ -389,7 +391,7 @@ int rlerc::render_impl(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_c
 	}
 	TraverseParams P;
 	if ((rc = fill_traverse(c, rm, cfg, ray_begin, ray_end, d_warp, P))) return rc;
-	if (cfg->flags != 0 && !(c->lanes == 0 || c->lanes == 65 || c->lanes == 68 || c->lanes == 69))
+	if ((cfg->flags & (RLERC_FLAG_CLIPREGION | RLERC_FLAG_HEIGHT_COLOR)) != 0 && !(c->lanes == 0 || c->lanes == 65 || c->lanes == 68 || c->lanes == 69))
 	{
 		set_error("frame config flags (CLIPREGION / HEIGHT_COLOR) are implemented by the production traversal kernels only (lanes_per_ray = 0, 65, 68)");
 		return RLERC_ERR_ARG;

@@ -478,7 +478,7 @@ struct UnwarpCol {            // per pixel column (frag:19,24,28-29,42-44)
 	bool left;
 };
 struct UnwarpRow {            // per pixel row (frag:20,25,27,36,38-40)
-	float scy1, ay, A, c2, fyx;
+	float scy, scy1, ay, A, c2, fyx;
 	bool upper;
 };
 
@@ -500,6 +500,7 @@ __device__ __forceinline__ void unwarp_row(const UnwarpParams& P, int pyg, Unwar
 	const float RESX = (float)P.W, RESY = (float)P.H;
 	const float fy = (float)pyg + 0.5f;                              // gl_FragCoord.y
 	const float scy = fy / RESY;                                     // frag:20
+	r.scy = scy;
 	r.scy1 = scy - P.vanish_y;                                       // frag:25
 	r.upper = 0.0f >= r.scy1;                                        // frag:27
 	r.ay = fabsf(r.scy1);
@@ -634,6 +635,36 @@ __device__ __forceinline__ uint32_t unwarp_shade(const UnwarpParams& P, uint32_t
 	return __ldg(P.shade_rgb + (t & 0xffffu)) | ((uint32_t)__ldg(P.shade_alpha + (t >> 16)) << 24);
 }
 
+// The pass-1 shader of the reference's -DANTIALIAS build (R/src/main.cpp:510-522), colorize_buddha_soft_2xAA.frag:79-139:
+// the attribute read as a 5:5:5 normal, a point light at (10, -5) behind the eye, two-term tone curve, vertical sky
+// gradient.  Depends on the fragment position and the depth, so it is evaluated per pixel (frame config flag
+// RLERC_FLAG_SHADER_2XAA; the texel geometry is the same with the ray-row ratio fixed at 1, frag:62).
+__device__ __forceinline__ uint32_t unwarp_shade_2xaa(uint32_t t, float scx, float scy, const float* q)
+{
+	const float cr = q[t & 255u], cg = q[(t >> 8) & 255u], cb = q[(t >> 16) & 255u], ca = q[t >> 24];
+	const int x1 = f2i(cr * 255.0f);                                   // frag:84-88: int(c.r*255.0) truncates
+	const int x2 = f2i(cg * 255.0f) * 256 + x1;
+	const float col16b = (float)(x2 & 31) / 31.0f, col16g = (float)((x2 >> 5) & 31) / 31.0f, col16r = (float)((x2 >> 10) & 31) / 31.0f;
+	float r, g, b, fragz = 0.0f;
+	if (cb != 1.0f)
+	{
+		const float z = (cb * (1.0f / 256.0f) + ca);                    // frag:103-106
+		fragz = 0.001f / z;
+		const float pos3dx = z * (scx * 2.0f - 1.0f), pos3dy = z * (scy * 2.0f - 1.0f);
+		const float nx = 2.0f * col16r - 1.0f, ny = 2.0f * col16g - 1.0f, nz = 2.0f * col16b - 1.0f;   // frag:108-113
+		float lx = pos3dx - 10.0f, ly = pos3dy + 5.0f, lz = z;         // frag:115-121
+		const float inv = 1.0f / sqrtf(lx * lx + ly * ly + lz * lz);
+		lx *= inv; ly *= inv; lz *= inv;
+		const float light = nx * lx + ny * ly + nz * lz;               // frag:123
+		r = light * 0.9f + light * light * 0.5f;                        // frag:131
+		g = light * 0.6f + light * light * 0.4f;
+		b = light * 0.3f + light * light * 0.3f;
+	}
+	else { r = 0.3f * (1.0f - scy) + 0.8f * scy; g = r; b = r; }        // frag:134
+	r = r * 1.1f; g = g * 1.1f; b = b * 1.1f;                           // frag:136
+	return quant8(r) | (quant8(g) << 8) | (quant8(b) << 16) | (quant8(fragz) << 24);
+}
+
 // TEXELS: write (iy << 16) | ix instead of the colour (rlerc_debug_unwarp_texels: per-pixel texel parity against the oracle)
 template <bool TEXELS>
 __global__ void __launch_bounds__(32 * RLERC_UNWARP_WARPS, RLERC_UNWARP_MINB) k_unwarp(const __grid_constant__ UnwarpParams P)
@@ -642,9 +673,11 @@ __global__ void __launch_bounds__(32 * RLERC_UNWARP_WARPS, RLERC_UNWARP_MINB) k_
 	constexpr int TW = RLERC_UNWARP_WARPS * RLERC_UNWARP_QW * 4;     // tile width in pixels
 	__shared__ UnwarpCol s_col[TW];
 	__shared__ UnwarpRow s_row[RLERC_UNWARP_TROWS];
+	__shared__ float q255[256];                                      // i / 255.0f (2xAA shader only)
 	const int lane = threadIdx.x;
 	const int tid = threadIdx.y * 32 + lane;
 	const int tile_px = (int)blockIdx.x * TW, tile_row = P.row_begin + (int)blockIdx.y * RLERC_UNWARP_TROWS;
+	if (P.shader == 1) for (int i = tid; i < 256; i += 32 * RLERC_UNWARP_WARPS) q255[i] = (float)i / 255.0f;
 	for (int i = tid; i < TW + RLERC_UNWARP_TROWS; i += 32 * RLERC_UNWARP_WARPS)
 	{
 		if (i < TW) unwarp_col(P, tile_px + i, s_col[i]);
@@ -686,7 +719,8 @@ __global__ void __launch_bounds__(32 * RLERC_UNWARP_WARPS, RLERC_UNWARP_MINB) k_
 		#pragma unroll
 		for (int k = 0; k < 4; k++) t[k] = take[k] ? __ldg(src[k]) : 0u;
 		#pragma unroll
-		for (int k = 0; k < 4; k++) out[k] = take[k] ? unwarp_shade(P, t[k]) : 0u;
+		for (int k = 0; k < 4; k++)
+			out[k] = !take[k] ? 0u : (P.shader == 1 ? unwarp_shade_2xaa(t[k], s_col[cx + k].scx, rw.scy, q255) : unwarp_shade(P, t[k]));
 	}
 	uint32_t* dst = reinterpret_cast<uint32_t*>(P.rgba) + (size_t)rowi * P.W + px0;
 	if (vec) *reinterpret_cast<uint4*>(dst) = make_uint4(out[0], out[1], out[2], out[3]);

@@ -82,6 +82,7 @@ struct UnwarpParams {
 	const uint32_t* warp_peer[8];
 	const uint32_t* shade_rgb;   // [65536] colour of every attribute value (k_shade_tables)
 	const uint8_t* shade_alpha;  // [65536] smoothing weight of every depth value
+	int shader;              // 0: colorize_buddha_soft.frag, 1: colorize_buddha_soft_2xAA.frag (RLERC_FLAG_SHADER_2XAA)
 	int generic;             // evaluate the shader's texel arithmetic statement by statement (vanishing point beyond 1e6, kernels.cu)
 };
 

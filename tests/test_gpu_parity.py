@@ -715,3 +715,30 @@ def test_multi_gpu_frame_one_process_per_gpu(R):
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert p.returncode == 0, (p.stdout[-3000:], p.stderr[-1500:])
     assert "mismatches 0" in p.stdout
+
+
+def test_unwarp_2xaa_shader_parity(R, rb, gpu, scene_mid):
+    """RLERC_FLAG_SHADER_2XAA: pass 1 of the reference's -DANTIALIAS build (colorize_buddha_soft_2xAA.frag, selected at
+    R/src/main.cpp:510-522) against the oracle's restatement of that shader: <= 1 LSB, >= 99.9 % identical (parity
+    unpinned like every GLSL restatement: there is no GL here)."""
+    import torch
+    gpu.all_to_gpu(scene_mid)
+    gpu.set_lanes_per_ray(0)
+    for wh in ((640, 480), (1920, 1080)):
+        cfg = R.FrameConfig.default(*wh)
+        aa = R.FrameConfig.default(*wh)
+        aa.flags = R.FrameConfig.SHADER_2XAA
+        for pos, rot in few_cameras(-100.0)[:3]:
+            rm = R.RayMap(cfg).get_ray_map(pos, rot)
+            orm, want_warp, _, _ = _oracle(rb, rm, scene_mid, cfg)
+            want = rb.orc_unwarp(orm, cfg.width, cfg.height, cfg.render_size, cfg.rays_casted, cfg.rays_casted_res, want_warp, shader=1)
+            plain = rb.orc_unwarp(orm, cfg.width, cfg.height, cfg.render_size, cfg.rays_casted, cfg.rays_casted_res, want_warp)
+            assert not np.array_equal(want[..., :3], plain[..., :3])          # a different picture ...
+            assert np.array_equal(want[..., 3], plain[..., 3])                # ... with the same smoothing weights
+            _fresh_warp(gpu, cfg)
+            gpu.render(rm, cfg)
+            buf = torch.zeros((cfg.height, cfg.width, 4), dtype=torch.uint8, device="cuda")
+            gpu.unwarp(rm, aa, d_rgba=buf.data_ptr())
+            gpu.sync()
+            mx, same = rgb_parity(buf.cpu().numpy(), want)
+            assert mx <= 1 and same >= 0.999, (wh, rot, mx, same)
