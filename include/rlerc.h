@@ -276,6 +276,24 @@ void* rlerc_group_stream(rlerc_group* g, int ticket);                           
 /* with rlerc_set_timing on the member's context: ms from the first kernel of the ticket's frame to its last barrier */
 int  rlerc_group_last_ms(rlerc_group* g, int ticket, float* ms);
 
+/* ---- LOD streaming: mip-level residency by distance (the reference keeps everything resident,
+ *      R/src/Rle4.cpp:432-438) ------------------------------------------------------------ */
+/* Like rlerc_scene_upload, but only address space is reserved: no level data is resident until rlerc_stream_prepare asks
+ * for it.  `s` is borrowed and has to outlive the context's use of it (chunks are uploaded from it on demand).  Kernels
+ * and results are the same as with a full replica; a frame rendered without the prepare call for its camera fails with
+ * RLERC_ERR_CUDA (a fault on unmapped memory), it never draws a wrong picture. */
+int  rlerc_scene_upload_streamed(rlerc_ctx* c, const rlerc_scene* s);
+typedef struct rlerc_stream_stats {
+	uint64_t resident_bytes, total_bytes;    /* after the call: HBM in use for level data / size of a full replica */
+	uint64_t uploaded_bytes, evicted_bytes;  /* this call */
+	int32_t  chunks_mapped, chunks_unmapped;
+} rlerc_stream_stats;
+/* Make resident what a frame at this camera can touch: of every mip level the z-rows within the distance the traversal
+ * covers while it reads that level (Cuda_Render.h:343-367), plus margin_voxels of look-ahead (level-0 voxels); rows
+ * beyond twice the margin are evicted.  Synchronous; call it between frames.  stats may be NULL. */
+int  rlerc_stream_prepare(rlerc_ctx* c, const float pos[3], const float rot[3], const rlerc_frame_config* cfg,
+                          int margin_voxels, rlerc_stream_stats* stats);
+
 /* ---- plumbing ------------------------------------------------------------------------ */
 int   rlerc_sync(rlerc_ctx* c);
 void* rlerc_stream(rlerc_ctx* c);                    /* cudaStream_t the kernels run on */

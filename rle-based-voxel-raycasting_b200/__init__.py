@@ -68,6 +68,11 @@ class FrameConfig(C.Structure):
         return cfg
 
 
+class StreamStats(C.Structure):
+    _fields_ = [("resident_bytes", C.c_uint64), ("total_bytes", C.c_uint64), ("uploaded_bytes", C.c_uint64),
+                ("evicted_bytes", C.c_uint64), ("chunks_mapped", C.c_int32), ("chunks_unmapped", C.c_int32)]
+
+
 assert C.sizeof(Map4) == 32 and C.sizeof(RayMapGPU) == 896
 
 _lib = None
@@ -94,6 +99,8 @@ _SIGS = {
     "rlerc_scene_upload": (C.c_int, [_P, _P]),
     "rlerc_scene_device_maps": (C.c_int, [_P, _P, C.POINTER(C.c_int)]),
     "rlerc_scene_share": (C.c_int, [_P, _P]),
+    "rlerc_scene_upload_streamed": (C.c_int, [_P, _P]),
+    "rlerc_stream_prepare": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), _P, C.c_int, _P]),
     "rlerc_frame_device": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "rlerc_set_lanes_per_ray": (C.c_int, [_P, C.c_int]),
     "rlerc_has_variants": (C.c_int, []),
@@ -331,6 +338,16 @@ class Renderer:
     # RLE4::all_to_gpu (R/src/Rle4.cpp:432-448)
     def all_to_gpu(self, scene):
         _check(lib().rlerc_scene_upload(self._c, scene._h))
+
+    def all_to_gpu_streamed(self, scene):
+        """LOD streaming: reserve address space only; `stream_prepare` makes resident what a camera needs."""
+        _check(lib().rlerc_scene_upload_streamed(self._c, scene._h))
+        self._streamed_scene = scene            # borrowed by the library: keep it alive
+
+    def stream_prepare(self, pos, rot, cfg, margin_voxels=256):
+        st = StreamStats()
+        _check(lib().rlerc_stream_prepare(self._c, _f3(pos), _f3(rot), C.byref(cfg), margin_voxels, C.byref(st)))
+        return st
 
     def share_scene(self, other):
         """Use the replica `other` (a Renderer on the same device) uploaded; `other` has to stay alive."""

@@ -26,6 +26,7 @@ int set_dev(rlerc_ctx* c)
 
 void free_scene(rlerc_ctx* c)
 {
+	stream_free(c);
 	for (void* p : c->scene_allocs) cudaFree(p);
 	c->scene_allocs.clear();
 	c->nummaps = 0;

@@ -27,6 +27,8 @@ struct FrameSlot {            // one in-flight frame of the pipelined path
 	bool busy = false;
 };
 
+struct rlerc_streamed;             // stream.cu: a streamed replica (virtual address ranges + resident chunks)
+
 struct rlerc_ctx {
 	int device = 0;
 	cudaStream_t stream = nullptr;      // traversal + unwarp
@@ -36,7 +38,8 @@ struct rlerc_ctx {
 	rlerc::LevelDev level[RLERC_MAX_MAPS];
 	int level_sy[RLERC_MAX_MAPS];
 	uint64_t level_slabs[RLERC_MAX_MAPS];
-	std::vector<void*> scene_allocs;    // empty when the replica is borrowed (rlerc_scene_share)
+	std::vector<void*> scene_allocs;    // empty when the replica is borrowed (rlerc_scene_share) or streamed
+	rlerc_streamed* stream_state = nullptr;   // rlerc_scene_upload_streamed
 	// frame resources
 	uint32_t* d_warp = nullptr;
 	size_t warp_bytes = 0;
@@ -77,6 +80,8 @@ namespace rlerc {
 int set_dev(rlerc_ctx* c);
 int ensure(void** p, size_t* have, size_t need, cudaStream_t st, bool zero = true);
 int check_cfg(const rlerc_frame_config* cfg);
+int fill_traverse(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_config* cfg, int ray_begin, int ray_end, uint32_t* d_warp, TraverseParams& P);
+void stream_free(rlerc_ctx* c);    // stream.cu
 int fill_unwarp(const rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_config* cfg, const uint32_t* d_warp, uint8_t* d_rgba, UnwarpParams& U);
 int render_impl(rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_config* cfg,
                 int ray_begin, int ray_end, uint32_t* d_warp, uint32_t* d_ids, bool ids,
