@@ -259,8 +259,10 @@ def main():
     ap.add_argument("--compose", default="pull", choices=["pull", "reduce"],
                     help="N > 1, slices: pull = unwarp bands with texels pulled over NVLink peer memory (csrc/group.cu, default); "
                          "reduce = every GPU unwarps its own pixels of the whole window, one NCCL reduce(sum) to rank 0")
-    ap.add_argument("--mp", default="slices", choices=["slices", "frames"],
-                    help="N > 1: split every frame into ray-plane slices (north-star split, default) or deal whole frames to the GPUs")
+    ap.add_argument("--mp", default="slices", choices=["slices", "frames", "views"],
+                    help="N > 1: split every frame into ray-plane slices (north-star split, default), deal whole frames to the GPUs, or "
+                         "views = BASELINE config 5: every GPU renders its own camera (the path shifted by rank * K / N frames) and the "
+                         "finished frames are gathered on rank 0 over NVLink")
     args = ap.parse_args()
     K, W = max(1, args.steps), max(3, args.warmup)
     rank = int(os.environ.get("RANK", "0"))
@@ -347,14 +349,20 @@ def main():
     scene_megabytes = scene.nbytes() / 1e6
     t0 = time.time()
     slices = world > 1 and args.mp == "slices"
+    views = world > 1 and args.mp == "views"
+
     def make_pipe(scene_, cfg_, rank_, world_, dist_, dst=0, host=None, share_from=None):
+        if views and world_ > 1:
+            return MG.GroupPipe(R, torch, local, scene_, cfg_, depth=F, rank=rank_, world=world_, dist=dist_, lanes=args.lanes,
+                                dst=dst, host=host, share_from=share_from, views=True)
         if args.compose == "reduce" and world_ > 1:
             return MG.FramePipe(R, torch, local, scene_, cfg_, depth=F, rank=rank_, world=world_, dist=dist_, block=args.slice_block,
                                 lanes=args.lanes, compose="reduce" if dst >= 0 else "bands", host=host, share_from=share_from)
         return MG.GroupPipe(R, torch, local, scene_, cfg_, depth=F, rank=rank_, world=world_, dist=dist_, block=args.slice_block,
                             lanes=args.lanes, dst=dst, host=host, share_from=share_from)
 
-    pipe = make_pipe(scene, cfg, rank if slices else 0, world if slices else 1, D if slices else None)
+    grouped = slices or views           # one group over all ranks (flag barriers per frame); else every rank on its own
+    pipe = make_pipe(scene, cfg, rank if grouped else 0, world if grouped else 1, D if grouped else None)
     log("replica uploaded, %d frame slots: %.1f s" % (F, time.time() - t0))
     r = pipe.r[0]
     poses = [path_pose(R, i, K, sy, imrodh) for i in range(K)]
@@ -367,6 +375,9 @@ def main():
     # ---- the timed region: R x K frames, F in flight per GPU
     if slices or world == 1:
         my_maps, myK = raymaps, K
+    elif views:                 # --mp views: every rank flies the same path, shifted by rank * K / N frames: N different cameras at any time
+        sh = (rank * K) // world
+        my_maps, myK = raymaps[sh:] + raymaps[:sh], K
     else:                       # --mp frames: whole frames dealt round-robin, each stays on the GPU that rendered it
         my_maps = raymaps[rank::world]
         myK = len(my_maps)
@@ -382,8 +393,8 @@ def main():
     th = throughput(pipe, my_maps, myK, args.min_seconds)
     wall = time.perf_counter() - wall0
     clocks = sampler.summary() if sampler else None
-    frames_done = th["repeats"] * K
-    if not (slices or world == 1):
+    frames_done = th["repeats"] * K * (world if views else 1)
+    if not (slices or views or world == 1):
         # every rank did repeats * len(my_maps) frames in ms_total; the job is all ranks' frames
         t = torch.tensor([th["repeats"] * myK], dtype=torch.float64, device="cuda")
         dist.all_reduce(t)
@@ -391,7 +402,7 @@ def main():
     fps = frames_done / (th["ms_total"] / 1e3)
     value = WW * HH * fps / 1e6
     # k_dda_states + traversal + k_unwarp per frame on this rank (+ two k_group_barrier with the peer-memory compositor)
-    launches = (5 if (slices and args.compose == "pull") else 3) * th["repeats"] * myK
+    launches = (5 if (slices and args.compose == "pull") else (4 if views else 3)) * th["repeats"] * myK
 
     # ---- latency: one frame at a time, L2 flushed before each (the round-1 `value` method)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
@@ -399,14 +410,15 @@ def main():
     KL = min(K, 200)
     seq_frames = [int(j * K / KL) for j in range(KL)]
     lat = trav_ms = unw_ms = None
-    if slices or world == 1:
+    if slices or views or world == 1:
         barrier()
-        per, trav_ms, unw_ms = sequential_job(torch, pipe, raymaps, seq_frames, flush, r)
+        per, trav_ms, unw_ms = sequential_job(torch, pipe, my_maps, seq_frames, flush, r)
         barrier()
         tot = allmax(sum(per))
-        lat = dict(dist_stats(per), frames=KL, value=WW * HH * KL / (tot / 1e3) / 1e6, frames_per_s=KL / (tot / 1e3),
+        lat = dict(dist_stats(per), frames=KL, value=(world if views else 1) * WW * HH * KL / (tot / 1e3) / 1e6, frames_per_s=(world if views else 1) * KL / (tot / 1e3),
                    how="one frame at a time, 512 MiB L2 flush before each, CUDA events around each frame (%s), this rank; value from the max over ranks of the summed frame times"
-                       % (("traversal slice + barrier + unwarp band with NVLink pull + barrier" if args.compose == "pull" else "traversal slice + unwarp + NCCL reduce") if slices else "k_dda_states + traversal + unwarp"))
+                       % (("traversal slice + barrier + unwarp band with NVLink pull + barrier" if args.compose == "pull" else "traversal slice + unwarp + NCCL reduce") if slices else
+                          ("k_dda_states + traversal + unwarp of this rank's own view + copy to rank 0 over NVLink + barrier" if views else "k_dda_states + traversal + unwarp")))
         trav_ms, unw_ms = allmax(trav_ms), allmax(unw_ms)
     r.set_timing(False)
     kernel_used = r.last_kernel
@@ -429,6 +441,23 @@ def main():
                 torch.cuda.synchronize()
                 ok = ok and bool(np.array_equal(got, solo.cpu().numpy()))
             barrier()
+        composite_identical = ok if rank == 0 else None
+    if views:
+        # every view as it arrived on rank 0 against rank 0's own render of that rank's camera
+        ok = True
+        k_ = pipe.submit(0, my_maps[3 % myK])
+        pipe.drain()
+        barrier()
+        if rank == 0:
+            for rr in range(world):
+                sh = (rr * K) // world
+                want_map = (raymaps[sh:] + raymaps[:sh])[3 % K]
+                solo = torch.zeros((HH, WW, 4), dtype=torch.uint8, device="cuda")
+                r.frame_device(want_map, cfg, 1, 1, 0, solo.data_ptr())
+                torch.cuda.synchronize()
+                got = pipe.view_numpy(k_, rr) if rr != 0 else pipe.image_numpy(k_)[0]
+                ok = ok and bool(np.array_equal(got, solo.cpu().numpy()))
+        barrier()
         composite_identical = ok if rank == 0 else None
 
     # ---- parity of THIS workload against the reference compiled for the host (outside every timed region)
@@ -565,16 +594,19 @@ def main():
         rc = torch.cuda.cudart().cudaHostRegister(host.data_ptr(), nbytes, 0)
         if int(rc) != 0:
             log("cudaHostRegister failed (%s): the copies into the shared host frame will be synchronous" % rc)
+        views_saved = views
+        views = False                       # e2e with host buffers: every rank copies ITS frames to the host itself (no gather on one GPU)
         pipe2 = make_pipe(scene, cfg, rank if slices else 0, world if slices else 1, D if slices else None, dst=-1,
                           host=host if slices else host[rank * F:(rank + 1) * F], share_from=r)
-        maps2 = raymaps if slices else raymaps[rank::world]
+        views = views_saved
+        maps2 = raymaps if slices else (my_maps if views else raymaps[rank::world])
         # host-side frame setup (get_ray_map) is inside the timed region, as in the single-GPU e2e
         for i in range(max(W, 2 * F)):
             pipe2.submit(i, maps2[i % len(maps2)])
         pipe2.drain()
         barrier()
         reps = th["repeats"]
-        my_poses = poses if slices else poses[rank::world]
+        my_poses = poses if slices else (poses[(rank * K) // world:] + poses[:(rank * K) // world] if views else poses[rank::world])
         t0 = time.perf_counter()
         n = 0
         last_slot = 0
@@ -586,7 +618,7 @@ def main():
         pipe2.drain()
         barrier()
         e2e_wall = allmax(time.perf_counter() - t0)
-        e2e_frames = reps * K
+        e2e_frames = reps * K * (world if views else 1)
         # the last frame of the job, as it landed in host memory, against rank 0's own single-GPU frame
         checksum = 0
         if slices:
@@ -707,6 +739,7 @@ def main():
     if rank == 0:
         line = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": th["ms_per_frame"] if (slices or world == 1) else th["ms_total"] / frames_done,
+                "mp": args.mp if world > 1 else None,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic" if not imrodh else "Imrodh.rle4",
                 "frames_per_s": fps, "config": make_config(args.workload, scene_name, cfg),
@@ -719,7 +752,8 @@ def main():
                                         ("every frame split into ray-plane slices x%d (interleaved blocks of %d), full replica per GPU, %s"
                                          % (world, args.slice_block, "every GPU unwarps its band of rows with texels pulled from the owners over NVLink peer memory and pushes the pixels into rank 0's frame; flag barriers in peer memory, no collective moves pixel data"
                                             if args.compose == "pull" else "one NCCL reduce per frame to rank 0") if slices else
-                                         "whole frames dealt round-robin to %d GPUs (full replica each); frames stay on the GPU that rendered them" % world))},
+                                         ("one camera per GPU (the path shifted by rank * K / %d frames), whole frames; every finished frame copied into rank 0's view array over NVLink peer memory, flag barrier per batch (BASELINE config 5)" % world
+                                          if views else "whole frames dealt round-robin to %d GPUs (full replica each); frames stay on the GPU that rendered them" % world)))},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "latency": lat, "roofline": roof, "parity": parity}
         if composite_identical is not None:
             line["composite_identical"] = composite_identical

@@ -257,7 +257,7 @@ int  rlerc_multi_frame_wait(rlerc_multi* m, int ticket);
  * RLERC_GROUP_BLOB_BYTES descriptions (CUDA IPC handles) by any means, connect, then submit the same frames in the same
  * order on every member. */
 typedef struct rlerc_group rlerc_group;
-#define RLERC_GROUP_BLOB_BYTES 256
+#define RLERC_GROUP_BLOB_BYTES 384
 int  rlerc_group_create(rlerc_ctx* c, int rank, int nranks, int depth, int slice_block,
                         const rlerc_frame_config* cfg, rlerc_group** out);
 void rlerc_group_destroy(rlerc_group* g);
@@ -268,6 +268,13 @@ int  rlerc_group_connect(rlerc_group* g, const void* blobs /* nranks * RLERC_GRO
  * dst_rank < 0: every member keeps its band of rows.  host_rgba (may be NULL) = start of the WHOLE frame in host memory:
  * the member that holds the frame (or every member its band) copies it there. */
 int  rlerc_group_submit(rlerc_group* g, const rlerc_raymap* rm, int dst_rank, uint8_t* host_rgba);
+/* View batches (BASELINE config 5: one camera per GPU, finished frames gathered over NVLink): every member renders the
+ * WHOLE frame of its own camera and copies it into slot [rank] of member dst_rank's view array (peer mapping).
+ * rlerc_group_enable_views (before the export / connect exchange) allocates that array on a member that is to receive. */
+int  rlerc_group_enable_views(rlerc_group* g);
+int  rlerc_group_submit_view(rlerc_group* g, const rlerc_raymap* rm, int dst_rank, uint8_t* host_rgba);
+/* the ticket's nranks views on this member: view r at d_views + r * view_stride, [height][width][4] each */
+int  rlerc_group_views(rlerc_group* g, int ticket, uint8_t** d_views, size_t* view_stride);
 int  rlerc_group_wait(rlerc_group* g, int ticket);
 int  rlerc_group_sync(rlerc_group* g);
 /* Device image of the ticket's slot [height][width][4] and the rows this member produces. */

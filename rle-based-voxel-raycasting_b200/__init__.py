@@ -143,6 +143,9 @@ _SIGS = {
     "rlerc_group_export": (C.c_int, [_P, _P]),
     "rlerc_group_connect": (C.c_int, [_P, _P]),
     "rlerc_group_submit": (C.c_int, [_P, _P, C.c_int, _P]),
+    "rlerc_group_enable_views": (C.c_int, [_P]),
+    "rlerc_group_submit_view": (C.c_int, [_P, _P, C.c_int, _P]),
+    "rlerc_group_views": (C.c_int, [_P, C.c_int, C.POINTER(_P), C.POINTER(C.c_size_t)]),
     "rlerc_group_wait": (C.c_int, [_P, C.c_int]),
     "rlerc_group_sync": (C.c_int, [_P]),
     "rlerc_group_image": (C.c_int, [_P, C.c_int, C.POINTER(_P), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
@@ -455,7 +458,7 @@ class Renderer:
         return self.download(self.warp_buffer(cfg), (cfg.rays_casted, cfg.render_size), np.uint32)
 
 
-GROUP_BLOB_BYTES = 256
+GROUP_BLOB_BYTES = 384
 
 
 class Group:
@@ -463,10 +466,12 @@ class Group:
     blocks of ray planes and produces its band of window rows, pulling texels from the other members' warped buffers
     over NVLink.  Members in other processes are reached through CUDA IPC: exchange export() blobs, then connect()."""
 
-    def __init__(self, renderer, cfg, rank=0, world=1, depth=4, block=32):
+    def __init__(self, renderer, cfg, rank=0, world=1, depth=4, block=32, views=False):
         self._g = C.c_void_p()
         self.r, self.cfg, self.rank, self.world, self.depth, self.block = renderer, cfg, rank, world, depth, block
         _check(lib().rlerc_group_create(renderer._c, rank, world, depth, block, C.byref(cfg), C.byref(self._g)))
+        if views:
+            _check(lib().rlerc_group_enable_views(self._g))
 
     def export(self):
         buf = (C.c_uint8 * GROUP_BLOB_BYTES)()
@@ -495,6 +500,16 @@ class Group:
     def submit(self, raymap_gpu, dst=0, host=None):
         """Enqueue the next frame (the same call, in the same order, on every member). Returns its ticket."""
         return _check(lib().rlerc_group_submit(self._g, C.byref(raymap_gpu), dst, _ptr(host) if host is not None else None))
+
+    def submit_view(self, raymap_gpu, dst=0, host=None):
+        """View batch: this member renders the whole frame of ITS camera and copies it to member dst's view array."""
+        return _check(lib().rlerc_group_submit_view(self._g, C.byref(raymap_gpu), dst, _ptr(host) if host is not None else None))
+
+    def views(self, ticket):
+        """(device pointer of the ticket's view array on this member, bytes between views)."""
+        p, st = C.c_void_p(), C.c_size_t()
+        _check(lib().rlerc_group_views(self._g, ticket, C.byref(p), C.byref(st)))
+        return p.value, st.value
 
     def wait(self, ticket):
         _check(lib().rlerc_group_wait(self._g, ticket))

@@ -48,6 +48,8 @@ struct GroupBlob {                      // what a member tells the others (RLERC
 	uint64_t warp_ptr, img_ptr, flags_ptr;          // addresses in the owner's process
 	uint64_t warp_slot_bytes, img_slot_bytes;
 	cudaIpcMemHandle_t warp_h, img_h, flags_h;
+	uint64_t views_ptr;                              // 0: the member takes no view batches (rlerc_group_enable_views)
+	cudaIpcMemHandle_t views_h;
 };
 static_assert(sizeof(GroupBlob) <= RLERC_GROUP_BLOB_BYTES, "blob size");
 
@@ -95,11 +97,13 @@ struct rlerc_group {
 	uint32_t* warp = nullptr;           // [depth][rays_casted][render_size]
 	uint8_t* img = nullptr;             // [depth][height][width][4]
 	uint32_t* flags = nullptr;          // [depth][2][RLERC_GROUP_MAX]
+	uint8_t* views = nullptr;           // [depth][nranks][height][width][4]: where the members' finished views arrive (rlerc_group_enable_views)
+	uint8_t* views_peer[RLERC_GROUP_MAX];
 	size_t warp_slot_bytes = 0, img_slot_bytes = 0;
 	const uint32_t* warp_peer[RLERC_GROUP_MAX];
 	uint8_t* img_peer[RLERC_GROUP_MAX];
 	uint32_t* flags_peer[RLERC_GROUP_MAX];
-	void* opened[RLERC_GROUP_MAX][3];   // IPC mappings to close
+	void* opened[RLERC_GROUP_MAX][4];   // IPC mappings to close
 	bool connected = false;
 	std::vector<GroupSlot> slot;
 	int next_ticket = 0;
@@ -141,6 +145,7 @@ int rlerc_group_create(rlerc_ctx* c, int rank, int nranks, int depth, int slice_
 	g->c = c; g->rank = rank; g->n = nranks; g->depth = depth; g->block = slice_block; g->cfg = *cfg;
 	memset(g->warp_peer, 0, sizeof(g->warp_peer)); memset(g->img_peer, 0, sizeof(g->img_peer));
 	memset(g->flags_peer, 0, sizeof(g->flags_peer)); memset(g->opened, 0, sizeof(g->opened));
+	memset(g->views_peer, 0, sizeof(g->views_peer));
 	g->warp_slot_bytes = ((size_t)cfg->rays_casted * cfg->render_size * 4 + 255) & ~(size_t)255;
 	g->img_slot_bytes = ((size_t)cfg->width * cfg->height * 4 + 255) & ~(size_t)255;
 	const size_t flag_bytes = (size_t)depth * 2 * RLERC_GROUP_MAX * sizeof(uint32_t);
@@ -177,7 +182,7 @@ void rlerc_group_destroy(rlerc_group* g)
 	if (!g) return;
 	if (g->c) { cudaSetDevice(g->c->device); cudaDeviceSynchronize(); }
 	for (int p = 0; p < RLERC_GROUP_MAX; p++)
-		for (int k = 0; k < 3; k++)
+		for (int k = 0; k < 4; k++)
 			if (g->opened[p][k]) cudaIpcCloseMemHandle(g->opened[p][k]);
 	for (auto& s : g->slot)
 	{
@@ -190,6 +195,7 @@ void rlerc_group_destroy(rlerc_group* g)
 	if (g->warp) cudaFree(g->warp);
 	if (g->img) cudaFree(g->img);
 	if (g->flags) cudaFree(g->flags);
+	if (g->views) cudaFree(g->views);
 	delete g;
 }
 
@@ -206,6 +212,7 @@ int rlerc_group_export(rlerc_group* g, void* blob)
 	CKG(cudaIpcGetMemHandle(&b.warp_h, g->warp));
 	CKG(cudaIpcGetMemHandle(&b.img_h, g->img));
 	CKG(cudaIpcGetMemHandle(&b.flags_h, g->flags));
+	if (g->views) { b.views_ptr = (uint64_t)g->views; CKG(cudaIpcGetMemHandle(&b.views_h, g->views)); }
 	memset(blob, 0, RLERC_GROUP_BLOB_BYTES);
 	memcpy(blob, &b, sizeof(b));
 	return RLERC_OK;
@@ -240,6 +247,7 @@ int rlerc_group_connect(rlerc_group* g, const void* blobs)
 				cudaGetLastError();
 			}
 			g->warp_peer[p] = (const uint32_t*)b.warp_ptr; g->img_peer[p] = (uint8_t*)b.img_ptr; g->flags_peer[p] = (uint32_t*)b.flags_ptr;
+			g->views_peer[p] = (uint8_t*)b.views_ptr;
 		}
 		else
 		{
@@ -251,6 +259,13 @@ int rlerc_group_connect(rlerc_group* g, const void* blobs)
 			CKG(cudaIpcOpenMemHandle(&f, b.flags_h, cudaIpcMemLazyEnablePeerAccess));
 			g->opened[p][2] = f;
 			g->warp_peer[p] = (const uint32_t*)w; g->img_peer[p] = (uint8_t*)i; g->flags_peer[p] = (uint32_t*)f;
+			if (b.views_ptr)
+			{
+				void* v = nullptr;
+				CKG(cudaIpcOpenMemHandle(&v, b.views_h, cudaIpcMemLazyEnablePeerAccess));
+				g->opened[p][3] = v;
+				g->views_peer[p] = (uint8_t*)v;
+			}
 		}
 	}
 	g->connected = true;
@@ -330,6 +345,76 @@ int rlerc_group_submit(rlerc_group* g, const rlerc_raymap* rm, int dst_rank, uin
 	S.busy = true;
 	g->next_ticket++;
 	return ticket;
+}
+
+int rlerc_group_enable_views(rlerc_group* g)
+{
+	if (!g) return RLERC_ERR_ARG;
+	if (g->connected && g->n > 1) { set_error("rlerc_group_enable_views: call it before rlerc_group_export / rlerc_group_connect"); return RLERC_ERR_STATE; }
+	if (g->views) return RLERC_OK;
+	int rc = set_dev(g->c);
+	if (rc) return rc;
+	const size_t bytes = g->img_slot_bytes * g->n * g->depth;
+	cudaError_t e = cudaMalloc((void**)&g->views, bytes);
+	if (e != cudaSuccess) { set_error("rlerc_group_enable_views: cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e)); return e == cudaErrorMemoryAllocation ? RLERC_ERR_NOMEM : RLERC_ERR_CUDA; }
+	CKG(cudaMemset(g->views, 0, bytes));
+	g->views_peer[g->rank] = g->views;
+	return RLERC_OK;
+}
+
+int rlerc_group_submit_view(rlerc_group* g, const rlerc_raymap* rm, int dst_rank, uint8_t* host_rgba)
+{
+	if (!g || !rm) { set_error("rlerc_group_submit_view: null argument"); return RLERC_ERR_ARG; }
+	if (!g->connected) { set_error("rlerc_group_submit_view: the group is not connected"); return RLERC_ERR_STATE; }
+	if (dst_rank >= g->n) { set_error("rlerc_group_submit_view: destination %d is not a member", dst_rank); return RLERC_ERR_ARG; }
+	if (dst_rank >= 0 && !g->views_peer[dst_rank]) { set_error("rlerc_group_submit_view: member %d takes no views (rlerc_group_enable_views before the exchange)", dst_rank); return RLERC_ERR_STATE; }
+	rlerc_ctx* c = g->c;
+	int rc = set_dev(c);
+	if (rc) return rc;
+	const int ticket = g->next_ticket;
+	const int k = ticket % g->depth;
+	const uint32_t gen = (uint32_t)(ticket / g->depth) + 1u;
+	GroupSlot& S = g->slot[k];
+	if (S.busy) { CKG(cudaEventSynchronize(S.done)); S.busy = false; }
+	uint32_t* warp = (uint32_t*)((char*)g->warp + (size_t)k * g->warp_slot_bytes);
+	uint8_t* img = g->img + (size_t)k * g->img_slot_bytes;
+	cudaStream_t const main_stream = c->stream;
+	const bool was_pipelined = c->pipelined;
+	c->stream = S.stream;
+	c->cur_states = &S.d_states; c->cur_states_bytes = &S.states_bytes;
+	c->pipelined = g->depth > 1;
+	if (c->timing) cudaEventRecord(S.t0, S.stream);
+	// this member's OWN camera: the whole frame on this GPU
+	rc = render_impl(c, rm, &g->cfg, 0, -1, warp, nullptr, false);
+	if (!rc) rc = unwarp_impl(c, rm, &g->cfg, warp, img, 0, -1, 0, -1);
+	const size_t frame_bytes = (size_t)g->cfg.width * g->cfg.height * 4;
+	// deliver the finished view into slot [k][rank] of the destination over NVLink (peer mapping), then tell everybody
+	if (!rc && dst_rank >= 0 && g->n > 1)
+	{
+		uint8_t* dst = g->views_peer[dst_rank] + ((size_t)k * g->n + g->rank) * g->img_slot_bytes;
+		cudaError_t e = cudaMemcpyAsync(dst, img, frame_bytes, cudaMemcpyDefault, S.stream);
+		if (e != cudaSuccess) { set_error("rlerc_group_submit_view: peer copy failed: %s", cudaGetErrorString(e)); rc = RLERC_ERR_CUDA; }
+	}
+	if (!rc && g->n > 1) rc = group_barrier(g, k, 1, gen, S.stream);
+	if (c->timing) { cudaEventRecord(S.t1, S.stream); S.timed = true; }
+	c->stream = main_stream;
+	c->cur_states = nullptr; c->cur_states_bytes = nullptr;
+	c->pipelined = was_pipelined;
+	if (rc) return rc;
+	CKG(cudaGetLastError());
+	if (host_rgba) CKG(cudaMemcpyAsync(host_rgba, img, frame_bytes, cudaMemcpyDeviceToHost, S.stream));
+	CKG(cudaEventRecord(S.done, S.stream));
+	S.busy = true;
+	g->next_ticket++;
+	return ticket;
+}
+
+int rlerc_group_views(rlerc_group* g, int ticket, uint8_t** d_views, size_t* view_stride)
+{
+	if (!g || !d_views || ticket < 0 || !g->views) { set_error("rlerc_group_views: bad argument or views not enabled"); return RLERC_ERR_ARG; }
+	*d_views = g->views + (size_t)(ticket % g->depth) * g->n * g->img_slot_bytes;
+	if (view_stride) *view_stride = g->img_slot_bytes;
+	return RLERC_OK;
 }
 
 int rlerc_group_wait(rlerc_group* g, int ticket)

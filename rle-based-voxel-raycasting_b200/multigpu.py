@@ -184,8 +184,11 @@ class GroupPipe:
     its band (and copies it into `host`, a [slots, H, W, 4] uint8 host tensor shared by all ranks, when given)."""
 
     def __init__(self, R, torch, device, scene, cfg, depth=4, rank=0, world=1, dist=None, block=DEFAULT_BLOCK, lanes=0,
-                 dst=0, host=None, share_from=None):
+                 dst=0, host=None, share_from=None, views=False):
+        """views: BASELINE config 5 — every rank renders the WHOLE frame of its own camera and delivers it into rank
+        dst's view array over NVLink (rlerc_group_submit_view) instead of a slice of a common frame."""
         import numpy as np
+        self.views = views
         self.np, self.torch, self.dist, self.cfg = np, torch, dist, cfg
         self.rank, self.world, self.block, self.depth, self.dst, self.host = rank, world, block, depth, dst, host
         r = R.Renderer(device)
@@ -195,7 +198,7 @@ class GroupPipe:
             r.all_to_gpu(scene)
         r.set_lanes_per_ray(lanes)
         self.r = [r]
-        self.g = R.Group(r, cfg, rank, world, depth=depth, block=block)
+        self.g = R.Group(r, cfg, rank, world, depth=depth, block=block, views=views)
         if world > 1:
             self.g.connect_distributed(torch, dist)
         dev = torch.device("cuda", device)
@@ -208,7 +211,10 @@ class GroupPipe:
         host = None
         if self.host is not None:
             host = self.host[(self.last_ticket + 1) % self.depth].data_ptr()
-        self.last_ticket = self.g.submit(raymap_gpu, self.dst, host)
+        if self.views:
+            self.last_ticket = self.g.submit_view(raymap_gpu, self.dst, host)
+        else:
+            self.last_ticket = self.g.submit(raymap_gpu, self.dst, host)
         return self.last_ticket % self.depth
 
     def finish_slot(self, k):
@@ -227,6 +233,11 @@ class GroupPipe:
         """Slot k's [H][W][4] image on this rank as numpy, and the rows this rank produced."""
         ptr, a, b = self.g.image(k)
         return self.r[0].download(ptr, (self.cfg.height, self.cfg.width, 4), self.np.uint8), a, b
+
+    def view_numpy(self, k, r):
+        """View r of slot k as it arrived on this rank (views mode, rank dst)."""
+        ptr, stride = self.g.views(k)
+        return self.r[0].download(ptr + r * stride, (self.cfg.height, self.cfg.width, 4), self.np.uint8)
 
     def close(self):
         self.torch.cuda.synchronize()
