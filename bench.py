@@ -350,8 +350,10 @@ def main():
     t0 = time.time()
     slices = world > 1 and args.mp == "slices"
     views = world > 1 and args.mp == "views"
+    F_default = F
 
-    def make_pipe(scene_, cfg_, rank_, world_, dist_, dst=0, host=None, share_from=None):
+    def make_pipe(scene_, cfg_, rank_, world_, dist_, dst=0, host=None, share_from=None, depth=None):
+        F = depth or F_default
         if views and world_ > 1:
             return MG.GroupPipe(R, torch, local, scene_, cfg_, depth=F, rank=rank_, world=world_, dist=dist_, lanes=args.lanes,
                                 dst=dst, host=host, share_from=share_from, views=True)
@@ -583,7 +585,9 @@ def main():
         # ONE host frame ring shared by all ranks; every rank copies its own part of every frame into it over its own PCIe link
         pull = args.compose == "pull"
         rows = HH if (pull or not slices) else MG.band_rows(HH, world) * world
-        shape = (F if slices else F * world, rows, WW, 4)
+        # frames / views: every rank has its own slots in the shared host ring; keep the ring below 4 GB (8K frames are 133 MB)
+        F2 = F if slices else max(2, min(F, int(4e9 / (world * rows * WW * 4))))
+        shape = (F2 if slices else F2 * world, rows, WW, 4)
         nbytes = int(np.prod(shape))
         name = [None]
         if rank == 0:
@@ -597,7 +601,7 @@ def main():
         views_saved = views
         views = False                       # e2e with host buffers: every rank copies ITS frames to the host itself (no gather on one GPU)
         pipe2 = make_pipe(scene, cfg, rank if slices else 0, world if slices else 1, D if slices else None, dst=-1,
-                          host=host if slices else host[rank * F:(rank + 1) * F], share_from=r)
+                          host=host if slices else host[rank * F2:(rank + 1) * F2], share_from=r, depth=F2)
         views = views_saved
         maps2 = raymaps if slices else (my_maps if views else raymaps[rank::world])
         # host-side frame setup (get_ray_map) is inside the timed region, as in the single-GPU e2e

@@ -242,7 +242,7 @@ int  rlerc_create_multi(const int* devices, int n, rlerc_multi** out);          
 void rlerc_multi_destroy(rlerc_multi* m);
 int  rlerc_multi_count(const rlerc_multi* m);
 rlerc_ctx* rlerc_multi_ctx(rlerc_multi* m, int i);                                     /* member i's context (borrowed) */
-/* frames in flight (default 4) and ray planes per interleaved block (default 32); takes effect at the next frame */
+/* frames in flight (default 8) and ray planes per interleaved block (default 32); takes effect at the next frame */
 int  rlerc_multi_set_depth(rlerc_multi* m, int depth, int slice_block);
 int  rlerc_multi_scene_upload(rlerc_multi* m, const rlerc_scene* s);                   /* RLE4::all_to_gpu on every GPU */
 /* rlerc_render_frame / rlerc_frame_submit / rlerc_frame_wait on all GPUs: get_ray_map -> traversal slices -> unwarp bands

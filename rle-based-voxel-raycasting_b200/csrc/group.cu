@@ -467,19 +467,70 @@ int rlerc_group_last_ms(rlerc_group* g, int ticket, float* ms)
 } // extern "C"
 
 // ---- all members in ONE process: the multi-GPU frame behind the C ABI (rlerc_create(devices, n)) --------
+// One worker thread per GPU issues that member's launches (five per frame): a single host thread issuing 5 N launches per
+// frame is the bottleneck from four GPUs up (measured: 8 GPUs, 1080p: 0.6 ms of launches per frame).
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <string>
+#include <thread>
+
+namespace {
+struct MultiJob { rlerc_raymap rm; uint8_t* host; };
+struct MultiWorker {
+	rlerc_group* g = nullptr;
+	std::thread th;
+	std::mutex mu;
+	std::condition_variable cv;
+	std::deque<MultiJob> q;
+	int done = 0;                    // frames this member has enqueued on its GPU
+	int err = 0;
+	std::string err_text;
+	bool stop = false;
+	void run()
+	{
+		for (;;)
+		{
+			MultiJob job;
+			{
+				std::unique_lock<std::mutex> lk(mu);
+				cv.wait(lk, [&] { return stop || !q.empty(); });
+				if (q.empty()) return;
+				job = q.front();
+				q.pop_front();
+			}
+			const int t = rlerc_group_submit(g, &job.rm, -1, job.host);     // every GPU copies its own band into the host frame
+			{
+				std::lock_guard<std::mutex> lk(mu);
+				if (t < 0 && !err) { err = t; err_text = rlerc_last_error(); }
+				done++;
+			}
+			cv.notify_all();
+		}
+	}
+};
+} // namespace
+
 struct rlerc_multi {
 	std::vector<rlerc_ctx*> ctx;
-	std::vector<rlerc_group*> grp;
+	std::vector<MultiWorker*> worker;
 	rlerc_frame_config cfg;
 	bool have_cfg = false;
-	int depth = 4, block = 32;
+	int depth = 8, block = 32;
 	int next_ticket = 0;
 };
 
 static void multi_drop_groups(rlerc_multi* m)
 {
-	for (rlerc_group* g : m->grp) rlerc_group_destroy(g);
-	m->grp.clear();
+	for (MultiWorker* w : m->worker)
+	{
+		{ std::lock_guard<std::mutex> lk(w->mu); w->stop = true; }
+		w->cv.notify_all();
+		if (w->th.joinable()) w->th.join();
+		rlerc_group_destroy(w->g);
+		delete w;
+	}
+	m->worker.clear();
 	m->have_cfg = false;
 	m->next_ticket = 0;
 }
@@ -490,16 +541,24 @@ static int multi_ensure_groups(rlerc_multi* m, const rlerc_frame_config* cfg)
 	multi_drop_groups(m);
 	const int n = (int)m->ctx.size();
 	int rc = RLERC_OK;
+	std::vector<rlerc_group*> grp;
 	for (int r = 0; r < n && !rc; r++)
 	{
 		rlerc_group* g = nullptr;
 		rc = rlerc_group_create(m->ctx[r], r, n, m->depth, m->block, cfg, &g);
-		if (!rc) m->grp.push_back(g);
+		if (!rc) grp.push_back(g);
 	}
 	std::vector<char> blobs((size_t)n * RLERC_GROUP_BLOB_BYTES);
-	for (int r = 0; r < n && !rc; r++) rc = rlerc_group_export(m->grp[r], blobs.data() + (size_t)r * RLERC_GROUP_BLOB_BYTES);
-	for (int r = 0; r < n && !rc; r++) rc = rlerc_group_connect(m->grp[r], blobs.data());
-	if (rc) { multi_drop_groups(m); return rc; }
+	for (int r = 0; r < n && !rc; r++) rc = rlerc_group_export(grp[r], blobs.data() + (size_t)r * RLERC_GROUP_BLOB_BYTES);
+	for (int r = 0; r < n && !rc; r++) rc = rlerc_group_connect(grp[r], blobs.data());
+	if (rc) { for (rlerc_group* g : grp) rlerc_group_destroy(g); return rc; }
+	for (int r = 0; r < n; r++)
+	{
+		MultiWorker* w = new MultiWorker();
+		w->g = grp[r];
+		w->th = std::thread([w] { w->run(); });
+		m->worker.push_back(w);
+	}
 	m->cfg = *cfg; m->have_cfg = true;
 	return RLERC_OK;
 }
@@ -562,27 +621,30 @@ int rlerc_multi_frame_submit(rlerc_multi* m, const float pos[3], const float rot
 	int rc = check_cfg(cfg);
 	if (rc) return rc;
 	if ((rc = multi_ensure_groups(m, cfg))) return rc;
-	rlerc_raymap rm;
-	memset(&rm, 0, sizeof(rm));
-	if ((rc = rlerc_frame_setup(pos, rot, cfg, &rm))) return rc;
-	int ticket = -1;
-	// every GPU copies its own band of rows into host_rgba over its own PCIe link
-	for (rlerc_group* g : m->grp)
+	MultiJob job;
+	memset(&job.rm, 0, sizeof(job.rm));
+	if ((rc = rlerc_frame_setup(pos, rot, cfg, &job.rm))) return rc;
+	job.host = host_rgba;
+	// the same frame, in the same order, to every member's worker; the ticket is the frame's number
+	for (MultiWorker* w : m->worker)
 	{
-		const int t = rlerc_group_submit(g, &rm, -1, host_rgba);
-		if (t < 0) return t;
-		ticket = t;
+		{ std::lock_guard<std::mutex> lk(w->mu); w->q.push_back(job); }
+		w->cv.notify_all();
 	}
-	m->next_ticket = ticket + 1;
-	return ticket;
+	return m->next_ticket++;
 }
 
 int rlerc_multi_frame_wait(rlerc_multi* m, int ticket)
 {
-	if (!m) return RLERC_ERR_ARG;
-	for (rlerc_group* g : m->grp)
+	if (!m || ticket < 0 || ticket >= m->next_ticket) { set_error("rlerc_multi_frame_wait: bad ticket"); return RLERC_ERR_ARG; }
+	for (MultiWorker* w : m->worker)
 	{
-		int rc = rlerc_group_wait(g, ticket);
+		{
+			std::unique_lock<std::mutex> lk(w->mu);
+			w->cv.wait(lk, [&] { return w->done > ticket; });
+			if (w->err) { set_error("%s", w->err_text.c_str()); return w->err; }
+		}
+		int rc = rlerc_group_wait(w->g, ticket);
 		if (rc) return rc;
 	}
 	return RLERC_OK;

@@ -27,7 +27,6 @@ void set_error(const char* fmt, ...)
 	va_end(ap);
 }
 
-static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 // Walk the slab stream column by column (x fastest, then z) and emit, per column,
 // {offset of the column header, n_runs | first_run << 16}.  The "first run" word is
@@ -427,10 +426,11 @@ int rlerc_scene_load(const char* path, rlerc_scene** out)
 			set_error("%s: level %d has implausible header %d x %d x %d, %llu slabs", path, m, hdr[0], hdr[1], hdr[2], (unsigned long long)n);
 			return RLERC_ERR_FORMAT;
 		}
-		if ((uint64_t)ftello(f) + 2 * n > file_bytes)
+		const uint64_t at = (uint64_t)ftello(f);
+		if (at + 2 * n > file_bytes)
 		{
 			fclose(f); delete s;
-			set_error("%s: truncated slabs of level %d (header claims %llu, the file has %llu bytes left)", path, m, (unsigned long long)(2 * n), (unsigned long long)(file_bytes - (uint64_t)ftello(f)));
+			set_error("%s: truncated slabs of level %d (header claims %llu, the file has %llu bytes left)", path, m, (unsigned long long)(2 * n), (unsigned long long)(file_bytes - at));
 			return RLERC_ERR_IO;
 		}
 		lv.slabs.resize(n);
