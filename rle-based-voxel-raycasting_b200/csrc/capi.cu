@@ -144,6 +144,10 @@ int fill_unwarp(const rlerc_ctx* c, const rlerc_raymap* rm, const rlerc_frame_co
 	U.W = cfg->width; U.H = cfg->height;
 	U.RS = cfg->render_size; U.RC = cfg->rays_casted;
 	const float border = rm->border;
+	{
+		const float RESX = (float)cfg->width, RESY = (float)cfg->height;
+		U.border = (RESX - RESY) / (RESX * 2);                            // colorize_buddha_soft.frag:22
+	}
 	U.vanish_x = 1 - rm->vanishing_point_2d.x;
 	U.vanish_y = (1 - rm->vanishing_point_2d.y - border) * float(cfg->width) / float(cfg->height);
 	const float ofs1 = 4 * float(rm->res[0]) / float(cfg->rays_casted_res);

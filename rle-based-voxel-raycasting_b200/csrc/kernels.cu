@@ -514,7 +514,7 @@ __device__ __forceinline__ void unwarp_row(const UnwarpParams& P, int pyg, Unwar
 __device__ __forceinline__ void unwarp_texel(const UnwarpParams& P, const UnwarpCol& c, const UnwarpRow& r, int& iy, int& ix)
 {
 	const float RESX = (float)P.W, RESY = (float)P.H;
-	const float border = (RESX - RESY) / (RESX * 2);                 // frag:22
+	const float border = P.border;                                   // frag:22, evaluated once on the host (same IEEE operations)
 	const bool ostep = 0.0f >= r.ay - c.axr;                          // frag:29
 	float x_pre, o2;
 	if (ostep)
@@ -543,8 +543,8 @@ __device__ __forceinline__ void unwarp_texel(const UnwarpParams& P, const Unwarp
 	// GL_NEAREST + CLAMP_TO_EDGE (R/src/GL_Main.cpp:154-157): texel = floor(coord * size), clamped
 	ix = f2i(floorf(tx * (float)P.RS));
 	iy = f2i(floorf(ty * (float)P.RC));
-	ix = ix < 0 ? 0 : (ix >= P.RS ? P.RS - 1 : ix);
-	iy = iy < 0 ? 0 : (iy >= P.RC ? P.RC - 1 : iy);
+	ix = max(0, min(ix, P.RS - 1));
+	iy = max(0, min(iy, P.RC - 1));
 }
 
 // The same texel with every statement of the shader evaluated as written (frag:19-77).  Used when the vanishing point is
@@ -666,7 +666,9 @@ __device__ __forceinline__ uint32_t unwarp_shade_2xaa(uint32_t t, float scx, flo
 }
 
 // TEXELS: write (iy << 16) | ix instead of the colour (rlerc_debug_unwarp_texels: per-pixel texel parity against the oracle)
-template <bool TEXELS>
+// RARE: any of the uncommon modes is on (multi-GPU slices / pull, the 2xAA shader, the generic texel arithmetic); the
+// single-GPU frame of the shipped configuration runs the instantiation without them.
+template <bool TEXELS, bool RARE>
 __global__ void __launch_bounds__(32 * RLERC_UNWARP_WARPS, RLERC_UNWARP_MINB) k_unwarp(const __grid_constant__ UnwarpParams P)
 {
 	// the tile's column and row invariants, computed once per block
@@ -677,7 +679,7 @@ __global__ void __launch_bounds__(32 * RLERC_UNWARP_WARPS, RLERC_UNWARP_MINB) k_
 	const int lane = threadIdx.x;
 	const int tid = threadIdx.y * 32 + lane;
 	const int tile_px = (int)blockIdx.x * TW, tile_row = P.row_begin + (int)blockIdx.y * RLERC_UNWARP_TROWS;
-	if (P.shader == 1) for (int i = tid; i < 256; i += 32 * RLERC_UNWARP_WARPS) q255[i] = (float)i / 255.0f;
+	if (RARE && P.shader == 1) for (int i = tid; i < 256; i += 32 * RLERC_UNWARP_WARPS) q255[i] = (float)i / 255.0f;
 	for (int i = tid; i < TW + RLERC_UNWARP_TROWS; i += 32 * RLERC_UNWARP_WARPS)
 	{
 		if (i < TW) unwarp_col(P, tile_px + i, s_col[i]);
@@ -697,12 +699,12 @@ __global__ void __launch_bounds__(32 * RLERC_UNWARP_WARPS, RLERC_UNWARP_MINB) k_
 	for (int k = 0; k < 4; k++)
 	{
 		int iy, ix;
-		if (P.generic) unwarp_texel_generic(P, px0 + k, P.H - 1 - rowi, iy, ix);
+		if (RARE && P.generic) unwarp_texel_generic(P, px0 + k, P.H - 1 - rowi, iy, ix);
 		else unwarp_texel(P, s_col[cx + k], rw, iy, ix);
 		take[k] = px0 + k < P.W;
-		if (P.ray_end >= 0 && (iy < P.ray_begin || iy >= P.ray_end)) take[k] = false;          // slice mode
+		if (RARE && P.ray_end >= 0 && (iy < P.ray_begin || iy >= P.ray_end)) take[k] = false;          // slice mode
 		const uint32_t* base = P.warp;
-		if (P.slice_n > 1)
+		if (RARE && P.slice_n > 1)
 		{
 			const int owner = (iy / P.slice_block) % P.slice_n;
 			if (P.peer_n > 1) base = P.warp_peer[owner];                                       // pull over NVLink
@@ -720,7 +722,7 @@ __global__ void __launch_bounds__(32 * RLERC_UNWARP_WARPS, RLERC_UNWARP_MINB) k_
 		for (int k = 0; k < 4; k++) t[k] = take[k] ? __ldg(src[k]) : 0u;
 		#pragma unroll
 		for (int k = 0; k < 4; k++)
-			out[k] = !take[k] ? 0u : (P.shader == 1 ? unwarp_shade_2xaa(t[k], s_col[cx + k].scx, rw.scy, q255) : unwarp_shade(P, t[k]));
+			out[k] = !take[k] ? 0u : ((RARE && P.shader == 1) ? unwarp_shade_2xaa(t[k], s_col[cx + k].scx, rw.scy, q255) : unwarp_shade(P, t[k]));
 	}
 	uint32_t* dst = reinterpret_cast<uint32_t*>(P.rgba) + (size_t)rowi * P.W + px0;
 	if (vec) *reinterpret_cast<uint4*>(dst) = make_uint4(out[0], out[1], out[2], out[3]);
@@ -735,8 +737,10 @@ void launch_unwarp(const UnwarpParams& p, cudaStream_t st, bool texels)
 	const int qpb = RLERC_UNWARP_QW * RLERC_UNWARP_WARPS;
 	dim3 block(32, RLERC_UNWARP_WARPS, 1);
 	dim3 grid((quads + qpb - 1) / qpb, (rows + RLERC_UNWARP_TROWS - 1) / RLERC_UNWARP_TROWS, 1);
-	if (texels) k_unwarp<true><<<grid, block, 0, st>>>(p);
-	else k_unwarp<false><<<grid, block, 0, st>>>(p);
+	const bool rare = p.generic || p.shader != 0 || p.slice_n > 1 || p.ray_end >= 0;
+	if (texels) k_unwarp<true, true><<<grid, block, 0, st>>>(p);
+	else if (rare) k_unwarp<false, true><<<grid, block, 0, st>>>(p);
+	else k_unwarp<false, false><<<grid, block, 0, st>>>(p);
 }
 
 

@@ -70,6 +70,7 @@ struct UnwarpParams {
 	int W, H;                // window
 	int RS, RC;              // warped buffer: RS texels wide (along a ray), RC rows (rays)
 	float vanish_x, vanish_y;
+	float border;            // (RESX - RESY) / (RESX * 2), frag:22
 	float ofs_add[4];
 	float ratio;             // RAYS_CASTED_RES / RAYS_CASTED
 	int rot_x_gt0;

@@ -26,7 +26,7 @@ M = {
         ("__device__ __noinline__ int coop_span(", "cooperative span shaders"), ("void long_column(", "long_column (lane <-> run)"),
         ("// ---- B0. rising-horizon", "B0 rising-horizon path"),
         ("// ---- B1. ownership-resolved", "B1 ownership-resolved path"), ("// ---- E. one event-loop iteration", "event loop (owner lane)"),
-        ("// ---- S. shade the short spans", "S deferred shading")]),
+        ("// SHADE (S): the short spans", "S deferred shading")]),
 }
 acc, T, C = {}, 0, 0
 for ln in sys.stdin:
