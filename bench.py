@@ -42,6 +42,10 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# Frames in flight live on one stream each; with the default of 8 hardware queues several streams share a queue and a
+# kernel that waits (the flag barriers of the multi-GPU path) holds up the unrelated kernels queued behind it.  Has to be in
+# the environment before the CUDA context exists (the library sets it too, rlerc_create).
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 WORKLOADS = {
     # name: (scene kind, base size (sx, sy, sz), tiling, window, description)
@@ -250,7 +254,7 @@ def main():
                     help="traversal kernel (rlerc_set_lanes_per_ray): 0 = automatic (k_traverse_f, or k_traverse_p for small launches), "
                          "65 = k_traverse_f, 68 = k_traverse_p, 1..32 = k_traverse<lanes>")
     ap.add_argument("--inflight", type=int, default=0,
-                    help="frames in flight per GPU in the throughput measurements (0 = 8 up to four GPUs, 2 per GPU beyond: a slice of a frame "
+                    help="frames in flight per GPU in the throughput measurements (0 = 8 on one GPU, 16 on several: a slice of a frame "
                          "is bound by its longest ray planes, not by the GPU, so the GPUs are kept busy by more frames in flight)")
     ap.add_argument("--min-seconds", type=float, default=0.6, help="the K-frame job is repeated until the timed region lasts this long")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -267,7 +271,7 @@ def main():
     K, W = max(1, args.steps), max(3, args.warmup)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    F = args.inflight if args.inflight > 0 else max(8, min(16, 2 * world))
+    F = args.inflight if args.inflight > 0 else (8 if world == 1 else 16)
     local = int(os.environ.get("LOCAL_RANK", "0"))
     log = (lambda m: print("[bench r%d] %s" % (rank, m), file=sys.stderr, flush=True))
 

@@ -192,6 +192,10 @@ int rlerc_create(int device, rlerc_ctx** out)
 {
 	if (!out) { set_error("rlerc_create: null out"); return RLERC_ERR_ARG; }
 	*out = nullptr;
+	// One stream per frame in flight (rlerc_frame_submit, groups): with the default of 8 hardware queues streams share
+	// queues, and a kernel that waits (k_group_barrier) holds up unrelated kernels queued behind it.  Only effective if
+	// the CUDA context does not exist yet; a host that created it earlier sets the variable itself.
+	setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
 	int n = 0;
 	cudaError_t e = cudaGetDeviceCount(&n);
 	if (e != cudaSuccess || n < 1) { set_error("no CUDA device: %s", cudaGetErrorString(e)); return RLERC_ERR_CUDA; }

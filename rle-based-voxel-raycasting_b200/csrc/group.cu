@@ -135,7 +135,7 @@ int rlerc_group_create(rlerc_ctx* c, int rank, int nranks, int depth, int slice_
 	*out = nullptr;
 	int rc = check_cfg(cfg);
 	if (rc) return rc;
-	if (nranks < 1 || nranks > RLERC_GROUP_MAX || rank < 0 || rank >= nranks || depth < 1 || depth > 16 || slice_block < 1)
+	if (nranks < 1 || nranks > RLERC_GROUP_MAX || rank < 0 || rank >= nranks || depth < 1 || depth > 64 || slice_block < 1)
 	{
 		set_error("rlerc_group_create: bad group shape (rank %d of %d, depth %d, block %d; at most %d members)", rank, nranks, depth, slice_block, RLERC_GROUP_MAX);
 		return RLERC_ERR_ARG;
@@ -293,6 +293,7 @@ int rlerc_group_submit(rlerc_group* g, const rlerc_raymap* rm, int dst_rank, uin
 	int rc = set_dev(c);
 	if (rc) return rc;
 	const int ticket = g->next_ticket;
+	if (dst_rank == RLERC_GROUP_DST_ROTATE) dst_rank = ticket % g->n;      // frame t is assembled on member t mod n
 	const int k = ticket % g->depth;
 	const uint32_t gen = (uint32_t)(ticket / g->depth) + 1u;
 	GroupSlot& S = g->slot[k];

@@ -441,9 +441,12 @@ __device__ __forceinline__ void ray_ctx_init(const TraverseParams& P, const Filt
 #endif
 
 // The traversal kernels are launched with programmatic stream serialization behind k_dda_states and never wait for it
-// as a whole; before a thread leaves, it does (normally long over by then): whatever follows in the stream — the next
-// frame's k_dda_states into the same buffers — must not start while the old one still writes.
-#define RLERC_EXIT_AFTER_PREPASS() asm volatile("griddepcontrol.wait;" ::: "memory")
+// as a whole, but whatever follows in the stream — the next frame's k_dda_states into the same buffers — must not
+// start while the old one still writes: ONE thread of the grid waits for the pre-pass before it leaves, which keeps the
+// grid (not its other blocks) alive until then.  (Until round 2 every thread waited: a ray plane that looks at the
+// ground is done in a third of the pre-pass's ~0.1 ms and then held its block's registers and shared memory idle —
+// invisible in a full frame, a fifth of the time of the small slice launches of the multi-GPU mode.)
+#define RLERC_EXIT_AFTER_PREPASS() do { if (blockIdx.x == 0 && threadIdx.x == 0) asm volatile("griddepcontrol.wait;" ::: "memory"); } while (0)
 
 __host__ __device__ inline int f_words_per_warp(int mask_words)
 {

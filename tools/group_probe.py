@@ -2,6 +2,7 @@
 single-GPU frame, then frames/s with `depth` frames in flight and one frame at a time.
 usage: torchrun --nproc-per-node N tools/group_probe.py [WORKLOAD] [FRAMES] [DEPTH]      (N = 1 works too)"""
 import ctypes as C, importlib, os, sys, time
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", os.environ.get("PROBE_CONNECTIONS", "32"))
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np
@@ -68,7 +69,7 @@ run(1, 0)
 reps_t = torch.tensor([max(1, int(0.5 / max(run(1, 0) * K, 1e-4)))], device="cuda")
 if world > 1: dist.all_reduce(reps_t, op=dist.ReduceOp.MAX)       # every member has to submit the SAME frames
 reps = int(reps_t.cpu()[0])
-ms_push = 1e3 * run(reps, 0); ms_band = 1e3 * run(reps, -1)
+ms_push = 1e3 * run(reps, 0); ms_band = 1e3 * run(reps, -1); ms_rot = 1e3 * run(reps, -2)
 # ---- parity again after many generations of every slot (stale data in any cache would show here)
 for i in (1, K - 1):
     t = g.submit(maps[i], 0); g.wait(t); barrier()
@@ -90,8 +91,8 @@ print("  rank %d: traversal %.3f ms, unwarp %.3f ms, whole frame incl. barriers 
 lat_t = torch.tensor([sum(lat) / K], device="cuda")
 if world > 1: dist.all_reduce(lat_t, op=dist.ReduceOp.MAX)
 if rank == 0:
-    print("group_probe %s N=%d depth=%d: mismatches %d | pipelined %.3f ms/frame to rank 0, %.3f ms/frame as bands | one at a time %.3f ms/frame | kernel %s"
-          % (workload, world, depth, bad, ms_push, ms_band, float(lat_t.cpu()[0]), r.last_kernel), flush=True)
+    print("group_probe %s N=%d depth=%d: mismatches %d | pipelined %.3f ms/frame to rank 0, %.3f ms/frame as bands, %.3f rotating the destination | one at a time %.3f ms/frame | kernel %s"
+          % (workload, world, depth, bad, ms_push, ms_band, ms_rot, float(lat_t.cpu()[0]), r.last_kernel), flush=True)
 g.close(); r.close()
 if world > 1: dist.destroy_process_group()
 sys.exit(1 if bad else 0)
