@@ -269,7 +269,7 @@ int  rlerc_group_connect(rlerc_group* g, const void* blobs /* nranks * RLERC_GRO
  * the member that holds the frame (or every member its band) copies it there. */
 int  rlerc_group_submit(rlerc_group* g, const rlerc_raymap* rm, int dst_rank, uint8_t* host_rgba);
 /* dst_rank = RLERC_GROUP_DST_ROTATE: frame t is assembled on member t mod nranks (spreads the NVLink ingest over all GPUs) */
-#define RLERC_GROUP_DST_ROTATE (-2)
+enum { RLERC_GROUP_DST_ROTATE = -2 };
 /* View batches (BASELINE config 5: one camera per GPU, finished frames gathered over NVLink): every member renders the
  * WHOLE frame of its own camera and copies it into slot [rank] of member dst_rank's view array (peer mapping).
  * rlerc_group_enable_views (before the export / connect exchange) allocates that array on a member that is to receive. */
