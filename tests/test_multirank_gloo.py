@@ -139,3 +139,76 @@ def test_frame_farm_deals_and_gathers_whole_frames(tmp_path, nframes):
     port = 31500 + (os.getpid() % 2000) + nframes
     mp.spawn(_farm_worker, args=(2, port, out, nframes), nprocs=2, join=True)
     assert open(out).read() == "1"
+
+
+def _pull_worker(rank, world, port, out_path, block):
+    """The round-2 compositor (csrc/group.cu) with the oracle standing in for the kernels and gloo for NVLink: every rank
+    traverses its interleaved blocks of ray planes into ITS warped buffer, then produces its band of window rows, taking
+    every texel from the buffer of the rank that owns the texel's ray plane."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    R = importlib.import_module("rle-based-voxel-raycasting_b200")
+    MG = importlib.import_module("rle-based-voxel-raycasting_b200.multigpu")
+    from oracle import refbind as rb
+    from util import few_cameras, oracle_raymap
+    scene = R.RLE4.synth(0, 64, 64, 64, seed=1)
+    cfg = R.FrameConfig.default(256, 190)                       # a height the band size does not divide
+    pos, rot = few_cameras(-40.0)[2]
+    rm = R.RayMap(cfg).get_ray_map(pos, rot)
+    orm = oracle_raymap(rb, rm, scene)
+    count = min(rm.map_line_count, cfg.rays_casted)
+    # 1. traversal of the owned ray planes only (rows of the others stay zero in this rank's buffer)
+    mine = np.zeros((cfg.rays_casted, cfg.render_size), np.uint32)
+    own = np.array(MG.owned_mask(count, block, world, rank), bool)
+    b = 0
+    while b < count:
+        if own[b]:
+            e = b
+            while e < count and own[e]:
+                e += 1
+            w, _, _ = rb.orc_render(orm, cfg.render_size, cfg.rays_casted, cfg.mip_distance, cfg.z_far, ray_begin=b, ray_end=e)
+            mine[b:e] = w[b:e]
+            b = e
+        else:
+            b += 1
+    # 2. "peer memory": every rank can read every rank's buffer
+    bufs = [torch.zeros(mine.shape, dtype=torch.int32) for _ in range(world)]
+    dist.all_gather(bufs, torch.from_numpy(mine.view(np.int32).copy()))
+    bufs = [t.numpy().view(np.uint32) for t in bufs]
+    # 3. this rank's band of rows: texel (iy, ix) of every pixel from the owner of ray plane iy
+    rows = MG.band_rows(cfg.height, world)
+    r0, r1 = min(cfg.height, rank * rows), min(cfg.height, (rank + 1) * rows)
+    _, tex = rb.orc_unwarp(orm, cfg.width, cfg.height, cfg.render_size, cfg.rays_casted, cfg.rays_casted_res, mine, want_texels=True)
+    iy, ix = tex[r0:r1, :, 0], tex[r0:r1, :, 1]
+    owner = (iy // block) % world
+    pulled = np.zeros((cfg.rays_casted, cfg.render_size), np.uint32)          # the texels this band samples, each from its owner
+    for p in range(world):
+        sel = owner == p
+        pulled[iy[sel], ix[sel]] = bufs[p][iy[sel], ix[sel]]
+    band = rb.orc_unwarp(orm, cfg.width, cfg.height, cfg.render_size, cfg.rays_casted, cfg.rays_casted_res, pulled)[r0:r1]
+    # 4. the bands assembled on rank 0 (the product pushes them there over NVLink)
+    padded = np.zeros((rows, cfg.width, 4), np.uint8)
+    padded[:r1 - r0] = band
+    parts = [torch.zeros(padded.shape, dtype=torch.uint8) for _ in range(world)] if rank == 0 else None
+    dist.gather(torch.from_numpy(padded), parts, dst=0)
+    if rank == 0:
+        got = np.concatenate([t.numpy() for t in parts], axis=0)[:cfg.height]
+        full_warp, _, _ = rb.orc_render(orm, cfg.render_size, cfg.rays_casted, cfg.mip_distance, cfg.z_far)
+        full = rb.orc_unwarp(orm, cfg.width, cfg.height, cfg.render_size, cfg.rays_casted, cfg.rays_casted_res, full_warp)
+        open(out_path, "w").write("%d %d" % (bool(np.array_equal(got, full)), int((owner != rank).sum())))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("block", [32, 7])
+def test_two_rank_pull_compositor_equals_single(tmp_path, block):
+    """csrc/group.cu's scheme on CPU: slices traversed per rank, bands unwarped per rank with texels pulled from the owning
+    rank, bands assembled on rank 0 == the single-process frame, byte for byte."""
+    out = str(tmp_path / "pull.txt")
+    port = 33500 + (os.getpid() % 2000) + block
+    mp.spawn(_pull_worker, args=(2, port, out, block), nprocs=2, join=True)
+    ok, remote = (int(v) for v in open(out).read().split())
+    assert ok == 1
+    assert remote > 0              # rank 0's band really needed texels of the other rank
