@@ -785,3 +785,42 @@ def test_lod_streaming_frames_equal_full_replica(R, rb, gpu):
     assert np.array_equal(st.read_warp(cfg), want)
     st.close()
     full.close()
+
+
+def test_view_batch_two_gpus_in_one_process(R, scene_mid):
+    """BASELINE config 5 in small: every GPU renders the whole frame of ITS OWN camera and delivers it into GPU 0's view
+    array over NVLink (rlerc_group_enable_views / rlerc_group_submit_view); each view equals the single-GPU frame of
+    that camera, also with frames in flight and after the slots have been recycled."""
+    import torch
+    n = min(torch.cuda.device_count(), 4)
+    if n < 2:
+        pytest.skip("needs two GPUs")
+    cfg = R.FrameConfig.default(800, 600)
+    rs = [R.Renderer(d) for d in range(n)]
+    for r in rs:
+        r.all_to_gpu(scene_mid)
+    gs = [R.Group(rs[d], cfg, d, n, depth=2, views=True) for d in range(n)]
+    blobs = b"".join(g.export() for g in gs)
+    for g in gs:
+        g.connect(blobs)
+    cams = few_cameras(-100.0) + list(camera_grid(-100.0))[:7]
+    rounds = len(cams) // n
+    for rd in range(rounds):
+        maps = []
+        for d in range(n):
+            rm = R.RayMapGPU()
+            C.memmove(C.byref(rm), C.byref(R.RayMap(cfg).get_ray_map(*cams[rd * n + d])), 896)
+            maps.append(rm)
+        tickets = [gs[d].submit_view(maps[d], 0) for d in range(n)]
+        for d in range(n):
+            gs[d].wait(tickets[d])
+        ptr, stride = gs[0].views(tickets[0])
+        img0, _, _ = gs[0].image(tickets[0])
+        for d in range(n):
+            got = rs[0].download(img0 if d == 0 else ptr + d * stride, (cfg.height, cfg.width, 4), np.uint8)
+            want = _solo_frame(R, rs[0], maps[d], cfg)
+            assert np.array_equal(got, want), (rd, d)
+    for g in gs:
+        g.close()
+    for r in rs:
+        r.close()
