@@ -251,8 +251,8 @@ def main():
     ap.add_argument("--workload", default="imrodh1080p", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="rlerc", choices=["rlerc", "reference"])
     ap.add_argument("--lanes", type=int, default=0,
-                    help="traversal kernel (rlerc_set_lanes_per_ray): 0 = automatic (k_traverse_f, or k_traverse_p for small launches), "
-                         "65 = k_traverse_f, 68 = k_traverse_p, 1..32 = k_traverse<lanes>")
+                    help="traversal kernel (rlerc_set_lanes_per_ray): 0 = automatic (k_traverse_f; k_traverse_q for small launches rendered one at a time), "
+                         "65 = k_traverse_f, 69 = k_traverse_q, 68 = k_traverse_p, 1..32 = k_traverse<lanes>")
     ap.add_argument("--inflight", type=int, default=0,
                     help="frames in flight per GPU in the throughput measurements (0 = 8 on one GPU, 16 on several: a slice of a frame "
                          "is bound by its longest ray planes, not by the GPU, so the GPUs are kept busy by more frames in flight)")

@@ -143,10 +143,12 @@ int  rlerc_scene_share(rlerc_ctx* dst, const rlerc_ctx* src);
 /* Device-side Map4 table as main.cpp:277-278 copies it into the ray map (all levels). */
 int  rlerc_scene_device_maps(rlerc_ctx* c, rlerc_map4* out16, int* nummaps);
 /* Traversal kernel variant, all bit-identical: 0 = automatic (default): the production kernel k_traverse_f (one warp
- * per ray plane, column filter in front of the occlusion machinery), or k_traverse_p (a filter warp and a consume warp
- * per ray plane) when the launch has at most 12 ray planes per SM and is therefore bound by its longest ray planes
- * (multi-GPU slices, small windows); 65 = k_traverse_f always; 68 = k_traverse_p always (both run the DDA pre-pass
- * k_dda_states first); 1,2,4,8,16,32 = k_traverse<lanes> (lane <-> run; 1 is the reference's thread-per-ray scheme).
+ * per ray plane, column filter in front of the occlusion machinery), or k_traverse_q (four warps per ray plane: filter /
+ * project / resolve / shade) when the launch has at most 5 ray planes per SM, is rendered alone (no frames in flight)
+ * and is therefore bound by the serial chain of its longest ray planes (multi-GPU slices one frame at a time, small
+ * windows); 65 = k_traverse_f always; 69 = k_traverse_q always; 68 = k_traverse_p (two warps per ray plane) always
+ * (all run the DDA pre-pass k_dda_states first); 1,2,4,8,16,32 = k_traverse<lanes> (lane <-> run; 1 is the reference's
+ * thread-per-ray scheme).
  * Only in a library built with `make VARIANTS=1` (rlerc_has_variants() == 1; measured and rejected in round 1):
  * 64 = k_traverse_w (three-stage pipeline over all columns); 66, 67 = k_traverse_c (DDA in a dedicated warp). */
 int  rlerc_set_lanes_per_ray(rlerc_ctx* c, int lanes);
