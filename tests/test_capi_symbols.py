@@ -77,3 +77,28 @@ def test_header_is_plain_c99_and_links(tmp_path):
     subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", exe,
                     "-L", pkg, "-lrlerc", "-Wl,-rpath," + pkg], check=True)
     assert subprocess.run([exe]).returncode == 0
+
+
+def test_multi_gpu_and_streaming_entry_points_fail_loudly_on_bad_arguments(R):
+    """The round-2 additions to the C ABI (multi-GPU groups, rlerc_create_multi, LOD streaming) return a negative
+    rlerc_status with a message for bad arguments — before any CUDA call, so this runs without a GPU."""
+    lib = R.lib()
+    m = C.c_void_p()
+    devs = (C.c_int * 2)(0, 0)
+    assert lib.rlerc_create_multi(devs, 2, C.byref(m)) == -1 and b"twice" in lib.rlerc_last_error()
+    assert lib.rlerc_create_multi(devs, 0, C.byref(m)) == -1
+    assert lib.rlerc_create_multi(devs, 9, C.byref(m)) == -1
+    assert lib.rlerc_multi_count(None) == 0 and not lib.rlerc_multi_ctx(None, 0)
+    assert lib.rlerc_multi_frame_wait(None, 0) < 0
+    g = C.c_void_p()
+    cfg = R.FrameConfig.default(640, 480)
+    assert lib.rlerc_group_create(None, 0, 2, 4, 32, C.byref(cfg), C.byref(g)) == -1
+    assert lib.rlerc_group_submit(None, None, 0, None) == -1
+    assert lib.rlerc_group_submit_view(None, None, 0, None) == -1
+    assert lib.rlerc_group_export(None, None) == -1 and lib.rlerc_group_connect(None, None) == -1
+    assert lib.rlerc_group_wait(None, 0) == -1 and lib.rlerc_group_enable_views(None) == -1
+    f3 = (C.c_float * 3)(0, 0, 0)
+    assert lib.rlerc_stream_prepare(None, f3, f3, C.byref(cfg), 0, None) == -1
+    assert lib.rlerc_scene_upload_streamed(None, None) == -1
+    assert lib.rlerc_legacy_adopt(None, C.byref(cfg)) == -1
+    assert R.GROUP_BLOB_BYTES == 384        # RLERC_GROUP_BLOB_BYTES
