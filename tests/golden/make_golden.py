@@ -46,9 +46,10 @@ def main():
             port, ids, cnt = rb.orc_render(orm, cfg.render_size, cfg.rays_casted, cfg.mip_distance, cfg.z_far, want_ids=True)
             assert np.array_equal(warp, port)
             rgba = rb.orc_unwarp(orm, W, H, cfg.render_size, cfg.rays_casted, cfg.rays_casted_res, warp)
+            rgba_2xaa = rb.orc_unwarp(orm, W, H, cfg.render_size, cfg.rays_casted, cfg.rays_casted_res, warp, shader=1)
             case["frames"].append({"pos": list(pos), "rot": list(rot), "raymap_sha": sha(np.frombuffer(bytes(ref_rm), np.uint8)),
                                    "rays": ref_rm.map_line_count, "warp_sha": sha(warp), "ids_sha": sha(ids),
-                                   "rgba_sha": sha(rgba), "pixels": cnt["pixels"]})
+                                   "rgba_sha": sha(rgba), "rgba_2xaa_sha": sha(rgba_2xaa), "pixels": cnt["pixels"]})
         out["cases"][name] = case
     # one tiny raw vector: the first frame of the smallest case, rays 0..3
     name, kind, n, seed, h, (W, H) = CASES[0]

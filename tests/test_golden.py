@@ -31,6 +31,8 @@ def test_port_reproduces_golden(R, rb, name):
         assert cnt["pixels"] == fr["pixels"]
         rgba = rb.orc_unwarp(orm, W, H, cfg.render_size, cfg.rays_casted, cfg.rays_casted_res, warp)
         assert sha(rgba) == fr["rgba_sha"]
+        aa = rb.orc_unwarp(orm, W, H, cfg.render_size, cfg.rays_casted, cfg.rays_casted_res, warp, shader=1)
+        assert sha(aa) == fr["rgba_2xaa_sha"]            # colorize_buddha_soft_2xAA.frag restatement
 
 
 def test_raw_golden_rows(R, rb):
