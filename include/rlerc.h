@@ -301,7 +301,8 @@ typedef struct rlerc_stream_stats {
 } rlerc_stream_stats;
 /* Make resident what a frame at this camera can touch: of every mip level the z-rows within the distance the traversal
  * covers while it reads that level (Cuda_Render.h:343-367), plus margin_voxels of look-ahead (level-0 voxels); rows
- * beyond twice the margin are evicted.  Synchronous; call it between frames.  stats may be NULL. */
+ * beyond twice the margin are evicted (after waiting for everything in flight on the device, if anything is evicted).
+ * Synchronous.  stats may be NULL. */
 int  rlerc_stream_prepare(rlerc_ctx* c, const float pos[3], const float rot[3], const rlerc_frame_config* cfg,
                           int margin_voxels, rlerc_stream_stats* stats);
 

@@ -93,6 +93,7 @@ struct rlerc_streamed {
 	size_t chunk = RLERC_STREAM_CHUNK;
 	int device = 0;
 	uint64_t resident = 0, total = 0;
+	bool synced_for_unmap = false;            // per rlerc_stream_prepare call
 };
 
 namespace {
@@ -151,6 +152,9 @@ int range_apply(rlerc_streamed* st, Range& r, const std::vector<char>& need, con
 		}
 		else if (!need[k] && !keep[k] && r.chunk[k])
 		{
+			// nothing on this device may still be reading the chunk: frames in flight on other streams (rlerc_frame_submit,
+			// groups) included, so the first eviction of a call waits for the whole device
+			if (!st->synced_for_unmap) { cudaDeviceSynchronize(); st->synced_for_unmap = true; }
 			CKD(drv().memUnmap(r.va + off, st->chunk));
 			CKD(drv().memRelease(r.chunk[k]));
 			r.chunk[k] = 0;
@@ -285,8 +289,8 @@ int rlerc_stream_prepare(rlerc_ctx* c, const float pos[3], const float rot[3], c
 		const long long r = z_end + (2ll << nsw) + 2;
 		if (r > reach[mip]) reach[mip] = r;
 	}
-	// nothing that is still in use may be unmapped
 	CK(cudaStreamSynchronize(c->stream));
+	st->synced_for_unmap = false;
 	const double cz = (double)pos[2];
 	for (int m = 0; m < n; m++)
 	{
